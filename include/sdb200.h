@@ -1,0 +1,198 @@
+/* sdb200.h -- C-ABI of libsdb200.so: the B200 (sm_100a) implementation of the data-parallel hot path of
+ * leohuang2013/pyannote-audio_speaker-diarization_cpp.
+ *
+ * The reference has no plugin / FFI layer: its boundary is the C++ function-level API of
+ * pipeline/src/speakerDiarizer.cpp (SD) and pipeline/src/clustering/clustering.h (CL).  Each entry point
+ * below names the reference function it replaces (file:line relative to the reference checkout).  The C++
+ * host shim `host/sdb200_host.hpp` rebuilds the reference's nested-std::vector signatures on top of these,
+ * so speakerDiarization() (SD:2937) can call them unchanged.
+ *
+ * Conventions
+ *  - plain pointers and sizes, caller-owned row-major buffers, no exceptions across the ABI;
+ *  - every function returns an sd_status (0 = OK); sd_last_error() gives the message;
+ *  - `*_dev` variants take DEVICE pointers and only enqueue work on the context's stream (no sync);
+ *    the un-suffixed variants take HOST pointers and include H2D, kernels, D2H and a stream sync;
+ *  - one sd_ctx per host thread and GPU (the reference is single-threaded and non-re-entrant);
+ *  - there is no CPU fallback: without a CUDA device sd_ctx_create fails with SD_ERR_CUDA.
+ */
+#ifndef SDB200_H_
+#define SDB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDB200_VERSION 100
+
+typedef struct sd_ctx sd_ctx;
+
+typedef enum sd_status {
+    SD_OK = 0,
+    SD_ERR_INVALID = 1,        /* bad argument (NULL, non-positive size, ...) */
+    SD_ERR_CUDA = 2,           /* CUDA runtime / driver failure, or no device */
+    SD_ERR_ZERO_MAGNITUDE = 3, /* reference throws std::runtime_error("Vectors have zero magnitude.") SD:493-495 */
+    SD_ERR_UNSUPPORTED = 4,    /* parameter combination the reference itself does not implement */
+    SD_ERR_NOMEM = 5,
+    SD_ERR_CAPACITY = 6        /* caller buffer too small; required size reported through the out-param */
+} sd_status;
+
+/* SlidingWindow POD, SD:1029-1036 */
+typedef struct sd_window {
+    double start;
+    double step;
+    double duration;
+    int64_t num_samples;
+} sd_window;
+
+/* ---- context / memory / timing ------------------------------------------------------------------ */
+int sd_version(void);
+int sd_ctx_create(int device, sd_ctx** out);
+void sd_ctx_destroy(sd_ctx* ctx);
+const char* sd_last_error(const sd_ctx* ctx);
+/* Adopt an existing cudaStream_t (e.g. the framework's current stream); NULL restores the private stream. */
+int sd_ctx_set_stream(sd_ctx* ctx, void* cuda_stream);
+void* sd_ctx_stream(sd_ctx* ctx);
+int sd_sync(sd_ctx* ctx);
+int sd_malloc(sd_ctx* ctx, size_t bytes, void** dptr);
+int sd_free(sd_ctx* ctx, void* dptr);
+int sd_host_alloc(sd_ctx* ctx, size_t bytes, void** hptr); /* pinned */
+int sd_host_free(sd_ctx* ctx, void* hptr);
+int sd_memcpy_h2d(sd_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on the ctx stream */
+int sd_memcpy_d2h(sd_ctx* ctx, void* dst, const void* src, size_t bytes);
+int sd_memset(sd_ctx* ctx, void* dst, int value, size_t bytes);
+/* CUDA-event timers recorded on the ctx stream (slot 0..15). */
+int sd_timer_start(sd_ctx* ctx, int slot);
+int sd_timer_stop(sd_ctx* ctx, int slot);
+int sd_timer_elapsed_ms(sd_ctx* ctx, int slot, float* ms); /* synchronises on the stop event */
+/* Number of kernels of this library launched on this ctx since creation. */
+int64_t sd_launch_count(const sd_ctx* ctx);
+/* Write `bytes` of zeros into a scratch buffer larger than L2 (benchmark hygiene). */
+int sd_flush_l2(sd_ctx* ctx);
+
+/* ---- a1/a2: STFT front-end of the embedding stage ------------------------------------------------
+ * Replaces EmbeddingModel1::infer (SD:1977-2036) up to the tensor handed to emd4.onnx, and the packing
+ * of EmbeddingModel1::_infer (SD:1889-1917): centre zero padding n_fft/2, periodic Hamming window,
+ * n_fft-point real DFT, one-sided, un-normalised, layout [B][T][n_fft/2+1][{re,im}] fp32, T = 1 + L/hop. */
+typedef enum sd_window_kind { SD_WINDOW_HAMMING_PERIODIC = 0, SD_WINDOW_POVEY = 1, SD_WINDOW_CUSTOM = 2 } sd_window_kind;
+
+typedef struct sd_stft_params {
+    int n_fft;          /* 400 (the only size with a kernel today) */
+    int hop;            /* 160 */
+    int window_kind;    /* sd_window_kind */
+    const float* window; /* HOST pointer to n_fft floats when SD_WINDOW_CUSTOM, else NULL */
+    float preemph;      /* 0 = off (reference); 0.97 = Kaldi-style per-frame pre-emphasis */
+    int pad_batch_to;   /* 32 reproduces _infer's fixed batch (rows >= B are zero); 0 = no padding */
+} sd_stft_params;
+
+void sd_stft_default_params(sd_stft_params* p);
+int64_t sd_stft_num_frames(int L, int hop);
+/* out must hold max(B, pad_batch_to) * T * (n_fft/2+1) * 2 floats. */
+int sd_stft(sd_ctx* ctx, const float* wav, int B, int L, const sd_stft_params* p, float* out);
+int sd_stft_dev(sd_ctx* ctx, const float* d_wav, int B, int L, const sd_stft_params* p, float* d_out);
+/* wav_lens packing of _infer (SD:1899-1900): copy n_lens values, remaining rows 1.0 (host only, trivial). */
+int sd_pack_wav_lens(const float* lens, int n_lens, int batch, float* out);
+
+/* ---- a3: fused |X|^2 -> mel -> dB -> top_db -> mean-norm (executes inside emd4.onnx in the reference;
+ * spec: embeddings/threeModel.py:212-221, 333-396).  out[B][T][n_mels] fp32.  Optional product. */
+typedef struct sd_fbank_params {
+    sd_stft_params stft;
+    int n_mels;        /* 80 */
+    float f_min;       /* 0 */
+    float f_max;       /* 8000 */
+    int sample_rate;   /* 16000 */
+    float top_db;      /* 80 */
+    float amin;        /* 1e-10 */
+    int mean_norm;     /* 1 */
+} sd_fbank_params;
+void sd_fbank_default_params(sd_fbank_params* p);
+int sd_fbank(sd_ctx* ctx, const float* wav, int B, int L, const float* wav_lens, const sd_fbank_params* p, float* out);
+int sd_fbank_dev(sd_ctx* ctx, const float* d_wav, int B, int L, const float* d_wav_lens, const sd_fbank_params* p,
+                 float* d_out);
+
+/* ---- a4/a5: sliding-window aggregation ------------------------------------------------------------
+ * Replaces PipelineHelper::aggregate (SD:1167-1311), SlidingWindow::closest_frame (SD:1084-1090) and
+ * Helper::np_rint (SD:260-272). */
+int sd_np_rint(double v);
+int64_t sd_closest_frame(const sd_window* w, double t);
+/* number of output frames for C chunks: closest_frame(start + duration + (C-1)*step) + 1, SD:1232-1234 */
+int64_t sd_aggregate_num_frames(int C, const sd_window* chunks, const sd_window* frames);
+/* scores[C][F][K] fp64 (NaN = missing) -> out[num_frames][K].  hamming != 0 weights each chunk with
+ * np.hamming(F) (the reference asserts "not implemented", SD:1214; pyannote semantics).
+ * count_out / mask_out (optional, [num_frames][K]) are overlapping_chunk_count / aggregated_mask (SD:1241-1245).
+ * cap_rows = rows available in out; *num_frames receives the row count (SD_ERR_CAPACITY if too small). */
+int sd_aggregate(sd_ctx* ctx, const double* scores, int C, int F, int K, const sd_window* chunks,
+                 const sd_window* frames, int hamming, double missing, int skip_average, double epsilon, double* out,
+                 int64_t cap_rows, int64_t* num_frames, sd_window* post_frames, double* count_out, double* mask_out);
+int sd_aggregate_dev(sd_ctx* ctx, const double* d_scores, int C, int F, int K, const sd_window* chunks,
+                     const sd_window* frames, int hamming, double missing, int skip_average, double epsilon,
+                     double* d_out, int64_t cap_rows, int64_t* num_frames, sd_window* post_frames, double* d_count_out,
+                     double* d_mask_out);
+
+/* ---- a6/a7: binarisation, trim, speaker count, clean ---------------------------------------------
+ * sd_binarize        : SegmentModel::binarize_swf (SD:1506-1563)  scores[C][F][K] fp32 -> out[C][F][K] fp64 {0,1}
+ * sd_binarize_rows   : SegmentModel::binarize_ndarray (SD:1565-1639) scores[R][F] fp64 -> out[R][F] uint8
+ * sd_trim            : SegmentModel::trim (SD:1742-1782)
+ * sd_speaker_count   : SegmentModel::speaker_count (SD:1665-1738): trim 10%/10% -> sum_k -> aggregate -> rint
+ * sd_clean_segmentations : Helper::cleanSegmentations (SD:710-743) */
+int sd_binarize(sd_ctx* ctx, const float* scores, int C, int F, int K, double onset, int initial_state, double* out);
+int sd_binarize_dev(sd_ctx* ctx, const float* d_scores, int C, int F, int K, double onset, int initial_state,
+                    double* d_out);
+int sd_binarize_rows(sd_ctx* ctx, const double* scores, int R, int F, double onset, int initial_state, uint8_t* out);
+int64_t sd_trim_num_frames(int F, double left, double right);
+int sd_trim(sd_ctx* ctx, const double* binarized, int C, int F, int K, double left, double right,
+            const sd_window* before, double* out, sd_window* trimmed_frames);
+int sd_speaker_count(sd_ctx* ctx, const double* binarized, int C, int F, int K, const sd_window* chunks,
+                     const sd_window* frames, int32_t* out, int64_t cap, int64_t* n_out, sd_window* count_frames);
+int sd_speaker_count_dev(sd_ctx* ctx, const double* d_binarized, int C, int F, int K, const sd_window* chunks,
+                         const sd_window* frames, int32_t* d_out, int64_t cap, int64_t* n_out, sd_window* count_frames);
+int sd_clean_segmentations(sd_ctx* ctx, const double* binarized, int C, int F, int K, double* out);
+
+/* ---- a9-a12: clustering library --------------------------------------------------------------------
+ * sd_normalize   : Helper::normalizeEmbeddings (SD:330-357)   in place, x[N][D]
+ * sd_pdist       : pdist of Clustering::linkage (CL:408-431)  condensed fp64, N(N-1)/2
+ * sd_linkage     : Clustering::linkage (CL:417-440) = pdist + fast_linkage (CL:289-406); Z[(N-1)][4]
+ * sd_fcluster    : Clustering::fcluster (CL:442-457), criterion "distance"; T[N] labels 1..K
+ * sd_cluster     : Clustering::cluster (CL:459-468)
+ * sd_cosine_cdist: Helper::cosineSimilarity (SD:502-516), out[na][nb] */
+typedef enum sd_pdist_mode {
+    SD_PDIST_EXACT_F64 = 0, /* parity mode: fp64, sequential k, no FMA -> bit-identical to the reference */
+    SD_PDIST_GEMM_TF32X3 = 1 /* tcgen05 Gram GEMM with 3xTF32 split precision; |err| evidenced in DESIGN.md */
+} sd_pdist_mode;
+int sd_normalize(sd_ctx* ctx, double* x, int N, int D);
+int sd_pdist(sd_ctx* ctx, const double* x, int N, int D, int mode, double* condensed);
+int sd_linkage(sd_ctx* ctx, const double* x, int N, int D, double* Z);
+int sd_linkage_dev(sd_ctx* ctx, const double* d_x, int N, int D, double* d_Z);
+int sd_fcluster(sd_ctx* ctx, const double* Z, int N, double cutoff, int32_t* T);
+int sd_cluster(sd_ctx* ctx, const double* x, int N, int D, double cutoff, int32_t* T);
+int sd_cosine_cdist(sd_ctx* ctx, const double* a, int na, const double* b, int nb, int D, double* out);
+
+/* ---- a8/a13/a14/a15: clustering driver -----------------------------------------------------------
+ * sd_cluster_labels : Cluster::cluster (SD:2300-2422) on already-filtered embeddings x[N][D] -> labels[N]
+ * sd_clustering     : Cluster::clustering (SD:2063-2116) = filter_embeddings (SD:2214) + set_num_clusters
+ *                     (SD:2261) + cluster + assign_embeddings (SD:2120-2212), then, when binarized != NULL,
+ *                     the inactive-speaker mask of SD:3166-3191 (hard = -2).
+ *   embeddings[C][S][D] fp64, a row whose first element is NaN is absent;  hard[C][S];
+ *   soft (optional) [C][S][soft_k_cap] receives 2 - cosine distance to each centroid. */
+typedef struct sd_cluster_params {
+    float threshold;       /* Cluster::m_threshold, a float: 0.7153814381597874f (SD:2049) */
+    int min_cluster_size;  /* 15 (SD:2050) */
+    int num_clusters;      /* -1; anything else is "not implemented" in the reference (SD:2368-2369) */
+    int min_clusters;      /* -1 */
+    int max_clusters;      /* -1 */
+    int pdist_mode;        /* sd_pdist_mode */
+} sd_cluster_params;
+void sd_cluster_default_params(sd_cluster_params* p);
+int sd_cluster_labels(sd_ctx* ctx, const double* x, int N, int D, const sd_cluster_params* p, int32_t* labels);
+int sd_clustering(sd_ctx* ctx, const double* embeddings, int C, int S, int D, const sd_cluster_params* p,
+                  const double* binarized, int F, int32_t* hard, double* soft, int soft_k_cap, int* num_clusters);
+int sd_clustering_dev(sd_ctx* ctx, const double* d_embeddings, int C, int S, int D, const sd_cluster_params* p,
+                      const double* d_binarized, int F, int32_t* d_hard, double* d_soft, int soft_k_cap,
+                      int* num_clusters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDB200_H_ */

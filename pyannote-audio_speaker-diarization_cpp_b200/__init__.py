@@ -1,0 +1,438 @@
+"""ctypes binding of libsdb200.so -- the B200 (sm_100a) hot path of the C++ pyannote diarization pipeline.
+
+The product is the C-ABI library (include/sdb200.h) plus the C++ host shim (host/sdb200_host.hpp) that keeps the
+reference's function-level API.  This module is the thin Python face used by tests/ and bench.py; method names
+follow the reference functions they stand in for.  There is no CPU fallback: if the library or a CUDA device is
+missing, construction fails loudly.
+
+The directory name contains '-', so import it by path (see __graft_entry__.load_package()).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsdb200.so")
+
+c_fp = C.POINTER(C.c_float)
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+c_lp = C.POINTER(C.c_int64)
+c_bp = C.POINTER(C.c_uint8)
+
+SD_OK, SD_ERR_INVALID, SD_ERR_CUDA, SD_ERR_ZERO_MAGNITUDE, SD_ERR_UNSUPPORTED, SD_ERR_NOMEM, SD_ERR_CAPACITY = range(7)
+
+# constants of the reference pipeline (speakerDiarizer.cpp:1335-1340, 2049-2050, 2429-2432)
+FRAME_STEP = 0.016875
+FRAME_DURATION = 0.016875
+ONSET = 0.4442333667381752
+EPS = float(np.finfo(np.float64).eps)
+
+
+class Window(C.Structure):
+    """SlidingWindow POD (speakerDiarizer.cpp:1029-1036)."""
+    _fields_ = [("start", C.c_double), ("step", C.c_double), ("duration", C.c_double), ("num_samples", C.c_int64)]
+
+    def astuple(self):
+        return (self.start, self.step, self.duration, self.num_samples)
+
+
+class StftParams(C.Structure):
+    _fields_ = [("n_fft", C.c_int), ("hop", C.c_int), ("window_kind", C.c_int), ("window", c_fp),
+                ("preemph", C.c_float), ("pad_batch_to", C.c_int)]
+
+
+class FbankParams(C.Structure):
+    _fields_ = [("stft", StftParams), ("n_mels", C.c_int), ("f_min", C.c_float), ("f_max", C.c_float),
+                ("sample_rate", C.c_int), ("top_db", C.c_float), ("amin", C.c_float), ("mean_norm", C.c_int)]
+
+
+class ClusterParams(C.Structure):
+    _fields_ = [("threshold", C.c_float), ("min_cluster_size", C.c_int), ("num_clusters", C.c_int),
+                ("min_clusters", C.c_int), ("max_clusters", C.c_int), ("pdist_mode", C.c_int)]
+
+
+class SdError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("sdb200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+EXPORTS = [
+    "sd_version", "sd_ctx_create", "sd_ctx_destroy", "sd_last_error", "sd_ctx_set_stream", "sd_ctx_stream", "sd_sync",
+    "sd_malloc", "sd_free", "sd_host_alloc", "sd_host_free", "sd_memcpy_h2d", "sd_memcpy_d2h", "sd_memset",
+    "sd_timer_start", "sd_timer_stop", "sd_timer_elapsed_ms", "sd_launch_count", "sd_flush_l2",
+    "sd_stft_default_params", "sd_stft_num_frames", "sd_stft", "sd_stft_dev", "sd_pack_wav_lens",
+    "sd_fbank_default_params", "sd_fbank", "sd_fbank_dev", "sd_np_rint", "sd_closest_frame", "sd_aggregate_num_frames",
+    "sd_aggregate", "sd_aggregate_dev", "sd_binarize", "sd_binarize_dev", "sd_binarize_rows", "sd_trim_num_frames",
+    "sd_trim", "sd_speaker_count", "sd_speaker_count_dev", "sd_clean_segmentations", "sd_normalize", "sd_pdist",
+    "sd_linkage", "sd_linkage_dev", "sd_fcluster", "sd_cluster", "sd_cosine_cdist", "sd_cluster_default_params",
+    "sd_cluster_labels", "sd_clustering", "sd_clustering_dev",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libsdb200.so (built by __graft_entry__.build() / `make` in this directory)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libsdb200.so is missing (%s): build it with `make -C %s`; there is no fallback path"
+                           % (LIB_PATH, HERE))
+    L = C.CDLL(LIB_PATH)
+    vp, i, d, i64, sz = C.c_void_p, C.c_int, C.c_double, C.c_int64, C.c_size_t
+    W = C.POINTER(Window)
+    sig = {
+        "sd_version": (i, []),
+        "sd_ctx_create": (i, [i, C.POINTER(vp)]),
+        "sd_ctx_destroy": (None, [vp]),
+        "sd_last_error": (C.c_char_p, [vp]),
+        "sd_ctx_set_stream": (i, [vp, vp]),
+        "sd_ctx_stream": (vp, [vp]),
+        "sd_sync": (i, [vp]),
+        "sd_malloc": (i, [vp, sz, C.POINTER(vp)]),
+        "sd_free": (i, [vp, vp]),
+        "sd_host_alloc": (i, [vp, sz, C.POINTER(vp)]),
+        "sd_host_free": (i, [vp, vp]),
+        "sd_memcpy_h2d": (i, [vp, vp, vp, sz]),
+        "sd_memcpy_d2h": (i, [vp, vp, vp, sz]),
+        "sd_memset": (i, [vp, vp, i, sz]),
+        "sd_timer_start": (i, [vp, i]),
+        "sd_timer_stop": (i, [vp, i]),
+        "sd_timer_elapsed_ms": (i, [vp, i, c_fp]),
+        "sd_launch_count": (i64, [vp]),
+        "sd_flush_l2": (i, [vp]),
+        "sd_stft_default_params": (None, [C.POINTER(StftParams)]),
+        "sd_stft_num_frames": (i64, [i, i]),
+        "sd_stft": (i, [vp, vp, i, i, C.POINTER(StftParams), vp]),
+        "sd_stft_dev": (i, [vp, vp, i, i, C.POINTER(StftParams), vp]),
+        "sd_pack_wav_lens": (i, [c_fp, i, i, c_fp]),
+        "sd_fbank_default_params": (None, [C.POINTER(FbankParams)]),
+        "sd_fbank": (i, [vp, vp, i, i, vp, C.POINTER(FbankParams), vp]),
+        "sd_fbank_dev": (i, [vp, vp, i, i, vp, C.POINTER(FbankParams), vp]),
+        "sd_np_rint": (i, [d]),
+        "sd_closest_frame": (i64, [W, d]),
+        "sd_aggregate_num_frames": (i64, [i, W, W]),
+        "sd_aggregate": (i, [vp, vp, i, i, i, W, W, i, d, i, d, vp, i64, c_lp, W, vp, vp]),
+        "sd_aggregate_dev": (i, [vp, vp, i, i, i, W, W, i, d, i, d, vp, i64, c_lp, W, vp, vp]),
+        "sd_binarize": (i, [vp, vp, i, i, i, d, i, vp]),
+        "sd_binarize_dev": (i, [vp, vp, i, i, i, d, i, vp]),
+        "sd_binarize_rows": (i, [vp, vp, i, i, d, i, vp]),
+        "sd_trim_num_frames": (i64, [i, d, d]),
+        "sd_trim": (i, [vp, vp, i, i, i, d, d, W, vp, W]),
+        "sd_speaker_count": (i, [vp, vp, i, i, i, W, W, vp, i64, c_lp, W]),
+        "sd_speaker_count_dev": (i, [vp, vp, i, i, i, W, W, vp, i64, c_lp, W]),
+        "sd_clean_segmentations": (i, [vp, vp, i, i, i, vp]),
+        "sd_normalize": (i, [vp, vp, i, i]),
+        "sd_pdist": (i, [vp, vp, i, i, i, vp]),
+        "sd_linkage": (i, [vp, vp, i, i, vp]),
+        "sd_linkage_dev": (i, [vp, vp, i, i, vp]),
+        "sd_fcluster": (i, [vp, vp, i, d, vp]),
+        "sd_cluster": (i, [vp, vp, i, i, d, vp]),
+        "sd_cosine_cdist": (i, [vp, vp, i, vp, i, i, vp]),
+        "sd_cluster_default_params": (None, [C.POINTER(ClusterParams)]),
+        "sd_cluster_labels": (i, [vp, vp, i, i, C.POINTER(ClusterParams), vp]),
+        "sd_clustering": (i, [vp, vp, i, i, i, C.POINTER(ClusterParams), vp, i, vp, vp, i, c_ip]),
+        "sd_clustering_dev": (i, [vp, vp, i, i, i, C.POINTER(ClusterParams), vp, i, vp, vp, i, c_ip]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _win(w):
+    if isinstance(w, Window):
+        return w
+    return Window(float(w[0]), float(w[1]), float(w[2]), int(w[3]) if len(w) > 3 else 0)
+
+
+FRAMES = (0.0, FRAME_STEP, FRAME_DURATION, 0)
+
+
+class Context:
+    """One sd_ctx (one GPU, one stream).  Host-array methods mirror the reference's function names."""
+
+    def __init__(self, device=0):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.sd_ctx_create(device, C.byref(h))
+        if rc != SD_OK:
+            raise SdError(rc, "sd_ctx_create(device=%d) failed: no usable CUDA device (no CPU fallback exists)" % device)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sd_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != SD_OK:
+            raise SdError(rc, self.L.sd_last_error(self.h).decode())
+
+    # ---- plumbing
+    def sync(self):
+        self._check(self.L.sd_sync(self.h))
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.L.sd_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def malloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(self.L.sd_malloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def free(self, dptr):
+        self._check(self.L.sd_free(self.h, C.c_void_p(dptr)))
+
+    def host_alloc(self, shape, dtype):
+        """Pinned host array."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        self._check(self.L.sd_host_alloc(self.h, n, C.byref(p)))
+        buf = (C.c_char * n).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+        return arr
+
+    def h2d(self, dptr, arr):
+        arr = np.ascontiguousarray(arr)
+        self._check(self.L.sd_memcpy_h2d(self.h, C.c_void_p(dptr), _ptr(arr), arr.nbytes))
+        return arr  # keep alive until sync
+
+    def d2h(self, arr, dptr):
+        self._check(self.L.sd_memcpy_d2h(self.h, _ptr(arr), C.c_void_p(dptr), arr.nbytes))
+
+    def to_device(self, arr):
+        arr = np.ascontiguousarray(arr)
+        d = self.malloc(arr.nbytes)
+        self.h2d(d, arr)
+        self.sync()
+        return d
+
+    def timer_start(self, slot=0):
+        self._check(self.L.sd_timer_start(self.h, slot))
+
+    def timer_stop(self, slot=0):
+        self._check(self.L.sd_timer_stop(self.h, slot))
+
+    def timer_ms(self, slot=0):
+        ms = C.c_float()
+        self._check(self.L.sd_timer_elapsed_ms(self.h, slot, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return self.L.sd_launch_count(self.h)
+
+    def flush_l2(self):
+        self._check(self.L.sd_flush_l2(self.h))
+
+    # ---- a1/a2
+    def stft_params(self, pad_batch_to=0, window=None, window_kind=0):
+        p = StftParams()
+        self.L.sd_stft_default_params(C.byref(p))
+        p.pad_batch_to = pad_batch_to
+        p.window_kind = window_kind
+        if window is not None:
+            self._win_keep = np.ascontiguousarray(window, np.float32)
+            p.window_kind = 2
+            p.window = self._win_keep.ctypes.data_as(c_fp)
+        return p
+
+    def stft(self, wav, pad_batch_to=0, window=None, window_kind=0):
+        """EmbeddingModel1::infer up to the ORT input: [max(B,pad)][T][201][2] fp32."""
+        wav = np.ascontiguousarray(wav, np.float32)
+        B, Ls = wav.shape
+        p = self.stft_params(pad_batch_to, window, window_kind)
+        T = self.L.sd_stft_num_frames(Ls, p.hop)
+        out = np.empty((max(B, pad_batch_to), T, p.n_fft // 2 + 1, 2), np.float32)
+        self._check(self.L.sd_stft(self.h, _ptr(wav), B, Ls, C.byref(p), _ptr(out)))
+        return out
+
+    def stft_dev(self, d_wav, B, Ls, d_out, p=None):
+        if p is None:
+            p = self.stft_params()
+        self._check(self.L.sd_stft_dev(self.h, C.c_void_p(d_wav), B, Ls, C.byref(p), C.c_void_p(d_out)))
+
+    def pack_wav_lens(self, lens, batch=32):
+        lens = np.ascontiguousarray(lens, np.float32)
+        out = np.empty(batch, np.float32)
+        rc = self.L.sd_pack_wav_lens(lens.ctypes.data_as(c_fp), lens.shape[0], batch, out.ctypes.data_as(c_fp))
+        if rc:
+            raise SdError(rc, "sd_pack_wav_lens")
+        return out
+
+    def fbank_params(self):
+        p = FbankParams()
+        self.L.sd_fbank_default_params(C.byref(p))
+        return p
+
+    def fbank(self, wav, wav_lens, params=None):
+        wav = np.ascontiguousarray(wav, np.float32)
+        wav_lens = np.ascontiguousarray(wav_lens, np.float32)
+        B, Ls = wav.shape
+        p = params or self.fbank_params()
+        T = self.L.sd_stft_num_frames(Ls, p.stft.hop)
+        out = np.empty((B, T, p.n_mels), np.float32)
+        self._check(self.L.sd_fbank(self.h, _ptr(wav), B, Ls, _ptr(wav_lens), C.byref(p), _ptr(out)))
+        return out
+
+    # ---- a4/a5
+    def np_rint(self, v):
+        return self.L.sd_np_rint(float(v))
+
+    def closest_frame(self, t, window=FRAMES):
+        w = _win(window)
+        return self.L.sd_closest_frame(C.byref(w), float(t))
+
+    def aggregate(self, scores, chunks, frames=FRAMES, hamming=False, missing=np.nan, skip_average=False, epsilon=EPS,
+                  want_aux=False):
+        """PipelineHelper::aggregate.  chunks = (start, step, duration, num_samples)."""
+        scores = np.ascontiguousarray(scores, np.float64)
+        Cn, F, K = scores.shape
+        cw, fw = _win(chunks), _win(frames)
+        NF = self.L.sd_aggregate_num_frames(Cn, C.byref(cw), C.byref(fw))
+        out = np.empty((NF, K), np.float64)
+        cnt = np.empty((NF, K), np.float64) if want_aux else None
+        msk = np.empty((NF, K), np.float64) if want_aux else None
+        n = C.c_int64()
+        post = Window()
+        self._check(self.L.sd_aggregate(self.h, _ptr(scores), Cn, F, K, C.byref(cw), C.byref(fw), int(hamming),
+                                        float(missing), int(skip_average), float(epsilon), _ptr(out), NF, C.byref(n),
+                                        C.byref(post), _ptr(cnt), _ptr(msk)))
+        assert n.value == NF
+        if want_aux:
+            return out, post, cnt, msk
+        return out, post
+
+    # ---- a6/a7
+    def binarize_swf(self, scores, onset=ONSET, initial_state=False):
+        scores = np.ascontiguousarray(scores, np.float32)
+        Cn, F, K = scores.shape
+        out = np.empty((Cn, F, K), np.float64)
+        self._check(self.L.sd_binarize(self.h, _ptr(scores), Cn, F, K, float(onset), int(initial_state), _ptr(out)))
+        return out
+
+    def binarize_ndarray(self, scores, onset=0.5, initial_state=False):
+        scores = np.ascontiguousarray(scores, np.float64)
+        R, F = scores.shape
+        out = np.empty((R, F), np.uint8)
+        self._check(self.L.sd_binarize_rows(self.h, _ptr(scores), R, F, float(onset), int(initial_state), _ptr(out)))
+        return out
+
+    def trim(self, binarized, left=0.1, right=0.1, before=(0.0, 0.5, 5.0, 0)):
+        b = np.ascontiguousarray(binarized, np.float64)
+        Cn, F, K = b.shape
+        Ft = self.L.sd_trim_num_frames(F, left, right)
+        out = np.empty((Cn, Ft, K), np.float64)
+        bw = _win(before)
+        tw = Window()
+        self._check(self.L.sd_trim(self.h, _ptr(b), Cn, F, K, left, right, C.byref(bw), _ptr(out), C.byref(tw)))
+        return out, tw
+
+    def speaker_count(self, binarized, chunks=(0.0, 0.5, 5.0, 1), frames=FRAMES):
+        b = np.ascontiguousarray(binarized, np.float64)
+        Cn, F, K = b.shape
+        cw, fw = _win(chunks), _win(frames)
+        cap = int((Cn * cw.step + cw.duration) / fw.step) + F + 64
+        out = np.empty(cap, np.int32)
+        n = C.c_int64()
+        cf = Window()
+        self._check(self.L.sd_speaker_count(self.h, _ptr(b), Cn, F, K, C.byref(cw), C.byref(fw), _ptr(out), cap,
+                                            C.byref(n), C.byref(cf)))
+        return out[:n.value].copy(), cf
+
+    def clean_segmentations(self, binarized):
+        b = np.ascontiguousarray(binarized, np.float64)
+        out = np.empty_like(b)
+        self._check(self.L.sd_clean_segmentations(self.h, _ptr(b), b.shape[0], b.shape[1], b.shape[2], _ptr(out)))
+        return out
+
+    # ---- a9-a12
+    def normalize_embeddings(self, x):
+        x = np.ascontiguousarray(x, np.float64).copy()
+        self._check(self.L.sd_normalize(self.h, _ptr(x), x.shape[0], x.shape[1]))
+        return x
+
+    def pdist(self, x, mode=0):
+        x = np.ascontiguousarray(x, np.float64)
+        N = x.shape[0]
+        out = np.empty(N * (N - 1) // 2, np.float64)
+        self._check(self.L.sd_pdist(self.h, _ptr(x), N, x.shape[1], mode, _ptr(out)))
+        return out
+
+    def linkage(self, x):
+        x = np.ascontiguousarray(x, np.float64)
+        Z = np.empty((x.shape[0] - 1, 4), np.float64)
+        self._check(self.L.sd_linkage(self.h, _ptr(x), x.shape[0], x.shape[1], _ptr(Z)))
+        return Z
+
+    def fcluster(self, Z, cutoff):
+        Z = np.ascontiguousarray(Z, np.float64)
+        N = Z.shape[0] + 1
+        T = np.empty(N, np.int32)
+        self._check(self.L.sd_fcluster(self.h, _ptr(Z), N, float(cutoff), _ptr(T)))
+        return T
+
+    def cluster(self, x, cutoff):
+        """Clustering::cluster (linkage + fcluster)."""
+        x = np.ascontiguousarray(x, np.float64)
+        T = np.empty(x.shape[0], np.int32)
+        self._check(self.L.sd_cluster(self.h, _ptr(x), x.shape[0], x.shape[1], float(cutoff), _ptr(T)))
+        return T
+
+    def cosine_cdist(self, a, b):
+        a = np.ascontiguousarray(a, np.float64)
+        b = np.ascontiguousarray(b, np.float64)
+        out = np.empty((a.shape[0], b.shape[0]), np.float64)
+        self._check(self.L.sd_cosine_cdist(self.h, _ptr(a), a.shape[0], _ptr(b), b.shape[0], a.shape[1], _ptr(out)))
+        return out
+
+    # ---- a8/a13-a15
+    def cluster_params(self, **kw):
+        p = ClusterParams()
+        self.L.sd_cluster_default_params(C.byref(p))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    def cluster_labels(self, x, params=None):
+        """Cluster::cluster on filtered embeddings."""
+        x = np.ascontiguousarray(x, np.float64)
+        p = params or self.cluster_params()
+        lab = np.empty(x.shape[0], np.int32)
+        self._check(self.L.sd_cluster_labels(self.h, _ptr(x), x.shape[0], x.shape[1], C.byref(p), _ptr(lab)))
+        return lab
+
+    def clustering(self, embeddings, binarized=None, params=None, soft_k_cap=0):
+        """Cluster::clustering (+ inactive-speaker mask when `binarized` is given) -> hard[C][S]."""
+        e = np.ascontiguousarray(embeddings, np.float64)
+        Cn, S, D = e.shape
+        p = params or self.cluster_params()
+        hard = np.empty((Cn, S), np.int32)
+        soft = np.empty((Cn, S, soft_k_cap), np.float64) if soft_k_cap else None
+        F = 0
+        if binarized is not None:
+            binarized = np.ascontiguousarray(binarized, np.float64)
+            F = binarized.shape[1]
+        k = C.c_int(0)
+        self._check(self.L.sd_clustering(self.h, _ptr(e), Cn, S, D, C.byref(p), _ptr(binarized), F, _ptr(hard),
+                                         _ptr(soft), soft_k_cap, C.byref(k)))
+        if soft_k_cap:
+            return hard, soft, k.value
+        return hard, k.value

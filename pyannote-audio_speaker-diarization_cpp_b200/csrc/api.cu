@@ -1,0 +1,750 @@
+// C-ABI of libsdb200.so (see include/sdb200.h).  Host-pointer entry points = H2D + kernels + D2H + sync;
+// *_dev entry points enqueue on the context stream only.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+namespace sdb {
+int normalize_launch(sd_ctx* ctx, const double* d_x, int N, int D, double* d_xn);
+int pdist_condensed_launch(sd_ctx* ctx, const double* d_x, int N, int D, double* d_cond);
+int linkage_launch(sd_ctx* ctx, const double* d_x, int N, int D, double* d_Z);
+int fcluster_launch(sd_ctx* ctx, const double* d_Z, int N, double cutoff, int* d_T, int* d_num);
+int cosine_cdist_launch(sd_ctx* ctx, const double* d_a, int na, const double* d_b, int nb, int D, double* d_out);
+int cluster_labels_launch(sd_ctx* ctx, const double* d_x, int N, int D, const sd_cluster_params* p, int* d_labels,
+                          int* d_num);
+int clustering_launch(sd_ctx* ctx, const double* d_emb, int C, int S, int D, const std::vector<int>& h_keep,
+                      const sd_cluster_params* p, const double* d_binarized, int F, int* d_hard, double* d_soft,
+                      int soft_k_cap, int* num_clusters_out);
+int row_valid_launch(sd_ctx* ctx, const double* d_emb, int R, int D, unsigned char* d_valid);
+
+// Small host -> device parameter uploads go through a ring of pinned slots so that they are truly
+// asynchronous and the caller's buffer can be reused immediately.
+constexpr int kRingSlots = 16;
+constexpr size_t kRingSlotBytes = 256 * 1024;
+struct Ring {
+    char* base = nullptr;
+    cudaEvent_t ev[kRingSlots] = {};
+    int next = 0;
+};
+static Ring* ring_of(sd_ctx* ctx);
+
+int upload_small(sd_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+    Ring* r = ring_of(ctx);
+    if (!r || bytes > kRingSlotBytes) {  // large or no ring: plain (staged) copy
+        SD_CUDA(ctx, cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        if (!r) SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return SD_OK;
+    }
+    const int s = r->next;
+    r->next = (s + 1) % kRingSlots;
+    SD_CUDA(ctx, cudaEventSynchronize(r->ev[s]));
+    std::memcpy(r->base + (size_t)s * kRingSlotBytes, h_src, bytes);
+    SD_CUDA(ctx, cudaMemcpyAsync(d_dst, r->base + (size_t)s * kRingSlotBytes, bytes, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    SD_CUDA(ctx, cudaEventRecord(r->ev[s], ctx->stream));
+    return SD_OK;
+}
+}  // namespace sdb
+
+using namespace sdb;
+
+struct CtxExtra {
+    Ring ring;
+};
+static std::vector<std::pair<sd_ctx*, CtxExtra*>> g_extras;  // contexts are few; linear search is fine
+
+namespace sdb {
+static Ring* ring_of(sd_ctx* ctx) {
+    for (auto& e : g_extras)
+        if (e.first == ctx) return e.second->ring.base ? &e.second->ring : nullptr;
+    return nullptr;
+}
+}  // namespace sdb
+
+extern "C" {
+
+int sd_version(void) { return SDB200_VERSION; }
+
+int sd_ctx_create(int device, sd_ctx** out) {
+    if (!out) return SD_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+        cudaGetLastError();
+        return SD_ERR_CUDA;  // no CPU fallback by design
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return SD_ERR_CUDA;
+    sd_ctx* ctx = new sd_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+        ctx->num_sms = prop.multiProcessorCount;
+        ctx->l2_bytes = (size_t)prop.l2CacheSize;
+    }
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return SD_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    for (int i = 0; i < 16; ++i) {
+        cudaEventCreate(&ctx->ev_start[i]);
+        cudaEventCreate(&ctx->ev_stop[i]);
+    }
+    cudaMalloc(&ctx->d_status, sizeof(int));
+    cudaMemset(ctx->d_status, 0, sizeof(int));
+    cudaHostAlloc(&ctx->h_status, sizeof(int), cudaHostAllocDefault);
+    CtxExtra* ex = new CtxExtra();
+    if (cudaHostAlloc(&ex->ring.base, kRingSlots * kRingSlotBytes, cudaHostAllocDefault) == cudaSuccess) {
+        for (int i = 0; i < kRingSlots; ++i) cudaEventCreateWithFlags(&ex->ring.ev[i], cudaEventDisableTiming);
+    } else {
+        ex->ring.base = nullptr;
+        cudaGetLastError();
+    }
+    g_extras.emplace_back(ctx, ex);
+    *out = ctx;
+    return SD_OK;
+}
+
+void sd_ctx_destroy(sd_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->bufs)
+        if (b.p) cudaFree(b.p);
+    if (ctx->d_window) cudaFree(ctx->d_window);
+    if (ctx->d_twiddle) cudaFree(ctx->d_twiddle);
+    if (ctx->d_mel) cudaFree(ctx->d_mel);
+    if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    if (ctx->d_status) cudaFree(ctx->d_status);
+    if (ctx->h_status) cudaFreeHost(ctx->h_status);
+    for (int i = 0; i < 16; ++i) {
+        cudaEventDestroy(ctx->ev_start[i]);
+        cudaEventDestroy(ctx->ev_stop[i]);
+    }
+    for (size_t i = 0; i < g_extras.size(); ++i)
+        if (g_extras[i].first == ctx) {
+            CtxExtra* ex = g_extras[i].second;
+            if (ex->ring.base) {
+                for (int k = 0; k < kRingSlots; ++k) cudaEventDestroy(ex->ring.ev[k]);
+                cudaFreeHost(ex->ring.base);
+            }
+            delete ex;
+            g_extras.erase(g_extras.begin() + i);
+            break;
+        }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+const char* sd_last_error(const sd_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int sd_ctx_set_stream(sd_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return SD_ERR_INVALID;
+    cudaStreamSynchronize(ctx->stream);
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return SD_OK;
+}
+void* sd_ctx_stream(sd_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int sd_sync(sd_ctx* ctx) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+int sd_malloc(sd_ctx* ctx, size_t bytes, void** dptr) {
+    if (!ctx || !dptr) return SD_ERR_INVALID;
+    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return ctx->fail(SD_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    }
+    return SD_OK;
+}
+int sd_free(sd_ctx* ctx, void* dptr) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_CUDA(ctx, cudaFree(dptr));
+    return SD_OK;
+}
+int sd_host_alloc(sd_ctx* ctx, size_t bytes, void** hptr) {
+    if (!ctx || !hptr) return SD_ERR_INVALID;
+    cudaError_t e = cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return ctx->fail(SD_ERR_NOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    }
+    return SD_OK;
+}
+int sd_host_free(sd_ctx* ctx, void* hptr) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_CUDA(ctx, cudaFreeHost(hptr));
+    return SD_OK;
+}
+int sd_memcpy_h2d(sd_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return SD_OK;
+}
+int sd_memcpy_d2h(sd_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return SD_OK;
+}
+int sd_memset(sd_ctx* ctx, void* dst, int value, size_t bytes) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_CUDA(ctx, cudaMemsetAsync(dst, value, bytes, ctx->stream));
+    return SD_OK;
+}
+int sd_timer_start(sd_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 16) return SD_ERR_INVALID;
+    SD_CUDA(ctx, cudaEventRecord(ctx->ev_start[slot], ctx->stream));
+    return SD_OK;
+}
+int sd_timer_stop(sd_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= 16) return SD_ERR_INVALID;
+    SD_CUDA(ctx, cudaEventRecord(ctx->ev_stop[slot], ctx->stream));
+    return SD_OK;
+}
+int sd_timer_elapsed_ms(sd_ctx* ctx, int slot, float* ms) {
+    if (!ctx || !ms || slot < 0 || slot >= 16) return SD_ERR_INVALID;
+    SD_CUDA(ctx, cudaEventSynchronize(ctx->ev_stop[slot]));
+    SD_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev_start[slot], ctx->ev_stop[slot]));
+    return SD_OK;
+}
+int64_t sd_launch_count(const sd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int sd_flush_l2(sd_ctx* ctx) {
+    if (!ctx) return SD_ERR_INVALID;
+    if (!ctx->flush_buf) {
+        ctx->flush_bytes = std::max<size_t>(2 * ctx->l2_bytes, (size_t)256 << 20);
+        SD_CUDA(ctx, cudaMalloc(&ctx->flush_buf, ctx->flush_bytes));
+    }
+    SD_CUDA(ctx, cudaMemsetAsync(ctx->flush_buf, 0, ctx->flush_bytes, ctx->stream));
+    return SD_OK;
+}
+
+/* ---------------------------------------------------------------- STFT / fbank */
+
+void sd_stft_default_params(sd_stft_params* p) {
+    if (!p) return;
+    p->n_fft = 400;
+    p->hop = 160;
+    p->window_kind = SD_WINDOW_HAMMING_PERIODIC;
+    p->window = nullptr;
+    p->preemph = 0.f;
+    p->pad_batch_to = 0;
+}
+
+int64_t sd_stft_num_frames(int L, int hop) { return hop > 0 ? 1 + L / hop : 0; }
+
+int sd_stft_dev(sd_ctx* ctx, const float* d_wav, int B, int L, const sd_stft_params* p, float* d_out) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_wav && d_out && p, "sd_stft_dev: null pointer");
+    SD_REQUIRE(ctx, B > 0 && L > 0, "sd_stft_dev: B and L must be positive");
+    return stft_launch(ctx, d_wav, B, L, p, d_out);
+}
+
+int sd_stft(sd_ctx* ctx, const float* wav, int B, int L, const sd_stft_params* p, float* out) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, wav && out && p, "sd_stft: null pointer");
+    SD_REQUIRE(ctx, B > 0 && L > 0, "sd_stft: B and L must be positive");
+    const int64_t T = sd_stft_num_frames(L, p->hop);
+    const int rows = std::max(B, p->pad_batch_to);
+    const size_t in_bytes = sizeof(float) * (size_t)B * L;
+    const size_t out_bytes = sizeof(float) * (size_t)rows * T * (p->n_fft / 2 + 1) * 2;
+    float* d_in = (float*)ctx->scratch(BUF_STFT_IN, in_bytes);
+    float* d_out = (float*)ctx->scratch(BUF_STFT_OUT, out_bytes);
+    if (!d_in || !d_out) return SD_ERR_NOMEM;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_in, wav, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = stft_launch(ctx, d_in, B, L, p, d_out);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+
+int sd_pack_wav_lens(const float* lens, int n_lens, int batch, float* out) {
+    if (!out || batch <= 0 || n_lens < 0 || n_lens > batch || (n_lens && !lens)) return SD_ERR_INVALID;
+    for (int i = 0; i < batch; ++i) out[i] = i < n_lens ? lens[i] : 1.0f;  // speakerDiarizer.cpp:1899-1900
+    return SD_OK;
+}
+
+void sd_fbank_default_params(sd_fbank_params* p) {
+    if (!p) return;
+    sd_stft_default_params(&p->stft);
+    p->n_mels = 80;
+    p->f_min = 0.f;
+    p->f_max = 8000.f;
+    p->sample_rate = 16000;
+    p->top_db = 80.f;
+    p->amin = 1e-10f;
+    p->mean_norm = 1;
+}
+
+int sd_fbank_dev(sd_ctx* ctx, const float* d_wav, int B, int L, const float* d_wav_lens, const sd_fbank_params* p,
+                 float* d_out) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_wav && d_out && p && d_wav_lens, "sd_fbank_dev: null pointer");
+    SD_REQUIRE(ctx, B > 0 && L > 0, "sd_fbank_dev: B and L must be positive");
+    return fbank_launch(ctx, d_wav, B, L, d_wav_lens, p, d_out);
+}
+
+int sd_fbank(sd_ctx* ctx, const float* wav, int B, int L, const float* wav_lens, const sd_fbank_params* p,
+             float* out) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, wav && out && p && wav_lens, "sd_fbank: null pointer");
+    SD_REQUIRE(ctx, B > 0 && L > 0, "sd_fbank: B and L must be positive");
+    const int64_t T = sd_stft_num_frames(L, p->stft.hop);
+    const size_t in_bytes = sizeof(float) * (size_t)B * L;
+    const size_t out_bytes = sizeof(float) * (size_t)B * T * p->n_mels;
+    float* d_in = (float*)ctx->scratch(BUF_STFT_IN, in_bytes);
+    float* d_out = (float*)ctx->scratch(BUF_FB_OUT, out_bytes);
+    float* d_lens = (float*)ctx->scratch(BUF_FB_LENS, sizeof(float) * (size_t)B);
+    if (!d_in || !d_out || !d_lens) return SD_ERR_NOMEM;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_in, wav, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    SD_CUDA(ctx, cudaMemcpyAsync(d_lens, wav_lens, sizeof(float) * (size_t)B, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = fbank_launch(ctx, d_in, B, L, d_lens, p, d_out);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+
+/* ---------------------------------------------------------------- aggregation */
+
+int sd_np_rint(double v) { return np_rint_host(v); }
+
+int64_t sd_closest_frame(const sd_window* w, double t) {
+    return w ? closest_frame_host(w->start, w->step, w->duration, t) : -1;
+}
+
+int64_t sd_aggregate_num_frames(int C, const sd_window* chunks, const sd_window* frames) {
+    if (!chunks || !frames || C <= 0) return -1;
+    const double target = chunks->start + chunks->duration + (double)(size_t)(C - 1) * chunks->step;
+    return closest_frame_host(chunks->start, frames->step, frames->duration, target) + 1;
+}
+
+static void fill_post(const sd_window* chunks, const sd_window* frames, sd_window* post) {
+    if (!post) return;  // speakerDiarizer.cpp:1278-1281
+    post->start = chunks->start;
+    post->step = frames->step;
+    post->duration = frames->duration;
+    post->num_samples = chunks->num_samples;
+}
+
+int sd_aggregate_dev(sd_ctx* ctx, const double* d_scores, int C, int F, int K, const sd_window* chunks,
+                     const sd_window* frames, int hamming, double missing, int skip_average, double epsilon,
+                     double* d_out, int64_t cap_rows, int64_t* num_frames, sd_window* post_frames, double* d_count_out,
+                     double* d_mask_out) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_scores && d_out && chunks && frames, "sd_aggregate_dev: null pointer");
+    SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0, "sd_aggregate_dev: C, F, K must be positive");
+    SD_REQUIRE(ctx, chunks->num_samples > 0, "sd_aggregate: scores_frames.num_samples must be > 0 (SD:1181)");
+    const int64_t NF = sd_aggregate_num_frames(C, chunks, frames);
+    if (num_frames) *num_frames = NF;
+    if (NF > cap_rows) return ctx->fail(SD_ERR_CAPACITY, "sd_aggregate: need %lld rows, have %lld", (long long)NF,
+                                        (long long)cap_rows);
+    fill_post(chunks, frames, post_frames);
+    return aggregate_launch(ctx, d_scores, C, F, K, chunks, frames, hamming, missing, skip_average, epsilon, d_out, NF,
+                            d_count_out, d_mask_out);
+}
+
+int sd_aggregate(sd_ctx* ctx, const double* scores, int C, int F, int K, const sd_window* chunks,
+                 const sd_window* frames, int hamming, double missing, int skip_average, double epsilon, double* out,
+                 int64_t cap_rows, int64_t* num_frames, sd_window* post_frames, double* count_out, double* mask_out) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, scores && out && chunks && frames, "sd_aggregate: null pointer");
+    SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0, "sd_aggregate: C, F, K must be positive");
+    const int64_t NF = sd_aggregate_num_frames(C, chunks, frames);
+    if (num_frames) *num_frames = NF;
+    if (NF > cap_rows) return ctx->fail(SD_ERR_CAPACITY, "sd_aggregate: need %lld rows, have %lld", (long long)NF,
+                                        (long long)cap_rows);
+    const size_t in_bytes = sizeof(double) * (size_t)C * F * K, out_bytes = sizeof(double) * (size_t)NF * K;
+    double* d_in = (double*)ctx->scratch(BUF_AGG_IN, in_bytes);
+    double* d_out = (double*)ctx->scratch(BUF_AGG_OUT, out_bytes);
+    double* d_cnt = count_out ? (double*)ctx->scratch(BUF_AGG_AUX, out_bytes) : nullptr;
+    double* d_msk = mask_out ? (double*)ctx->scratch(BUF_AGG_AUX2, out_bytes) : nullptr;
+    if (!d_in || !d_out || (count_out && !d_cnt) || (mask_out && !d_msk)) return SD_ERR_NOMEM;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_in, scores, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int64_t nf2 = 0;
+    int rc = sd_aggregate_dev(ctx, d_in, C, F, K, chunks, frames, hamming, missing, skip_average, epsilon, d_out, NF,
+                              &nf2, post_frames, d_cnt, d_msk);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (count_out) SD_CUDA(ctx, cudaMemcpyAsync(count_out, d_cnt, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    if (mask_out) SD_CUDA(ctx, cudaMemcpyAsync(mask_out, d_msk, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+
+/* ---------------------------------------------------------------- binarize / trim / count / clean */
+
+int sd_binarize_dev(sd_ctx* ctx, const float* d_scores, int C, int F, int K, double onset, int initial_state,
+                    double* d_out) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_scores && d_out, "sd_binarize_dev: null pointer");
+    SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0, "sd_binarize_dev: C, F, K must be positive");
+    return binarize_launch(ctx, d_scores, C, F, K, onset, initial_state, d_out);
+}
+
+int sd_binarize(sd_ctx* ctx, const float* scores, int C, int F, int K, double onset, int initial_state, double* out) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, scores && out, "sd_binarize: null pointer");
+    SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0, "sd_binarize: C, F, K must be positive");
+    const size_t n = (size_t)C * F * K;
+    float* d_in = (float*)ctx->scratch(BUF_BIN_IN, sizeof(float) * n);
+    double* d_out = (double*)ctx->scratch(BUF_BIN_OUT, sizeof(double) * n);
+    if (!d_in || !d_out) return SD_ERR_NOMEM;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_in, scores, sizeof(float) * n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = binarize_launch(ctx, d_in, C, F, K, onset, initial_state, d_out);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+
+int sd_binarize_rows(sd_ctx* ctx, const double* scores, int R, int F, double onset, int initial_state, uint8_t* out) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, scores && out, "sd_binarize_rows: null pointer");
+    SD_REQUIRE(ctx, R > 0 && F > 0, "sd_binarize_rows: R, F must be positive");
+    const size_t n = (size_t)R * F;
+    double* d_in = (double*)ctx->scratch(BUF_BIN_OUT, sizeof(double) * n);
+    uint8_t* d_out = (uint8_t*)ctx->scratch(BUF_BIN_IN, n);
+    if (!d_in || !d_out) return SD_ERR_NOMEM;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_in, scores, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = binarize_rows_launch(ctx, d_in, R, F, onset, initial_state, d_out);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+
+int64_t sd_trim_num_frames(int F, double left, double right) {
+    // floor, not round: speakerDiarizer.cpp:1755-1758
+    return (int64_t)F - (int64_t)std::floor((double)F * left) - (int64_t)std::floor((double)F * right);
+}
+
+static void trimmed_window(int F, double left, double right, const sd_window* before, sd_window* tw) {
+    tw->start = before->start + left * before->duration;  // speakerDiarizer.cpp:1776-1779
+    tw->step = before->step;
+    tw->duration = (1 - left - right) * before->duration;
+    tw->num_samples = sd_trim_num_frames(F, left, right);
+}
+
+int sd_trim(sd_ctx* ctx, const double* binarized, int C, int F, int K, double left, double right,
+            const sd_window* before, double* out, sd_window* trimmed_frames) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, binarized && out && before, "sd_trim: null pointer");
+    SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0, "sd_trim: C, F, K must be positive");
+    const int nl = (int)std::floor((double)F * left);
+    const int Ft = (int)sd_trim_num_frames(F, left, right);
+    SD_REQUIRE(ctx, Ft > 0, "sd_trim: nothing left after trimming");
+    if (trimmed_frames) trimmed_window(F, left, right, before, trimmed_frames);
+    const size_t in_bytes = sizeof(double) * (size_t)C * F * K, out_bytes = sizeof(double) * (size_t)C * Ft * K;
+    double* d_in = (double*)ctx->scratch(BUF_BIN_OUT, in_bytes);
+    double* d_out = (double*)ctx->scratch(BUF_CNT_TMP, out_bytes);
+    if (!d_in || !d_out) return SD_ERR_NOMEM;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_in, binarized, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = trim_launch(ctx, d_in, C, F, K, nl, Ft, d_out);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+
+int sd_speaker_count_dev(sd_ctx* ctx, const double* d_binarized, int C, int F, int K, const sd_window* chunks,
+                         const sd_window* frames, int32_t* d_out, int64_t cap, int64_t* n_out, sd_window* count_frames) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_binarized && d_out && chunks && frames, "sd_speaker_count_dev: null pointer");
+    SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0, "sd_speaker_count_dev: C, F, K must be positive");
+    // trim 10% / 10% of the chunk window (speakerDiarizer.cpp:1691-1693; the reference anchors it at 0.0)
+    sd_window before = *chunks, tw;
+    before.start = 0.0;
+    trimmed_window(F, 0.1, 0.1, &before, &tw);
+    const int nl = (int)std::floor((double)F * 0.1);
+    const int Ft = (int)tw.num_samples;
+    SD_REQUIRE(ctx, Ft > 0, "sd_speaker_count: nothing left after trimming");
+    const int64_t NF = sd_aggregate_num_frames(C, &tw, frames);
+    if (n_out) *n_out = NF;
+    if (NF > cap) return ctx->fail(SD_ERR_CAPACITY, "sd_speaker_count: need %lld entries, have %lld", (long long)NF,
+                                   (long long)cap);
+    double* d_sum = (double*)ctx->scratch(BUF_CNT_TMP, sizeof(double) * (size_t)C * Ft);
+    double* d_agg = (double*)ctx->scratch(BUF_CNT_OUT, sizeof(double) * (size_t)NF);
+    if (!d_sum || !d_agg) return SD_ERR_NOMEM;
+    int rc = trim_sum_launch(ctx, d_binarized, C, F, K, nl, Ft, d_sum);
+    if (rc) return rc;
+    // aggregate(sum_trimmed, trimmed_frames, pre_frame, hamming=false, missing=0.0, skip_average=false), SD:1719
+    rc = aggregate_launch(ctx, d_sum, C, Ft, 1, &tw, frames, 0, 0.0, 0, DBL_EPSILON, d_agg, NF, nullptr, nullptr);
+    if (rc) return rc;
+    rc = rint_launch(ctx, d_agg, NF, d_out);  // np.rint, SD:1731-1735
+    if (rc) return rc;
+    fill_post(&tw, frames, count_frames);
+    return SD_OK;
+}
+
+int sd_speaker_count(sd_ctx* ctx, const double* binarized, int C, int F, int K, const sd_window* chunks,
+                     const sd_window* frames, int32_t* out, int64_t cap, int64_t* n_out, sd_window* count_frames) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, binarized && out && chunks && frames, "sd_speaker_count: null pointer");
+    SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0, "sd_speaker_count: C, F, K must be positive");
+    const size_t in_bytes = sizeof(double) * (size_t)C * F * K;
+    double* d_in = (double*)ctx->scratch(BUF_BIN_OUT, in_bytes);
+    int32_t* d_out = (int32_t*)ctx->scratch(BUF_GENERIC_A, sizeof(int32_t) * (size_t)std::max<int64_t>(cap, 1));
+    if (!d_in || !d_out) return SD_ERR_NOMEM;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_in, binarized, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int64_t n = 0;
+    int rc = sd_speaker_count_dev(ctx, d_in, C, F, K, chunks, frames, d_out, cap, &n, count_frames);
+    if (n_out) *n_out = n;
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(out, d_out, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+
+int sd_clean_segmentations(sd_ctx* ctx, const double* binarized, int C, int F, int K, double* out) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, binarized && out, "sd_clean_segmentations: null pointer");
+    SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0, "sd_clean_segmentations: C, F, K must be positive");
+    const size_t bytes = sizeof(double) * (size_t)C * F * K;
+    double* d_in = (double*)ctx->scratch(BUF_BIN_OUT, bytes);
+    double* d_out = (double*)ctx->scratch(BUF_CNT_TMP, bytes);
+    if (!d_in || !d_out) return SD_ERR_NOMEM;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_in, binarized, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = clean_launch(ctx, d_in, (int64_t)C * F, K, d_out);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+
+/* ---------------------------------------------------------------- clustering library */
+
+static int check_status(sd_ctx* ctx) {
+    SD_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int st = *ctx->h_status;
+    if (st == SD_ERR_ZERO_MAGNITUDE) return ctx->fail(st, "Vectors have zero magnitude.");
+    if (st) return ctx->fail(st, "device-side failure %d", st);
+    return SD_OK;
+}
+
+static int reset_status(sd_ctx* ctx) {
+    SD_CUDA(ctx, cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream));
+    return SD_OK;
+}
+
+int sd_normalize(sd_ctx* ctx, double* x, int N, int D) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, x, "sd_normalize: null pointer");
+    SD_REQUIRE(ctx, N > 0 && D > 0, "sd_normalize: N, D must be positive");
+    const size_t bytes = sizeof(double) * (size_t)N * D;
+    double* d_x = (double*)ctx->scratch(BUF_CL_X, bytes);
+    double* d_xn = (double*)ctx->scratch(BUF_CL_XN, bytes);
+    if (!d_x || !d_xn) return SD_ERR_NOMEM;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_x, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = normalize_launch(ctx, d_x, N, D, d_xn);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(x, d_xn, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+
+int sd_pdist(sd_ctx* ctx, const double* x, int N, int D, int mode, double* condensed) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, x && condensed, "sd_pdist: null pointer");
+    SD_REQUIRE(ctx, N > 1 && D > 0, "sd_pdist: need N > 1, D > 0");
+    if (mode != SD_PDIST_EXACT_F64) return ctx->fail(SD_ERR_UNSUPPORTED, "sd_pdist: mode %d not available", mode);
+    const size_t bytes = sizeof(double) * (size_t)N * D;
+    const size_t cbytes = sizeof(double) * ((size_t)N * (N - 1) / 2);
+    double* d_x = (double*)ctx->scratch(BUF_CL_X, bytes);
+    double* d_c = (double*)ctx->scratch(BUF_GENERIC_B, cbytes);
+    if (!d_x || !d_c) return SD_ERR_NOMEM;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_x, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = pdist_condensed_launch(ctx, d_x, N, D, d_c);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(condensed, d_c, cbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+
+int sd_linkage_dev(sd_ctx* ctx, const double* d_x, int N, int D, double* d_Z) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_x && d_Z, "sd_linkage_dev: null pointer");
+    SD_REQUIRE(ctx, N > 1 && D > 0, "sd_linkage_dev: need N > 1, D > 0");
+    int rc = reset_status(ctx);
+    if (rc) return rc;
+    return linkage_launch(ctx, d_x, N, D, d_Z);
+}
+
+int sd_linkage(sd_ctx* ctx, const double* x, int N, int D, double* Z) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, x && Z, "sd_linkage: null pointer");
+    SD_REQUIRE(ctx, N > 1 && D > 0, "sd_linkage: need N > 1, D > 0");
+    const size_t bytes = sizeof(double) * (size_t)N * D;
+    double* d_x = (double*)ctx->scratch(BUF_CL_X, bytes);
+    double* d_Z = (double*)ctx->scratch(BUF_CL_Z, sizeof(double) * 4 * (size_t)N);
+    if (!d_x || !d_Z) return SD_ERR_NOMEM;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_x, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = sd_linkage_dev(ctx, d_x, N, D, d_Z);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(Z, d_Z, sizeof(double) * 4 * (size_t)(N - 1), cudaMemcpyDeviceToHost, ctx->stream));
+    return check_status(ctx);
+}
+
+int sd_fcluster(sd_ctx* ctx, const double* Z, int N, double cutoff, int32_t* T) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, Z && T, "sd_fcluster: null pointer");
+    SD_REQUIRE(ctx, N > 1, "sd_fcluster: need N > 1");
+    double* d_Z = (double*)ctx->scratch(BUF_CL_Z, sizeof(double) * 4 * (size_t)N);
+    int* d_T = (int*)ctx->scratch(BUF_CL_LABELS, sizeof(int) * (size_t)N + 256);
+    if (!d_Z || !d_T) return SD_ERR_NOMEM;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_Z, Z, sizeof(double) * 4 * (size_t)(N - 1), cudaMemcpyHostToDevice, ctx->stream));
+    int rc = fcluster_launch(ctx, d_Z, N, cutoff, d_T, d_T + N);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(T, d_T, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+
+int sd_cluster(sd_ctx* ctx, const double* x, int N, int D, double cutoff, int32_t* T) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, x && T, "sd_cluster: null pointer");
+    SD_REQUIRE(ctx, N > 1 && D > 0, "sd_cluster: need N > 1, D > 0");
+    const size_t bytes = sizeof(double) * (size_t)N * D;
+    double* d_x = (double*)ctx->scratch(BUF_CL_X, bytes);
+    double* d_Z = (double*)ctx->scratch(BUF_CL_Z, sizeof(double) * 4 * (size_t)N);
+    int* d_T = (int*)ctx->scratch(BUF_CL_LABELS, sizeof(int) * (size_t)N + 256);
+    if (!d_x || !d_Z || !d_T) return SD_ERR_NOMEM;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_x, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = reset_status(ctx);
+    if (rc) return rc;
+    rc = linkage_launch(ctx, d_x, N, D, d_Z);
+    if (rc) return rc;
+    rc = fcluster_launch(ctx, d_Z, N, cutoff, d_T, d_T + N);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(T, d_T, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+    return check_status(ctx);
+}
+
+int sd_cosine_cdist(sd_ctx* ctx, const double* a, int na, const double* b, int nb, int D, double* out) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, a && b && out, "sd_cosine_cdist: null pointer");
+    SD_REQUIRE(ctx, na > 0 && nb > 0 && D > 0, "sd_cosine_cdist: sizes must be positive");
+    double* d_a = (double*)ctx->scratch(BUF_CL_X, sizeof(double) * (size_t)na * D);
+    double* d_b = (double*)ctx->scratch(BUF_CL_XN, sizeof(double) * (size_t)nb * D);
+    double* d_o = (double*)ctx->scratch(BUF_CL_SOFT, sizeof(double) * (size_t)na * nb);
+    if (!d_a || !d_b || !d_o) return SD_ERR_NOMEM;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_a, a, sizeof(double) * (size_t)na * D, cudaMemcpyHostToDevice, ctx->stream));
+    SD_CUDA(ctx, cudaMemcpyAsync(d_b, b, sizeof(double) * (size_t)nb * D, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = reset_status(ctx);
+    if (rc) return rc;
+    rc = cosine_cdist_launch(ctx, d_a, na, d_b, nb, D, d_o);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(out, d_o, sizeof(double) * (size_t)na * nb, cudaMemcpyDeviceToHost, ctx->stream));
+    return check_status(ctx);
+}
+
+/* ---------------------------------------------------------------- clustering driver */
+
+void sd_cluster_default_params(sd_cluster_params* p) {
+    if (!p) return;
+    p->threshold = 0.7153814381597874f;  // stored as float by the reference (speakerDiarizer.cpp:2049)
+    p->min_cluster_size = 15;
+    p->num_clusters = -1;
+    p->min_clusters = -1;
+    p->max_clusters = -1;
+    p->pdist_mode = SD_PDIST_EXACT_F64;
+}
+
+int sd_cluster_labels(sd_ctx* ctx, const double* x, int N, int D, const sd_cluster_params* p, int32_t* labels) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, x && labels && p, "sd_cluster_labels: null pointer");
+    SD_REQUIRE(ctx, N > 0 && D > 0, "sd_cluster_labels: N, D must be positive");
+    if (N == 1) {
+        labels[0] = 0;
+        return SD_OK;
+    }
+    const size_t bytes = sizeof(double) * (size_t)N * D;
+    double* d_x = (double*)ctx->scratch(BUF_CL_X, bytes);
+    int* d_lab = (int*)ctx->scratch(BUF_CL_LABELS, sizeof(int) * (size_t)N + 256);
+    if (!d_x || !d_lab) return SD_ERR_NOMEM;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_x, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = reset_status(ctx);
+    if (rc) return rc;
+    rc = cluster_labels_launch(ctx, d_x, N, D, p, d_lab, d_lab + N);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(labels, d_lab, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+    return check_status(ctx);
+}
+
+int sd_clustering_dev(sd_ctx* ctx, const double* d_embeddings, int C, int S, int D, const sd_cluster_params* p,
+                      const double* d_binarized, int F, int32_t* d_hard, double* d_soft, int soft_k_cap,
+                      int* num_clusters) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_embeddings && d_hard && p, "sd_clustering_dev: null pointer");
+    SD_REQUIRE(ctx, C > 0 && S > 0 && D > 0, "sd_clustering_dev: C, S, D must be positive");
+    const int R = C * S;
+    unsigned char* d_valid = (unsigned char*)ctx->scratch(BUF_GENERIC_A, (size_t)R);
+    if (!d_valid) return SD_ERR_NOMEM;
+    int rc = row_valid_launch(ctx, d_embeddings, R, D, d_valid);
+    if (rc) return rc;
+    std::vector<unsigned char> valid((size_t)R);
+    SD_CUDA(ctx, cudaMemcpyAsync(valid.data(), d_valid, (size_t)R, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<int> keep;
+    keep.reserve((size_t)R);
+    for (int r = 0; r < R; ++r)
+        if (valid[r]) keep.push_back(r);
+    rc = reset_status(ctx);
+    if (rc) return rc;
+    rc = clustering_launch(ctx, d_embeddings, C, S, D, keep, p, d_binarized, F, d_hard, d_soft, soft_k_cap,
+                           num_clusters);
+    if (rc) return rc;
+    return check_status(ctx);
+}
+
+int sd_clustering(sd_ctx* ctx, const double* embeddings, int C, int S, int D, const sd_cluster_params* p,
+                  const double* binarized, int F, int32_t* hard, double* soft, int soft_k_cap, int* num_clusters) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, embeddings && hard && p, "sd_clustering: null pointer");
+    SD_REQUIRE(ctx, C > 0 && S > 0 && D > 0, "sd_clustering: C, S, D must be positive");
+    SD_REQUIRE(ctx, !binarized || F > 0, "sd_clustering: F must be positive when binarized is given");
+    const int R = C * S;
+    const size_t ebytes = sizeof(double) * (size_t)R * D;
+    double* d_emb = (double*)ctx->scratch(BUF_CL_EMB, ebytes);
+    int* d_hard = (int*)ctx->scratch(BUF_GENERIC_B, sizeof(int) * (size_t)R);
+    double* d_bin = nullptr;
+    double* d_soft = nullptr;
+    if (!d_emb || !d_hard) return SD_ERR_NOMEM;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_emb, embeddings, ebytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (binarized) {
+        const size_t bbytes = sizeof(double) * (size_t)C * F * S;
+        d_bin = (double*)ctx->scratch(BUF_CL_BIN, bbytes);
+        if (!d_bin) return SD_ERR_NOMEM;
+        SD_CUDA(ctx, cudaMemcpyAsync(d_bin, binarized, bbytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (soft && soft_k_cap > 0) {
+        d_soft = (double*)ctx->scratch(BUF_CL_SOFT, sizeof(double) * (size_t)R * soft_k_cap);
+        if (!d_soft) return SD_ERR_NOMEM;
+        // entries beyond the number of clusters stay NaN
+        SD_CUDA(ctx, cudaMemsetAsync(d_soft, 0xff, sizeof(double) * (size_t)R * soft_k_cap, ctx->stream));
+    }
+    // filter_embeddings (speakerDiarizer.cpp:2222-2229): the host already holds the rows
+    std::vector<int> keep;
+    keep.reserve((size_t)R);
+    for (int r = 0; r < R; ++r)
+        if (!std::isnan(embeddings[(size_t)r * D])) keep.push_back(r);
+    int rc = reset_status(ctx);
+    if (rc) return rc;
+    rc = clustering_launch(ctx, d_emb, C, S, D, keep, p, d_bin, F, d_hard, d_soft, soft_k_cap, num_clusters);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(hard, d_hard, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_soft)
+        SD_CUDA(ctx, cudaMemcpyAsync(soft, d_soft, sizeof(double) * (size_t)R * soft_k_cap, cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+    return check_status(ctx);
+}
+
+}  // extern "C"

@@ -1,0 +1,53 @@
+// TEST INFRASTRUCTURE: thread-by-thread CPU replay of the three STFT kernel phases in csrc/fft400.cuh,
+// checked against a direct fp64 DFT.  Validates the index maps / exchange layouts without a GPU.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../../pyannote-audio_speaker-diarization_cpp_b200/csrc/fft400.cuh"
+
+int main() {
+    using namespace sdb;
+    const int groups = 8, frames = 16, nthreads = groups * kRadix;
+    const int nsig = (frames - 1) * kHop + kNfft;
+    std::vector<float> sig(nsig), w(kNfft);
+    srand(1);
+    for (auto& s : sig) s = (float)rand() / RAND_MAX * 2.f - 1.f;
+    for (int n = 0; n < kNfft; ++n) w[n] = (float)(0.54 - 0.46 * cos(2.0 * M_PI * n / kNfft));
+    std::vector<float2> xchg(groups * kGroupStride), zbuf(groups * kGroupStride);
+    std::vector<float> out(frames * kBins * 2, 0.f);
+    struct TS { float win[20]; float2 tw[20]; };
+    std::vector<TS> ts(nthreads);
+    for (int t = 0; t < nthreads; ++t) {
+        int r = t % kRadix;
+        for (int n1 = 0; n1 < 20; ++n1) ts[t].win[n1] = w[20 * n1 + r];
+        for (int k1 = 0; k1 < 20; ++k1) {
+            double a = -2.0 * M_PI * (double)(r * k1) / kNfft;
+            ts[t].tw[k1] = make_float2((float)cos(a), (float)sin(a));
+        }
+    }
+    for (int t = 0; t < nthreads; ++t) {
+        int g = t / kRadix, r = t % kRadix;
+        stft_phase1(sig.data(), (2 * g) * kHop, (2 * g + 1) * kHop, ts[t].win, ts[t].tw, g, r, xchg.data());
+    }
+    for (int t = 0; t < nthreads; ++t) stft_phase2(xchg.data(), t / kRadix, t % kRadix, zbuf.data());
+    for (int t = 0; t < nthreads; ++t) {
+        int g = t / kRadix;
+        stft_phase3(zbuf.data(), g, t % kRadix, &out[(2 * g) * kBins * 2], &out[(2 * g + 1) * kBins * 2]);
+    }
+    double maxerr = 0, maxabs = 0;
+    for (int f = 0; f < frames; ++f)
+        for (int k = 0; k < kBins; ++k) {
+            double re = 0, im = 0;
+            for (int n = 0; n < kNfft; ++n) {
+                double x = (double)sig[f * kHop + n] * (double)w[n];
+                double a = -2.0 * M_PI * (double)((long)k * n % kNfft) / kNfft;
+                re += x * cos(a);
+                im += x * sin(a);
+            }
+            maxerr = fmax(maxerr, fmax(fabs(re - out[(f * kBins + k) * 2]), fabs(im - out[(f * kBins + k) * 2 + 1])));
+            maxabs = fmax(maxabs, fmax(fabs(re), fabs(im)));
+        }
+    printf("max|X| %.3f  max abs err %.3e\n", maxabs, maxerr);
+    return maxerr < 2e-5 ? 0 : 1;
+}
