@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- audio-seconds/second of the fbank(STFT) + aggregation + clustering hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+A "step" is one pass of the hot path over one synthetic 10-minute file at BASELINE.json configs[1]
+(10 s chunks / 1 s step -> 591 chunks x 589 frames x 3 local speakers, 1 773 STFT items of 160 000 samples,
+1 773 embeddings of dimension 192): STFT of every (chunk, speaker) item, hysteresis binarisation, speaker
+count (trim + aggregate + rint), clustering (normalise, fp64 pdist, centroid linkage, fcluster, centroid
+assignment) and the skip-average aggregation of the diarization path.
+
+ * `value`   : device-resident (inputs already in HBM), CUDA-event timed on the library's stream, max over ranks
+ * `e2e`     : the same step through the host-pointer C-ABI calls (pinned host buffers, H2D + D2H inside)
+ * `roofline`: the STFT kernel (the HBM-bound kernel the metric names) -- algorithmic bytes / event time
+ * `cpu_baseline`: the reference's own code (oracle/_ref) on this box's host cores, bounded sample
+With N > 1 every rank processes its own file per step (files shard with no data-path collective; labels are
+gathered with one NCCL all_gather per step) -> weak scaling.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import __graft_entry__ as ge  # noqa: E402
+
+METRIC = "audio-sec/sec of fbank+aggregation+clustering path; fbank GB/s vs HBM peak"
+UNIT = "audio-s/s"
+
+WORKLOAD = dict(
+    name="configs[1]: synthetic 10-min 16 kHz mono, 10 s chunks / 1 s step, 3 local speakers",
+    audio_seconds=600.0, window_s=10.0, step_s=1.0, frames_per_chunk=589, local_speakers=3, embedding_dim=192,
+    n_fft=400, hop=160, diar_clusters=4)
+
+
+def geometry():
+    synth = ge.load_synth()
+    C = synth.chunk_geometry(WORKLOAD["audio_seconds"], WORKLOAD["window_s"], WORKLOAD["step_s"])
+    S = WORKLOAD["local_speakers"]
+    L = int(WORKLOAD["window_s"] * 16000)
+    return dict(C=C, F=WORKLOAD["frames_per_chunk"], S=S, items=C * S, L=L, T=1 + L // WORKLOAD["hop"],
+                D=WORKLOAD["embedding_dim"], Kd=WORKLOAD["diar_clusters"])
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per STFT launch from the committed ncu capture, if any (profiles/stft_ncu_summary.json)."""
+    p = os.path.join(ROOT, "profiles", "stft_ncu_summary.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch_cfg2")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_inputs(synth, geo, seed):
+    """Host-side synthetic inputs of one file (seeded per rank)."""
+    wav_items = synth.fbank_items(seed + 102, geo["items"], geo["L"])
+    seg = synth.segmentations(seed + 1102, geo["C"], geo["F"], geo["S"])
+    emb, _ = synth.embeddings(seed + 202, geo["C"], geo["S"], geo["D"], n_speakers=4)
+    diar = synth.segmentations(seed + 2102, geo["C"], geo["F"], geo["Kd"]).astype(np.float64)
+    rng = np.random.default_rng(seed + 3)
+    diar[np.broadcast_to(rng.random((geo["C"], 1, geo["Kd"])) < 0.4, diar.shape)] = np.nan  # absent clusters
+    return wav_items, seg, emb, diar
+
+
+def run_product(args, rank, world):
+    import torch
+    import torch.distributed as dist
+
+    pkg = ge.load_package()
+    synth = ge.load_synth()
+    geo = geometry()
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = pkg.Context(local)
+    import ctypes as C
+
+    C_, F, S, items, L, T, D, Kd = (geo[k] for k in ("C", "F", "S", "items", "L", "T", "D", "Kd"))
+    wav_items, seg, emb, diar = build_inputs(synth, geo, 1000 * rank)
+    chunks = pkg.Window(0.0, WORKLOAD["step_s"], WORKLOAD["window_s"], int(WORKLOAD["audio_seconds"] * 16000))
+    frames = pkg.Window(0.0, pkg.FRAME_STEP, pkg.FRAME_DURATION, 0)
+    NFd = ctx.L.sd_aggregate_num_frames(C_, C.byref(chunks), C.byref(frames))
+    cap_cnt = NFd + 64
+
+    # ---- device-resident buffers
+    d_wav = ctx.to_device(wav_items)
+    d_seg = ctx.to_device(seg)
+    d_emb = ctx.to_device(emb)
+    d_diar = ctx.to_device(diar)
+    d_stft = ctx.malloc(items * T * 201 * 2 * 4)
+    d_bin = ctx.malloc(C_ * F * S * 8)
+    d_cnt = ctx.malloc(cap_cnt * 4)
+    d_agg = ctx.malloc(NFd * Kd * 8)
+    sp = ctx.stft_params()
+    cp = ctx.cluster_params()
+    n_out = C.c_int64()
+    cf = pkg.Window()
+    post = pkg.Window()
+    kc = C.c_int()
+    vp = C.c_void_p
+    hard_t = torch.empty(C_ * S, dtype=torch.int32, device="cuda")  # torch-owned so NCCL can gather it
+    d_hard = hard_t.data_ptr()
+    gathered = [torch.empty_like(hard_t) for _ in range(world)] if world > 1 else None
+
+    def step_resident(timed):
+        if timed:
+            ctx.timer_start(1)
+        ctx.stft_dev(d_wav, items, L, d_stft, sp)
+        if timed:
+            ctx.timer_stop(1)
+            ctx.timer_start(2)
+        ctx._check(ctx.L.sd_binarize_dev(ctx.h, vp(d_seg), C_, F, S, pkg.ONSET, 0, vp(d_bin)))
+        ctx._check(ctx.L.sd_speaker_count_dev(ctx.h, vp(d_bin), C_, F, S, C.byref(chunks), C.byref(frames), vp(d_cnt),
+                                              cap_cnt, C.byref(n_out), C.byref(cf)))
+        if timed:
+            ctx.timer_stop(2)
+            ctx.timer_start(3)
+        ctx._check(ctx.L.sd_clustering_dev(ctx.h, vp(d_emb), C_, S, D, C.byref(cp), vp(d_bin), F, vp(d_hard), None, 0,
+                                           C.byref(kc)))
+        if timed:
+            ctx.timer_stop(3)
+            ctx.timer_start(4)
+        ctx._check(ctx.L.sd_aggregate_dev(ctx.h, vp(d_diar), C_, F, Kd, C.byref(chunks), C.byref(frames), 0, 0.0, 1,
+                                          pkg.EPS, vp(d_agg), NFd, C.byref(n_out), C.byref(post), None, None))
+        if timed:
+            ctx.timer_stop(4)
+        if world > 1:  # labels of every file to every rank: the only collective on the path (KBs)
+            ctx.sync()
+            dist.all_gather(gathered, hard_t)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stage_ms = {1: 0.0, 2: 0.0, 3: 0.0, 4: 0.0}
+    for _ in range(args.warmup):
+        step_resident(False)
+    ctx.sync()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    barrier()
+    ctx.timer_start(0)
+    for _ in range(args.steps):
+        step_resident(True)
+        for s in stage_ms:  # events already recorded; reading them waits for the step (host is idle anyway)
+            stage_ms[s] += ctx.timer_ms(s)
+    ctx.timer_stop(0)
+    total_ms = ctx.timer_ms(0)
+    barrier()
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([total_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * WORKLOAD["audio_seconds"] / (ms_per_step / 1e3)
+
+    # ---- e2e: host-pointer C-ABI calls, pinned buffers, H2D/D2H inside the timed region
+    h_wav = ctx.host_alloc(wav_items.shape, np.float32)
+    h_wav[...] = wav_items
+    h_stft = ctx.host_alloc((items, T, 201, 2), np.float32)
+    h_seg = ctx.host_alloc(seg.shape, np.float32)
+    h_seg[...] = seg
+    h_bin = ctx.host_alloc(seg.shape, np.float64)
+    h_cnt = ctx.host_alloc((cap_cnt,), np.int32)
+    h_emb = ctx.host_alloc(emb.shape, np.float64)
+    h_emb[...] = emb
+    h_hard = ctx.host_alloc((C_, S), np.int32)
+    h_diar = ctx.host_alloc(diar.shape, np.float64)
+    h_diar[...] = diar
+    h_agg = ctx.host_alloc((NFd, Kd), np.float64)
+    P = pkg._ptr
+
+    def step_e2e():
+        ctx._check(ctx.L.sd_stft(ctx.h, P(h_wav), items, L, C.byref(sp), P(h_stft)))
+        ctx._check(ctx.L.sd_binarize(ctx.h, P(h_seg), C_, F, S, pkg.ONSET, 0, P(h_bin)))
+        ctx._check(ctx.L.sd_speaker_count(ctx.h, P(h_bin), C_, F, S, C.byref(chunks), C.byref(frames), P(h_cnt),
+                                          cap_cnt, C.byref(n_out), C.byref(cf)))
+        ctx._check(ctx.L.sd_clustering(ctx.h, P(h_emb), C_, S, D, C.byref(cp), P(h_bin), F, P(h_hard), None, 0,
+                                       C.byref(kc)))
+        ctx._check(ctx.L.sd_aggregate(ctx.h, P(h_diar), C_, F, Kd, C.byref(chunks), C.byref(frames), 0, 0.0, 1, pkg.EPS,
+                                      P(h_agg), NFd, C.byref(n_out), C.byref(post), None, None))
+
+    h2d = wav_items.nbytes + seg.nbytes + h_bin.nbytes * 2 + emb.nbytes + diar.nbytes
+    d2h = h_stft.nbytes + h_bin.nbytes + int(n_out.value or NFd) * 4 + h_hard.nbytes + h_agg.nbytes
+    e2e_steps = max(2, min(args.steps, 5))
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * WORKLOAD["audio_seconds"] / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peaks()
+    stft_ms = stage_ms[1] / args.steps
+    stft_bytes = items * (4 * L + 4 * T * 201 * 2)
+    achieved = stft_bytes / (stft_ms / 1e3) / 1e9
+    n_merge = int((~np.isnan(emb[:, :, 0])).sum()) - 1
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 stft / f64 aggregation+clustering",
+        "data": "synthetic (seeded; stand-ins for segment2.onnx / emd4.onnx outputs, see synth.py)",
+        "config": {"workload": WORKLOAD["name"], "chunks": C_, "frames_per_chunk": F, "local_speakers": S,
+                   "stft_items": items, "samples_per_item": L, "embeddings": items, "embedding_dim": D,
+                   "l2_policy": "inputs larger than L2 (STFT streams 3.99 GB per step)",
+                   "files_per_step_per_gpu": 1, "parallelism": "file-sharded x%d" % world},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": e2e_s * 1e3, "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "stft400_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": int(stft_bytes), "ms_per_launch": stft_ms},
+        "stages_ms_per_step": {"stft": stft_ms, "binarize+speaker_count": stage_ms[2] / args.steps,
+                               "clustering": stage_ms[3] / args.steps, "aggregate_diar": stage_ms[4] / args.steps},
+        "linkage": {"merges": n_merge, "us_per_merge_upper_bound": stage_ms[3] / args.steps * 1e3 / max(n_merge, 1),
+                    "bound": "latency (N-1 dependent merges)"},
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(geo, wav_items, seg, emb, diar)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(geo, wav_items, seg, emb, diar, stft_sample_items=2):
+    """The reference's own code (oracle/_ref when built, else the C restatement) on this box's host cores.
+    Bounded sample: `stft_sample_items` STFT items as written (per-element .item() copy + /tmp dump included,
+    speakerDiarizer.cpp:2022-2036, 1923-1928) scaled to the 1 773 items, plus the full segmentation
+    post-processing and clustering of the file."""
+    from oracle.oracle import Oracle, Ref
+    kind = "reference" if Ref.available() else "port"
+    o = Oracle()
+    r = Ref() if kind == "reference" else None
+    items = geo["items"]
+    sample = np.ascontiguousarray(wav_items[:stft_sample_items])
+    t0 = time.perf_counter()
+    if r is not None:
+        r.stft(sample)
+    else:
+        o.stft(sample)
+    t_stft_sample = time.perf_counter() - t0
+    t_fft_only = None
+    if r is not None:
+        t0 = time.perf_counter()
+        r.stft_fft_only(np.ascontiguousarray(wav_items[:32]))
+        t_fft_only = (time.perf_counter() - t0) / 32
+    t0 = time.perf_counter()
+    # SegmentModel::binarize_swf / speaker_count are tied to the reference's 5 s / 0.5 s constants; the C
+    # restatement (bit-identical on the golden vectors) runs them at this workload's 10 s / 1 s geometry.
+    b = (r.binarize(seg) if r is not None else o.binarize(seg))
+    o.speaker_count(b, chunk_step=WORKLOAD["step_s"], chunk_duration=WORKLOAD["window_s"])
+    t_seg = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    if r is not None:
+        r.clustering_stage(emb, b)
+    else:
+        o.clustering_stage(emb, b)
+    t_cl = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    sf = (0.0, WORKLOAD["step_s"], WORKLOAD["window_s"], int(WORKLOAD["audio_seconds"] * 16000))
+    (r.aggregate(diar, sf, missing=0.0, skip_average=True) if r is not None
+     else o.aggregate(diar, sf, missing=0.0, skip_average=True))
+    t_agg = time.perf_counter() - t0
+    t_step = t_stft_sample / stft_sample_items * items + t_seg + t_cl + t_agg
+    return {
+        "value": WORKLOAD["audio_seconds"] / t_step, "unit": UNIT, "cores": 1, "kind": kind,
+        "sample": "%d of %d STFT items as written (EmbeddingModel1::infer incl. per-element copy and /tmp dump), "
+                  "scaled; full binarize+count (%.3f s), clustering N=%d (%.3f s), aggregate (%.3f s); "
+                  "reference is single-threaded except ATen OpenMP inside torch::stft; -O2 build"
+                  % (stft_sample_items, items, t_seg, int((~np.isnan(emb[:, :, 0])).sum()), t_cl, t_agg),
+        "stft_s_per_item_as_written": t_stft_sample / stft_sample_items,
+        "stft_s_per_item_fft_only": t_fft_only,
+        "value_fft_only": (WORKLOAD["audio_seconds"] / (t_fft_only * items + t_seg + t_cl + t_agg)) if t_fft_only else None,
+        "host_cpus": os.cpu_count(),
+    }
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    synth = ge.load_synth()
+    geo = geometry()
+    wav_items = synth.fbank_items(102, 4, geo["L"])  # only the sampled items are needed
+    seg = synth.segmentations(1102, geo["C"], geo["F"], geo["S"])
+    emb, _ = synth.embeddings(202, geo["C"], geo["S"], geo["D"], n_speakers=4)
+    diar = synth.segmentations(2102, geo["C"], geo["F"], geo["Kd"]).astype(np.float64)
+    vals = []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline(geo, wav_items, seg, emb, diar, stft_sample_items=1)
+        if i >= args.warmup:
+            vals.append(cb["value"])
+    v = float(np.mean(vals))
+    cb["value"] = v
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": WORKLOAD["audio_seconds"] / v * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD["name"], "note": "each step = bounded sample scaled to the full workload"},
+            "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_product(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,15 @@ int sd_timer_stop(sd_ctx* ctx, int slot);
 int sd_timer_elapsed_ms(sd_ctx* ctx, int slot, float* ms); /* synchronises on the stop event */
 /* Number of kernels of this library launched on this ctx since creation. */
 int64_t sd_launch_count(const sd_ctx* ctx);
+/* Options.  SD_OPT_FORCE_EXACT_LINKAGE: always run the heap-driven linkage kernel (normally it only runs when
+ * the heap-free kernel meets a tied minimum); results are identical either way. */
+typedef enum sd_option { SD_OPT_FORCE_EXACT_LINKAGE = 1, SD_OPT_LINKAGE_THREADS = 2 /* 0 auto, 512, 1024 */ } sd_option;
+int sd_ctx_set_option(sd_ctx* ctx, int option, int value);
+/* Diagnostic counters accumulated by the kernels: [0] stale nearest-neighbour revalidations in linkage,
+ * [1] heap updates replayed after Lance-Williams sweeps, [2] problems handed from the heap-free linkage kernel to
+ * the heap-driven one, [3] cycles popping/publishing, [4] cycles revalidating, [5] cycles sweeping, [6] cycles at
+ * the request barrier (all as seen by the control warp of the heap-free kernel), [7] merges.  Synchronises. */
+int sd_debug_counters(sd_ctx* ctx, int64_t* out8, int reset);
 /* Write `bytes` of zeros into a scratch buffer larger than L2 (benchmark hygiene). */
 int sd_flush_l2(sd_ctx* ctx);
 

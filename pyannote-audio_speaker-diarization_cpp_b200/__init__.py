@@ -23,6 +23,8 @@ c_bp = C.POINTER(C.c_uint8)
 
 SD_OK, SD_ERR_INVALID, SD_ERR_CUDA, SD_ERR_ZERO_MAGNITUDE, SD_ERR_UNSUPPORTED, SD_ERR_NOMEM, SD_ERR_CAPACITY = range(7)
 
+SD_OPT_FORCE_EXACT_LINKAGE = 1
+
 # constants of the reference pipeline (speakerDiarizer.cpp:1335-1340, 2049-2050, 2429-2432)
 FRAME_STEP = 0.016875
 FRAME_DURATION = 0.016875
@@ -62,7 +64,7 @@ class SdError(RuntimeError):
 EXPORTS = [
     "sd_version", "sd_ctx_create", "sd_ctx_destroy", "sd_last_error", "sd_ctx_set_stream", "sd_ctx_stream", "sd_sync",
     "sd_malloc", "sd_free", "sd_host_alloc", "sd_host_free", "sd_memcpy_h2d", "sd_memcpy_d2h", "sd_memset",
-    "sd_timer_start", "sd_timer_stop", "sd_timer_elapsed_ms", "sd_launch_count", "sd_flush_l2",
+    "sd_timer_start", "sd_timer_stop", "sd_timer_elapsed_ms", "sd_launch_count", "sd_ctx_set_option", "sd_debug_counters", "sd_flush_l2",
     "sd_stft_default_params", "sd_stft_num_frames", "sd_stft", "sd_stft_dev", "sd_pack_wav_lens",
     "sd_fbank_default_params", "sd_fbank", "sd_fbank_dev", "sd_np_rint", "sd_closest_frame", "sd_aggregate_num_frames",
     "sd_aggregate", "sd_aggregate_dev", "sd_binarize", "sd_binarize_dev", "sd_binarize_rows", "sd_trim_num_frames",
@@ -105,6 +107,8 @@ def lib():
         "sd_timer_elapsed_ms": (i, [vp, i, c_fp]),
         "sd_launch_count": (i64, [vp]),
         "sd_flush_l2": (i, [vp]),
+        "sd_debug_counters": (i, [vp, c_lp, i]),
+        "sd_ctx_set_option": (i, [vp, i, i]),
         "sd_stft_default_params": (None, [C.POINTER(StftParams)]),
         "sd_stft_num_frames": (i64, [i, i]),
         "sd_stft": (i, [vp, vp, i, i, C.POINTER(StftParams), vp]),
@@ -238,6 +242,14 @@ class Context:
 
     def launch_count(self):
         return self.L.sd_launch_count(self.h)
+
+    def set_option(self, option, value):
+        self._check(self.L.sd_ctx_set_option(self.h, int(option), int(value)))
+
+    def debug_counters(self, reset=True):
+        out = np.zeros(8, np.int64)
+        self._check(self.L.sd_debug_counters(self.h, out.ctypes.data_as(c_lp), int(reset)))
+        return out
 
     def flush_l2(self):
         self._check(self.L.sd_flush_l2(self.h))

@@ -96,6 +96,8 @@ int sd_ctx_create(int device, sd_ctx** out) {
     cudaMalloc(&ctx->d_status, sizeof(int));
     cudaMemset(ctx->d_status, 0, sizeof(int));
     cudaHostAlloc(&ctx->h_status, sizeof(int), cudaHostAllocDefault);
+    cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long));
+    cudaMemset(ctx->d_stats, 0, 8 * sizeof(unsigned long long));
     CtxExtra* ex = new CtxExtra();
     if (cudaHostAlloc(&ex->ring.base, kRingSlots * kRingSlotBytes, cudaHostAllocDefault) == cudaSuccess) {
         for (int i = 0; i < kRingSlots; ++i) cudaEventCreateWithFlags(&ex->ring.ev[i], cudaEventDisableTiming);
@@ -119,6 +121,7 @@ void sd_ctx_destroy(sd_ctx* ctx) {
     if (ctx->d_mel) cudaFree(ctx->d_mel);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->d_status) cudaFree(ctx->d_status);
+    if (ctx->d_stats) cudaFree(ctx->d_stats);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     for (int i = 0; i < 16; ++i) {
         cudaEventDestroy(ctx->ev_start[i]);
@@ -214,6 +217,30 @@ int sd_timer_elapsed_ms(sd_ctx* ctx, int slot, float* ms) {
     return SD_OK;
 }
 int64_t sd_launch_count(const sd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int sd_ctx_set_option(sd_ctx* ctx, int option, int value) {
+    if (!ctx) return SD_ERR_INVALID;
+    switch (option) {
+        case SD_OPT_FORCE_EXACT_LINKAGE:
+            ctx->force_exact_linkage = value != 0;
+            return SD_OK;
+        case SD_OPT_LINKAGE_THREADS:
+            if (value != 0 && value != 512 && value != 1024)
+                return ctx->fail(SD_ERR_INVALID, "SD_OPT_LINKAGE_THREADS must be 0, 512 or 1024");
+            ctx->linkage_threads = value;
+            return SD_OK;
+        default:
+            return ctx->fail(SD_ERR_INVALID, "unknown option %d", option);
+    }
+}
+
+int sd_debug_counters(sd_ctx* ctx, int64_t* out8, int reset) {
+    if (!ctx || !out8) return SD_ERR_INVALID;
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    SD_CUDA(ctx, cudaMemcpy(out8, ctx->d_stats, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (reset) SD_CUDA(ctx, cudaMemset(ctx->d_stats, 0, 8 * sizeof(int64_t)));
+    return SD_OK;
+}
 
 int sd_flush_l2(sd_ctx* ctx) {
     if (!ctx) return SD_ERR_INVALID;

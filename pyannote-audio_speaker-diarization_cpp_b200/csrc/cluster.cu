@@ -26,23 +26,53 @@ namespace sdb {
 // gather + normalise
 // ------------------------------------------------------------------------------------------------
 
-// x[i][:] = emb[keep[i]][:];  xn[i][:] = x[i][:] / (double)(float)sqrt(sum_k x^2)  (sum in k order, fp64)
-__global__ void __launch_bounds__(128)
+// x[i][:] = emb[keep[i]][:];  xn[i][:] = x[i][:] / (double)(float)sqrt(sum_k x^2)
+// One warp per row: coalesced loads (lane l holds elements l, l+32, ...), and the squared norm is accumulated
+// strictly in k order (the reference's sequential fp64 sum) by broadcasting one element at a time.
+constexpr int GN_MAX_PER_LANE = 16;  // D <= 512
+__global__ void __launch_bounds__(256)
     gather_normalize_kernel(const double* __restrict__ emb, const int* __restrict__ keep, int N, int D,
                             double* __restrict__ x, double* __restrict__ xn) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (i >= N) return;
     const double* src = emb + (size_t)(keep ? keep[i] : i) * D;
-    double ss = 0.0;
-    for (int k = 0; k < D; ++k) {
-        const double v = src[k];
-        if (x) x[(size_t)i * D + k] = v;
-        ss = __dadd_rn(ss, __dmul_rn(v, v));
-    }
-    const double norm = (double)(float)__dsqrt_rn(ss);  // L2Norm returns float, speakerDiarizer.cpp:332
-    for (int k = 0; k < D; ++k) {
-        const double v = src[k];
-        xn[(size_t)i * D + k] = norm != 0.0 ? __ddiv_rn(v, norm) : v;
+    if (D <= 32 * GN_MAX_PER_LANE) {
+        double v[GN_MAX_PER_LANE];
+#pragma unroll
+        for (int q = 0; q < GN_MAX_PER_LANE; ++q) {
+            const int k = q * 32 + lane;
+            v[q] = k < D ? src[k] : 0.0;
+        }
+        double ss = 0.0;
+#pragma unroll
+        for (int q = 0; q < GN_MAX_PER_LANE; ++q) {
+            if (q * 32 < D) {
+                for (int l = 0; l < 32; ++l) {
+                    const double e = __shfl_sync(0xffffffffu, v[q], l);
+                    if (q * 32 + l < D) ss = __dadd_rn(ss, __dmul_rn(e, e));
+                }
+            }
+        }
+        const double norm = (double)(float)__dsqrt_rn(ss);  // L2Norm returns float, speakerDiarizer.cpp:332
+#pragma unroll
+        for (int q = 0; q < GN_MAX_PER_LANE; ++q) {
+            const int k = q * 32 + lane;
+            if (k < D) {
+                if (x) x[(size_t)i * D + k] = v[q];
+                if (xn) xn[(size_t)i * D + k] = norm != 0.0 ? __ddiv_rn(v[q], norm) : v[q];
+            }
+        }
+    } else if (lane == 0) {  // very wide rows: plain sequential fallback
+        double ss = 0.0;
+        for (int k = 0; k < D; ++k) {
+            const double e = src[k];
+            if (x) x[(size_t)i * D + k] = e;
+            ss = __dadd_rn(ss, __dmul_rn(e, e));
+        }
+        const double norm = (double)(float)__dsqrt_rn(ss);
+        if (xn)
+            for (int k = 0; k < D; ++k) xn[(size_t)i * D + k] = norm != 0.0 ? __ddiv_rn(src[k], norm) : src[k];
     }
 }
 
@@ -61,7 +91,9 @@ constexpr int PD_KC = 16;
 // Dm[i][j] = sqrt(sum_k (x_ik - x_jk)^2), k ascending, mul then add, no FMA.  Full square (both triangles
 // are produced by identical arithmetic since (a-b)^2 == (b-a)^2 bit for bit).
 __global__ void __launch_bounds__(256)
-    pdist_f64_kernel(const double* __restrict__ x, int N, int D, double* __restrict__ Dm, long ld) {
+    pdist_f64_kernel(const double* __restrict__ x, int N, int D, double* __restrict__ Dm, long ld,
+                     const int* __restrict__ run_flag) {
+    if (run_flag && !*run_flag) return;
     __shared__ double A[PD_KC][PD_TILE + 1];
     __shared__ double B[PD_KC][PD_TILE + 1];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -145,12 +177,15 @@ struct LinkWork {
     int* cid;       // [N]
     int* nbr;       // [N]   nearest-neighbour candidate among higher indices
     double* lb;     // [N]   lower bound of the distance to it
+    double* cur;    // [N]   mirror of D[z][nbr[z]]
     int* pos_of;    // heap: key -> slot
     int* key_at;    // heap: slot -> key
     double* hval;   // heap: slot -> value
     unsigned* bitmap;  // [ceil(N/32)] rows whose bound dropped in this merge
     double* Z;      // [N-1][4]
     int* status;    // device status word
+    unsigned long long* stats;  // [0] stale revalidations, [1] heap updates replayed after sweeps, [2] fallbacks
+    void* fast_scratch;         // state of the heap-free kernel when it does not fit in shared memory
 };
 
 struct MinIdx {
@@ -176,7 +211,8 @@ __device__ __forceinline__ MinIdx warp_min(MinIdx m) {
 }
 
 // find_min_dist for all rows at start (clustering.cpp:314-318): one warp per row
-__global__ void __launch_bounds__(256) rowmin_init_kernel(LinkWork w, int n) {
+__global__ void __launch_bounds__(256) rowmin_init_kernel(LinkWork w, int n, const int* __restrict__ run_flag) {
+    if (run_flag && !*run_flag) return;
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= n) return;
@@ -207,45 +243,61 @@ __global__ void __launch_bounds__(256) rowmin_init_kernel(LinkWork w, int n) {
 }
 
 // ---- indexed binary min-heap, comparison rules of clustering.cpp:28-119 ----
+// The reference sifts with pairwise swaps; moving a "hole" instead performs the same comparisons in the
+// same order and leaves the same arrangement, with one dependent shared-memory load per level.
 struct Heap {
     int* pos_of;
     int* key_at;
     double* val;
     int n;
-    __device__ __forceinline__ void swp(int a, int b) {
-        const double tv = val[a];
-        val[a] = val[b];
-        val[b] = tv;
-        const int ka = key_at[a], kb = key_at[b];
-        key_at[a] = kb;
-        key_at[b] = ka;
-        pos_of[ka] = b;
-        pos_of[kb] = a;
+    __device__ __forceinline__ void place(int i, int key, double v) {
+        val[i] = v;
+        key_at[i] = key;
+        pos_of[key] = i;
     }
-    __device__ __forceinline__ void down(int i) {
+    __device__ __forceinline__ void down(int i, int key, double v) {
         for (int c = 2 * i + 1; c < n; c = 2 * i + 1) {
-            if (c + 1 < n && val[c + 1] < val[c]) ++c;
-            if (!(val[i] > val[c])) break;
-            swp(i, c);
+            double cv = val[c];
+            if (c + 1 < n) {
+                const double rv = val[c + 1];
+                if (rv < cv) {
+                    cv = rv;
+                    ++c;
+                }
+            }
+            if (!(v > cv)) break;
+            place(i, key_at[c], cv);
             i = c;
         }
+        place(i, key, v);
     }
-    __device__ __forceinline__ void up(int i) {
+    __device__ __forceinline__ void up(int i, int key, double v) {
         while (i > 0) {
             const int p = (i - 1) >> 1;
-            if (!(val[p] > val[i])) break;
-            swp(i, p);
+            const double pv = val[p];
+            if (!(pv > v)) break;
+            place(i, key_at[p], pv);
             i = p;
         }
+        place(i, key, v);
     }
-    __device__ __forceinline__ void set(int key, double v) {
+    // sift_down(i) of the element already stored at slot i
+    __device__ __forceinline__ void down_at(int i) { down(i, key_at[i], val[i]); }
+    __device__ __forceinline__ void set(int key, double v) {  // change_value, clustering.cpp:109-118
         const int i = pos_of[key];
         const double old = val[i];
-        val[i] = v;
         if (v < old)
-            up(i);
+            up(i, key, v);
         else
-            down(i);
+            down(i, key, v);
+    }
+    __device__ __forceinline__ void remove_min() {  // clustering.cpp:103-107: swap(0, n-1); --n; sift_down(0)
+        const int last = n - 1;
+        const int k0 = key_at[0], kl = key_at[last];
+        const double v0 = val[0], vl = val[last];
+        place(last, k0, v0);
+        n = last;
+        if (n > 0) down(0, kl, vl);
     }
 };
 
@@ -258,6 +310,7 @@ __device__ __forceinline__ double centroid_update(double dxi, double dyi, double
 }
 
 constexpr int LK_THREADS = 1024;
+constexpr int LK_WORKERS = LK_THREADS - 32;  // warp 0 owns the heap; warps 1..31 sweep rows
 
 __device__ __forceinline__ MinIdx block_min(MinIdx m, MinIdx* red) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -273,20 +326,110 @@ __device__ __forceinline__ MinIdx block_min(MinIdx m, MinIdx* red) {
     return red[32];
 }
 
+// Where the per-cluster state lives.  ALL: everything in shared memory (N <= ~5 000); HEAP: only the heap in
+// shared memory (N <= ~14 000); GLOBAL: everything in the (L1/L2-cached) global workspace.
+enum LinkMode { LK_SMEM_ALL = 0, LK_SMEM_HEAP = 1, LK_GLOBAL = 2 };
+
+__host__ __device__ inline size_t link_smem_bytes(int mode, int n) {
+    const size_t N = (size_t)((n + 1) / 2 * 2);
+    if (mode == LK_SMEM_ALL) return N * (8 + 8 + 8 + 4 + 4 + 4 + 4 + 4) + ((size_t)n / 32 + 2) * 4 + 64;
+    if (mode == LK_SMEM_HEAP) return N * (8 + 4 + 4) + 64;
+    return 64;
+}
+
 // One persistent CTA performs all N-1 merges of one problem (grid.x = number of independent problems).
-__global__ void __launch_bounds__(LK_THREADS) linkage_kernel(const LinkWork* __restrict__ works, const int* ns) {
+//
+// Per merge, fast path = two block barriers:
+//   thread 0   : read heap top, compare with the cached current distance of its candidate pair
+//   ---- barrier ----
+//   warp 0     : remove_min + dendrogram row           | warps 1..31 : Lance-Williams sweep over all live z
+//   ---- barrier ----
+//   warp 0     : reduce y's new nearest neighbour, replay heap updates for rows whose bound dropped
+// `cur[z]` mirrors D[z][nbr[z]] exactly (it is refreshed whenever that entry or nbr[z] changes), so the
+// reference's "dist == D[x][y]" validity test needs no global-memory round trip.
+template <int MODE>
+__global__ void __launch_bounds__(LK_THREADS)
+    linkage_kernel(const LinkWork* __restrict__ works, const int* ns, const int* __restrict__ run_flags) {
+    if (run_flags && !run_flags[blockIdx.x]) return;
     const LinkWork w = works[blockIdx.x];
     const int n = ns[blockIdx.x];
+    if (threadIdx.x == 0 && run_flags && w.stats) w.stats[2] += 1;  // fell back from the heap-free path
+    extern __shared__ __align__(16) unsigned char lk_smem[];
     __shared__ MinIdx red[33];
-    __shared__ int s_x, s_y, s_nx, s_ny, s_stale;
+    __shared__ int s_x, s_y, s_nx, s_ny, s_stale, s_abort;
     __shared__ double s_dist;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (n < 2) return;
 
+    // ---- state pointers ----
+    double *hval, *lb, *cur;
+    int *pos_of, *key_at, *nbr, *size, *cid;
+    unsigned* bitmap;
+    {
+        const size_t N = (size_t)((n + 1) / 2 * 2);
+        unsigned char* p = lk_smem;
+        if (MODE == LK_SMEM_ALL || MODE == LK_SMEM_HEAP) {
+            hval = reinterpret_cast<double*>(p);
+            p += N * 8;
+        } else
+            hval = w.hval;
+        if (MODE == LK_SMEM_ALL) {
+            lb = reinterpret_cast<double*>(p);
+            p += N * 8;
+            cur = reinterpret_cast<double*>(p);
+            p += N * 8;
+        } else {
+            lb = w.lb;
+            cur = w.cur;
+        }
+        if (MODE == LK_SMEM_ALL || MODE == LK_SMEM_HEAP) {
+            pos_of = reinterpret_cast<int*>(p);
+            p += N * 4;
+            key_at = reinterpret_cast<int*>(p);
+            p += N * 4;
+        } else {
+            pos_of = w.pos_of;
+            key_at = w.key_at;
+        }
+        if (MODE == LK_SMEM_ALL) {
+            nbr = reinterpret_cast<int*>(p);
+            p += N * 4;
+            size = reinterpret_cast<int*>(p);
+            p += N * 4;
+            cid = reinterpret_cast<int*>(p);
+            p += N * 4;
+            bitmap = reinterpret_cast<unsigned*>(p);
+        } else {
+            nbr = w.nbr;
+            size = w.size;
+            cid = w.cid;
+            bitmap = w.bitmap;
+        }
+    }
+    // rowmin_init_kernel left the initial state in the global workspace
+    for (int i = tid; i < n; i += LK_THREADS) {
+        if (MODE != LK_GLOBAL && i < n - 1) {
+            hval[i] = w.hval[i];
+            pos_of[i] = i;
+            key_at[i] = i;
+        }
+        if (MODE == LK_SMEM_ALL) {
+            size[i] = 1;
+            cid[i] = i;
+            if (i < n - 1) {
+                nbr[i] = w.nbr[i];
+                lb[i] = w.lb[i];
+            }
+        }
+        if (i < n - 1) cur[i] = w.lb[i];  // D[i][nbr[i]] == the row minimum right after initialisation
+    }
+    if (tid == 0) s_abort = 0;
+    __syncthreads();
+
     Heap h;
-    h.pos_of = w.pos_of;
-    h.key_at = w.key_at;
-    h.val = w.hval;
+    h.pos_of = pos_of;
+    h.key_at = key_at;
+    h.val = hval;
     h.n = n - 1;
 
     // heapify: the reference sifts down i = size/2 .. 0 (clustering.cpp:94-96).  Sift-downs of nodes on one
@@ -295,30 +438,51 @@ __global__ void __launch_bounds__(LK_THREADS) linkage_kernel(const LinkWork* __r
     {
         const int last = h.n / 2;
         int top = 0;
-        while (((2 << top) - 1) <= last) ++top;  // deepest level that contains an index <= last
+        while (((2 << top) - 1) <= last) ++top;
         for (int lev = top; lev >= 0; --lev) {
             const int first = (1 << lev) - 1;
             int end = (2 << lev) - 2;
             if (end > last) end = last;
             for (int i = first + tid; i <= end; i += LK_THREADS)
-                if (i < h.n) h.down(i);
+                if (i < h.n) h.down_at(i);
             __syncthreads();
         }
     }
 
     const int nwords = (n + 31) >> 5;
     for (int k = 0; k < n - 1; ++k) {
-        // ---- pop the closest pair, revalidating stale candidates (clustering.cpp:323-339) ----
+        // ---- closest pair, revalidating stale candidates (clustering.cpp:323-339) ----
         int tries = 0;
+        bool forced = false;
         for (;;) {
             if (tid == 0) {
-                const int x = h.key_at[0];
-                const double dist = h.val[0];
-                const int y = w.nbr[x];
+                int x, y;
+                double dist;
+                if (!forced) {
+                    x = h.key_at[0];
+                    dist = h.val[0];
+                    y = nbr[x];
+                    s_stale = (y < 0) || !(dist == cur[x]);
+                } else {  // loop bound of the reference reached: continue with the recomputed pair
+                    x = s_x;
+                    y = s_y;
+                    dist = s_dist;
+                    s_stale = 0;
+                }
                 s_x = x;
                 s_y = y;
                 s_dist = dist;
-                s_stale = (y < 0) || !(dist == w.D[(size_t)x * w.ld + y]);
+                if (!s_stale) {
+                    if (y < 0) {
+                        s_abort = 1;
+                    } else {
+                        const int nx = size[x], ny = size[y];
+                        s_nx = nx;
+                        s_ny = ny;
+                        size[x] = 0;  // clustering.cpp:356-357 (visible to the sweep after the barrier)
+                        size[y] = nx + ny;
+                    }
+                }
             }
             __syncthreads();
             if (!s_stale) break;
@@ -328,7 +492,7 @@ __global__ void __launch_bounds__(LK_THREADS) linkage_kernel(const LinkWork* __r
             m.i = -1;
             const double* r = w.D + (size_t)x * w.ld;
             for (int i = x + 1 + tid; i < n; i += LK_THREADS) {
-                if (w.size[i] == 0) continue;
+                if (size[i] == 0) continue;
                 const double d = r[i];
                 if (d < m.v) {
                     m.v = d;
@@ -336,88 +500,89 @@ __global__ void __launch_bounds__(LK_THREADS) linkage_kernel(const LinkWork* __r
                 }
             }
             m = block_min(m, red);
+            ++tries;
             if (tid == 0) {
+                if (w.stats) w.stats[0] += 1;
                 const double v = m.i >= 0 ? m.v : INFINITY;
-                w.nbr[x] = m.i;
-                w.lb[x] = v;
+                nbr[x] = m.i;
+                lb[x] = v;
+                cur[x] = v;
                 h.set(x, v);
                 s_y = m.i;
                 s_dist = v;
             }
-            ++tries;
-            if (tries >= n - k) {  // loop bound of the reference: fall through with the recomputed pair
-                __syncthreads();
-                break;
-            }
-            __syncthreads();
+            forced = tries >= n - k;
         }
-        const int x = s_x, y = s_y;
-        const double dist = s_dist;
-        if (y < 0) {  // no live partner (only reachable through NaN distances): the reference indexes out of range
+        if (s_abort) {  // no live partner: only reachable through NaN distances (the reference indexes out of range)
             if (tid == 0) atomicExch(w.status, SD_ERR_INVALID);
             return;
         }
-        if (tid == 0) {
-            h.swp(0, h.n - 1);  // remove_min, clustering.cpp:103-107
-            h.n -= 1;
-            h.down(0);
-            int ix = w.cid[x], iy = w.cid[y];
-            const int nx = w.size[x], ny = w.size[y];
-            if (ix > iy) {
-                const int t = ix;
-                ix = iy;
-                iy = t;
-            }
-            double* z = w.Z + 4 * (size_t)k;
-            z[0] = ix;
-            z[1] = iy;
-            z[2] = dist;
-            z[3] = nx + ny;
-            s_nx = nx;
-            s_ny = ny;
-            w.size[x] = 0;
-            w.size[y] = nx + ny;
-            w.cid[y] = n + k;
-        }
-        __syncthreads();
-        h.n = (n - 1) - (k + 1);  // every thread tracks the heap size
-        const int nx = s_nx, ny = s_ny;
-
-        // ---- Lance-Williams update of row/column y, neighbour fix-ups, and y's own nearest neighbour
-        //      (clustering.cpp:361-404), fused into one sweep over z ----
-        const double* rowx = w.D + (size_t)x * w.ld;
-        double* rowy = w.D + (size_t)y * w.ld;
+        const int x = s_x, y = s_y, nx = s_nx, ny = s_ny;
+        const double dist = s_dist;
         MinIdx ym;
         ym.v = INFINITY;
         ym.i = -1;
-        for (int z0 = 0; z0 < n; z0 += LK_THREADS) {
-            const int z = z0 + tid;
-            bool changed = false;
-            if (z < n && z != y && w.size[z] != 0) {
-                const double nd = centroid_update(rowx[z], rowy[z], dist, nx, ny);
-                rowy[z] = nd;
-                w.D[(size_t)z * w.ld + y] = nd;
-                if (z < x && w.nbr[z] == x) w.nbr[z] = y;
-                if (z < y) {
-                    if (nd < w.lb[z]) {
-                        w.nbr[z] = y;
-                        w.lb[z] = nd;
-                        changed = true;
-                    }
-                } else if (nd < ym.v) {  // z > y, ascending within a thread: first strict minimum
-                    ym.v = nd;
-                    ym.i = z;
-                }
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, changed);
-            if (lane == 0 && (z0 >> 5) + warp < nwords) w.bitmap[(z0 >> 5) + warp] = bal;
-        }
-        ym = block_min(ym, red);  // contains __syncthreads: bitmap, lb, nbr are visible afterwards
-
-        // ---- replay the heap updates in increasing z, exactly as the sequential loop would ----
         if (warp == 0) {
+            if (lane == 0) {
+                h.remove_min();
+                int ix = cid[x], iy = cid[y];
+                if (ix > iy) {
+                    const int t = ix;
+                    ix = iy;
+                    iy = t;
+                }
+                double* z = w.Z + 4 * (size_t)k;  // clustering.cpp:347-354
+                z[0] = ix;
+                z[1] = iy;
+                z[2] = dist;
+                z[3] = nx + ny;
+                cid[y] = n + k;
+            }
+        } else {
+            // ---- Lance-Williams update of row/column y, neighbour fix-ups and y's own nearest neighbour
+            //      (clustering.cpp:361-404) fused into one sweep over z ----
+            const double* rowx = w.D + (size_t)x * w.ld;
+            double* rowy = w.D + (size_t)y * w.ld;
+            const int wt = tid - 32;
+            for (int z0 = 0; z0 < n; z0 += LK_WORKERS) {
+                const int z = z0 + wt;
+                bool changed = false;
+                if (z < n && z != y && size[z] != 0) {
+                    const double nd = centroid_update(rowx[z], rowy[z], dist, nx, ny);
+                    rowy[z] = nd;
+                    w.D[(size_t)z * w.ld + y] = nd;
+                    if (z < y) {
+                        int nb = nbr[z];
+                        if (z < x && nb == x) nb = y;  // clustering.cpp:374-378
+                        if (nd < lb[z]) {              // clustering.cpp:381-392
+                            nb = y;
+                            lb[z] = nd;
+                            changed = true;
+                        }
+                        if (nb == y) cur[z] = nd;  // keep cur[z] == D[z][nbr[z]]
+                        nbr[z] = nb;
+                    } else if (nd < ym.v) {  // z > y, ascending within a thread: first strict minimum
+                        ym.v = nd;
+                        ym.i = z;
+                    }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, changed);
+                const int word = (z0 >> 5) + (warp - 1);
+                if (lane == 0 && word < nwords) bitmap[word] = bal;
+            }
+            ym = warp_min(ym);
+            if (lane == 0) red[warp] = ym;
+        }
+        __syncthreads();
+        // ---- warp 0: y's nearest neighbour, then the heap updates in increasing z (sequential order) ----
+        if (warp == 0) {
+            MinIdx t;
+            t.v = INFINITY;
+            t.i = -1;
+            if (lane > 0) t = red[lane];
+            t = warp_min(t);
             for (int wb = 0; wb < nwords; wb += 32) {
-                const unsigned word = (wb + lane < nwords) ? w.bitmap[wb + lane] : 0u;
+                const unsigned word = (wb + lane < nwords) ? bitmap[wb + lane] : 0u;
                 unsigned nz = __ballot_sync(0xffffffffu, word != 0u);
                 while (nz) {
                     const int src = __ffs(nz) - 1;
@@ -428,18 +593,387 @@ __global__ void __launch_bounds__(LK_THREADS) linkage_kernel(const LinkWork* __r
                             const int b = __ffs(bits) - 1;
                             bits &= bits - 1;
                             const int z = ((wb + src) << 5) + b;
-                            h.set(z, w.lb[z]);
+                            h.set(z, lb[z]);
+                            if (w.stats) w.stats[1] += 1;
                         }
                     }
                 }
             }
-            if (lane == 0 && y < n - 1 && ym.i != -1) {  // clustering.cpp:395-404
-                w.nbr[y] = ym.i;
-                w.lb[y] = ym.v;
-                h.set(y, ym.v);
+            if (lane == 0 && y < n - 1 && t.i != -1) {  // clustering.cpp:395-404
+                nbr[y] = t.i;
+                lb[y] = t.v;
+                cur[y] = t.v;
+                h.set(y, t.v);
             }
         }
-        __syncthreads();
+        // no barrier: only thread 0 touches the heap / s_* until the next one, the other warps wait there
+    }
+}
+
+// ---- fast path: heap-free merges with a uniqueness proof ----------------------------------------------
+//
+// The binary heap of the reference only decides *which* row is examined next when several rows share the
+// smallest bound.  Whenever the smallest bound is attained by exactly one row, every valid heap -- whatever its
+// internal arrangement -- returns that row, so the whole state sequence (revalidations, merges, updates) is
+// the one the reference goes through.  This kernel therefore keeps no heap: the (value, row, multiplicity) of
+// the smallest bound is a block-wide reduction fused into the Lance-Williams sweep, and the ~40 dependent
+// decrease-key operations per merge of the heap version disappear.  If the minimum is ever tied (or the
+// reference's pop-loop bound is reached) the kernel raises `*need_exact` and stops; the exact heap kernel
+// then redoes the problem from a fresh distance matrix.  Both paths give the reference's Z bit for bit.
+struct Top {
+    double v;  // smallest value (never NaN, never negative: distances and +inf)
+    int i;     // lowest row attaining it (-1: none)
+    int c;     // how many rows attain it
+};
+
+// Warp argmin of non-negative doubles with multiplicity.  For v >= 0 the IEEE bit pattern is monotone, so the
+// 64-bit minimum is two 32-bit redux.sync steps; ties resolve to the lowest index.  A lane with c == 0
+// contributes nothing (it must pass v = +inf).
+__device__ __forceinline__ Top warp_top(double v, int i, int c) {
+    const unsigned full = 0xffffffffu;
+    const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+    const unsigned mh = __reduce_min_sync(full, hi);
+    const bool cand = (hi == mh) && c > 0;
+    const unsigned b = __ballot_sync(full, cand);
+    Top t;
+    if (b == 0u) {  // nothing to reduce
+        t.v = INFINITY;
+        t.i = -1;
+        t.c = 0;
+    } else if ((b & (b - 1u)) == 0u) {  // common case: the high words already single out one lane
+        const int src = __ffs(b) - 1;
+        t.v = __shfl_sync(full, v, src);
+        t.i = __shfl_sync(full, i, src);
+        t.c = __shfl_sync(full, c, src);
+    } else {
+        const unsigned ml = __reduce_min_sync(full, cand ? lo : 0xffffffffu);
+        const bool is_min = cand && (lo == ml);
+        t.c = (int)__reduce_add_sync(full, is_min ? (unsigned)c : 0u);
+        t.i = (int)__reduce_min_sync(full, is_min ? (unsigned)i : 0xffffffffu);
+        t.v = __hiloint2double((int)mh, (int)ml);
+    }
+    return t;
+}
+
+// s / d for a divisor whose correctly rounded reciprocal r = RN(1/d) is known (Markstein): q = RN(s r),
+// rem = s - q d exactly (FMA), result RN(q + rem r) == RN(s / d) whenever d's significand is not all ones --
+// d is a cluster size here.  Non-finite inputs take the library division.
+__device__ __forceinline__ double div_by(double s, double d, double r) {
+    const double q = __dmul_rn(s, r);
+    const double rem = __fma_rn(-q, d, s);
+    const double q1 = __fma_rn(rem, r, q);
+    return isfinite(s) ? q1 : __ddiv_rn(s, d);
+}
+
+enum FastMode { LF_SMEM = 0, LF_GLOBAL = 1 };
+
+enum FastOp { OP_MERGE = 0, OP_RESCAN = 1, OP_ABORT = 2 };
+
+struct MergeRec {
+    int op, x, y, nx, ny;
+    double dist;
+};
+
+struct GroupMin {  // smallest bound of a 32-row group: value, lowest row attaining it, multiplicity
+    double v;
+    int i;
+    int c;
+};
+
+__host__ __device__ inline size_t linkfast_smem_bytes(int n) {
+    const size_t N = (size_t)((n + 31) / 32 * 32);
+    return N * (8 + 8 + 4 + 4 + 4) + (N / 32) * sizeof(GroupMin) + 64;
+}
+
+// Heap-free linkage, one persistent CTA per problem.
+//
+//   warp 0 ("control")  keeps the smallest bound through a two-level structure -- per 32-row group
+//                        (min value, lowest row, multiplicity) in shared memory -- pops the closest pair and
+//                        publishes either the merge or a request to revalidate a stale candidate;
+//   all warps           execute the request: rescan one row (find_min_dist) or sweep the live rows
+//                        (Lance-Williams update of row/column y, neighbour fix-ups, group minima, y's next
+//                        nearest neighbour).  Global loads are issued before any dependent work so that each
+//                        phase pays the L2 latency once.
+// Two block barriers per request.
+template <int MODE, int T>
+__global__ void __launch_bounds__(T)
+    linkage_fast_kernel(const LinkWork* __restrict__ works, const int* ns, int* __restrict__ need_exact) {
+    const LinkWork w = works[blockIdx.x];
+    const int n = ns[blockIdx.x];
+    extern __shared__ __align__(16) unsigned char lk_smem[];
+    constexpr int NW = T / 32;
+    constexpr int PF = 4;  // groups (sweep) / strides (rescan) whose loads are in flight together
+    __shared__ MergeRec rec;
+    __shared__ double part_v[NW];
+    __shared__ int part_i[NW];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) need_exact[blockIdx.x] = 0;
+    if (n < 2) return;
+
+    const int NG = (n + 31) / 32;        // groups of 32 rows
+    const int HG = (n - 1 + 31) / 32;    // groups that contain heap rows (0 .. n-2)
+    double *lb, *cur;
+    GroupMin* gm;
+    int *nbr, *size, *cid;
+    {
+        const size_t N = (size_t)NG * 32;
+        unsigned char* p = MODE == LF_SMEM ? lk_smem : reinterpret_cast<unsigned char*>(w.fast_scratch);
+        gm = reinterpret_cast<GroupMin*>(p);
+        p += (size_t)NG * sizeof(GroupMin);
+        lb = reinterpret_cast<double*>(p);
+        p += N * 8;
+        cur = reinterpret_cast<double*>(p);
+        p += N * 8;
+        nbr = reinterpret_cast<int*>(p);
+        p += N * 4;
+        size = reinterpret_cast<int*>(p);
+        p += N * 4;
+        cid = reinterpret_cast<int*>(p);
+    }
+    for (int i = tid; i < NG * 32; i += T) {
+        size[i] = i < n ? 1 : 0;
+        cid[i] = i;
+        nbr[i] = i < n - 1 ? w.nbr[i] : -1;
+        lb[i] = i < n - 1 ? w.lb[i] : INFINITY;
+        cur[i] = lb[i];  // D[i][nbr[i]] equals the row minimum right after initialisation
+    }
+    __syncthreads();
+
+    auto store_group = [&](int g, const Top& t) {
+        if (lane == 0) {
+            GroupMin e;
+            e.v = t.v;
+            e.i = t.i;
+            e.c = t.c;
+            gm[g] = e;
+        }
+    };
+    // group minimum over live heap rows; all lanes of the calling warp
+    auto group_min = [&](int g) {
+        const int z = g * 32 + lane;
+        const bool in = z < n - 1 && size[z] != 0;
+        store_group(g, warp_top(in ? lb[z] : INFINITY, z, in ? 1 : 0));
+    };
+    // smallest bound over all groups (control warp)
+    auto select_top = [&]() -> Top {
+        Top m;
+        m.v = INFINITY;
+        m.i = -1;
+        m.c = 0;
+        for (int g = lane; g < HG; g += 32) {
+            const GroupMin e = gm[g];
+            if (e.c == 0) continue;
+            if (m.c == 0 || e.v < m.v) {
+                m.v = e.v;
+                m.i = e.i;
+                m.c = e.c;
+            } else if (e.v == m.v)
+                m.c += e.c;  // g ascending: the stored row stays the lowest
+        }
+        return warp_top(m.v, m.i, m.c);
+    };
+    for (int g = warp; g < HG; g += NW) group_min(g);
+    __syncthreads();
+
+    int k = 0;
+    int tries = 0;
+    long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0, ta, tb;
+    for (;;) {
+        ta = clock64();
+        // ================= control warp: pop, decide, publish =================
+        if (warp == 0) {
+            int op = OP_MERGE, x = -1, y = -1;
+            double dist = 0.0;
+            if (k >= n - 1) {
+                op = OP_ABORT;  // all merges done
+            } else {
+                const Top top = select_top();
+                x = top.i;
+                dist = top.v;
+                if (top.c != 1 || x < 0 || tries >= n - k) {  // tied minimum: the heap order would matter
+                    if (lane == 0) need_exact[blockIdx.x] = 1;
+                    op = OP_ABORT;
+                } else {
+                    y = nbr[x];
+                    if (!(y >= 0 && dist == cur[x])) op = OP_RESCAN;  // stale candidate (clustering.cpp:329)
+                }
+            }
+            if (lane == 0) {
+                rec.op = op;
+                rec.x = x;
+                rec.y = y;
+                rec.dist = dist;
+                if (op == OP_MERGE) {
+                    const int nx = size[x], ny = size[y];
+                    const int ix = cid[x], iy = cid[y];
+                    rec.nx = nx;
+                    rec.ny = ny;
+                    double* z = w.Z + 4 * (size_t)k;  // clustering.cpp:347-358
+                    z[0] = ix < iy ? ix : iy;
+                    z[1] = ix < iy ? iy : ix;
+                    z[2] = dist;
+                    z[3] = nx + ny;
+                    size[x] = 0;
+                    size[y] = nx + ny;
+                    cid[y] = n + k;
+                }
+            }
+        }
+        tb = clock64();
+        c0 += tb - ta;  // select + publish (warp 0)
+        __syncthreads();  // B1: the request is published
+        ta = clock64();
+        c1 += ta - tb;  // B1
+        const int op = rec.op;
+        if (op == OP_ABORT) {
+            if (tid == 0 && w.stats) {  // cycle breakdown as seen by the control warp (sd_debug_counters)
+                w.stats[3] += c0;       // pop + publish
+                w.stats[4] += c2 + c3;  // revalidation (row rescans)
+                w.stats[5] += c4 + c5;  // Lance-Williams sweeps
+                w.stats[6] += c1;       // waiting for the request barrier
+                w.stats[7] += (unsigned long long)(n - 1);
+            }
+            return;
+        }
+        const int x = rec.x;
+        if (op == OP_RESCAN) {
+            // find_min_dist(x), clustering.cpp:259-276: first minimum in index order over live i > x
+            const double* r = w.D + (size_t)x * w.ld;
+            double bv = INFINITY;
+            int bi = -1;
+            for (int i0 = x + 1 + tid; i0 < n; i0 += T * PF) {
+                double d[PF];
+#pragma unroll
+                for (int u = 0; u < PF; ++u) {
+                    const int i = i0 + u * T;
+                    d[u] = i < n ? r[i] : INFINITY;
+                }
+#pragma unroll
+                for (int u = 0; u < PF; ++u) {
+                    const int i = i0 + u * T;
+                    if (i < n && size[i] != 0 && d[u] < bv) {
+                        bv = d[u];
+                        bi = i;
+                    }
+                }
+            }
+            const Top m = warp_top(bi >= 0 ? bv : INFINITY, bi, bi >= 0 ? 1 : 0);
+            if (lane == 0) {
+                part_v[warp] = m.v;
+                part_i[warp] = m.i;
+            }
+            tb = clock64();
+            c2 += tb - ta;  // rescan work
+            __syncthreads();  // B2
+            if (warp == 0) {
+                const bool has = lane < NW && part_i[lane] >= 0;
+                const Top t = warp_top(has ? part_v[lane] : INFINITY, has ? part_i[lane] : -1, has ? 1 : 0);
+                if (lane == 0) {
+                    const double v = t.i >= 0 ? t.v : INFINITY;
+                    nbr[x] = t.i;
+                    lb[x] = v;
+                    cur[x] = v;
+                    if (w.stats) w.stats[0] += 1;
+                }
+                __syncwarp();
+                group_min(x >> 5);
+                __syncwarp();
+            }
+            c3 += clock64() - tb;  // rescan B2 + post
+            ++tries;
+            continue;
+        }
+        // ================= all warps: Lance-Williams sweep (clustering.cpp:361-404) =================
+        const int y = rec.y, nx = rec.nx, ny = rec.ny;
+        const double dist = rec.dist;
+        const double* rowx = w.D + (size_t)x * w.ld;
+        double* rowy = w.D + (size_t)y * w.ld;
+        double ymv = INFINITY;  // y's new nearest neighbour among z > y
+        int ymi = -1;
+        double fx = 0.0, fy = 0.0, fs = 1.0, t3 = 0.0, rs = 1.0;
+        bool have_terms = false;
+        for (int g0 = warp; g0 < NG; g0 += NW * PF) {
+            double dx[PF], dy[PF];
+            bool live[PF];
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int z = (g0 + u * NW) * 32 + lane;
+                live[u] = z < n && z != x && z != y && size[z] != 0;
+                dx[u] = live[u] ? rowx[z] : 0.0;
+                dy[u] = live[u] ? rowy[z] : 0.0;
+            }
+            if (!have_terms) {
+                // centroid update, clustering.cpp:250-256: the third term and the divisor do not depend on z;
+                // computed here, under the shadow of the loads just issued
+                fx = (double)nx;
+                fy = (double)ny;
+                fs = (double)(nx + ny);
+                t3 = __ddiv_rn(__dmul_rn(__dmul_rn((double)(nx * ny), dist), dist), fs);
+                rs = __drcp_rn(fs);
+                have_terms = true;
+            }
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int g = g0 + u * NW;
+                if (g >= NG) break;
+                const int z = g * 32 + lane;
+                double lbz = INFINITY;
+                if (live[u]) {
+                    const double t1 = __dmul_rn(__dmul_rn(fx, dx[u]), dx[u]);
+                    const double t2 = __dmul_rn(__dmul_rn(fy, dy[u]), dy[u]);
+                    const double nd = __dsqrt_rn(div_by(__dsub_rn(__dadd_rn(t1, t2), t3), fs, rs));
+                    rowy[z] = nd;
+                    w.D[(size_t)z * w.ld + y] = nd;
+                    if (z < y) {
+                        int nb = nbr[z];
+                        lbz = lb[z];
+                        if (z < x && nb == x) nb = y;  // clustering.cpp:374-378
+                        if (nd < lbz) {                // clustering.cpp:381-392
+                            nb = y;
+                            lbz = nd;
+                            lb[z] = nd;
+                        }
+                        if (nb == y) cur[z] = nd;  // cur[z] mirrors D[z][nbr[z]]
+                        nbr[z] = nb;
+                    } else {
+                        if (nd < ymv) {  // groups ascend within a warp: first strict minimum
+                            ymv = nd;
+                            ymi = z;
+                        }
+                        if (z < n - 1) lbz = lb[z];
+                    }
+                }
+                if (g < HG) {
+                    const bool in = live[u] && z < n - 1;
+                    store_group(g, warp_top(in ? lbz : INFINITY, z, in ? 1 : 0));
+                }
+            }
+        }
+        {
+            const Top t = warp_top(ymi >= 0 ? ymv : INFINITY, ymi, ymi >= 0 ? 1 : 0);
+            if (lane == 0) {
+                part_v[warp] = t.v;
+                part_i[warp] = t.i;
+            }
+        }
+        tb = clock64();
+        c4 += tb - ta;  // sweep work
+        __syncthreads();  // B2: sweep results are visible
+        if (warp == 0 && y < n - 1) {
+            const bool has = lane < NW && part_i[lane] >= 0;
+            const Top t = warp_top(has ? part_v[lane] : INFINITY, has ? part_i[lane] : -1, has ? 1 : 0);
+            if (lane == 0 && t.i != -1) {  // clustering.cpp:395-404
+                nbr[y] = t.i;
+                lb[y] = t.v;
+                cur[y] = t.v;
+            }
+            __syncwarp();
+            group_min(y >> 5);  // the sweep left y out of its group
+            __syncwarp();
+        }
+        c5 += clock64() - tb;  // sweep B2 + post
+        ++k;
+        tries = 0;
     }
 }
 
@@ -447,12 +981,14 @@ __global__ void __launch_bounds__(LK_THREADS) linkage_kernel(const LinkWork* __r
 // fcluster (criterion "distance")
 // ------------------------------------------------------------------------------------------------
 
-// Single thread: both passes are O(n) chains of dependent steps.  T[n] receives labels 1..K in the
-// reference's depth-first numbering; *num_out = K.
-__global__ void fcluster_kernel(const double* __restrict__ Z, int n, double cutoff, double* __restrict__ MD,
-                                int* __restrict__ stack, unsigned char* __restrict__ stage, int* __restrict__ T,
-                                int* __restrict__ num_out) {
+// Sequential form (single thread), kept as the exact fallback for dendrograms that contain NaN merge distances
+// (the reference's max-propagation ignores NaN children, which the scan formulation below does not model).
+// T[n] receives labels 1..K in the reference's depth-first numbering; *num_out = K.
+__global__ void fcluster_seq_kernel(const double* __restrict__ Z, int n, double cutoff, double* __restrict__ MD,
+                                    int* __restrict__ stack, unsigned char* __restrict__ stage, int* __restrict__ T,
+                                    int* __restrict__ num_out, const int* __restrict__ run_flag) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (run_flag && !*run_flag) return;
     if (n < 2) {
         if (n == 1) T[0] = 1;
         *num_out = n;
@@ -511,6 +1047,193 @@ __global__ void fcluster_kernel(const double* __restrict__ Z, int n, double cuto
     *num_out = ncl;
 }
 
+// in-place inclusive scan of a[0..m) by one CTA (a in shared or global memory)
+__device__ void block_inclusive_scan(int* a, int m, int* warp_tot) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const int per = (m + nt - 1) / nt;
+    const int lo = tid * per, hi = min(lo + per, m);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += a[i];
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int v = lane < nw ? warp_tot[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        warp_tot[lane] = v;  // inclusive totals of warps
+    }
+    __syncthreads();
+    int run = inc - sum + (warp > 0 ? warp_tot[warp - 1] : 0);
+    for (int i = lo; i < hi; ++i) {
+        run += a[i];
+        a[i] = run;
+    }
+    __syncthreads();
+}
+
+// Parallel fcluster (criterion "distance"), one CTA.
+//
+// The reference assigns leaf labels in a fixed depth-first order (clustering.cpp:174-232): at a node, first
+// the leaves of an internal left child, then those of an internal right child, then a leaf left child, then a
+// leaf right child.  In that order every subtree occupies one contiguous interval of leaf positions whose
+// length is the cluster size stored in Z, so
+//   start[node] = sum of per-edge offsets on the path to the root          (pointer jumping, log depth rounds)
+//   every internal node owns exactly one gap between two consecutive positions (where its two blocks meet)
+//   MD[node] <= cutoff  <=>  no gap inside its interval belongs to a merge with distance > cutoff (prefix sums)
+//   two consecutive leaves share a flat cluster  <=>  the owner of the gap between them satisfies that
+// and the flat-cluster number of a leaf is the number of cluster starts at or before its position, which is the
+// order in which the reference's traversal discovers clusters.  NaN distances set *nan_flag and the caller
+// runs the sequential kernel instead.
+struct FcWork {
+    int* up;     // [2n] pointer-jumping parent
+    int* acc;    // [2n] accumulated offset
+    int* up2;    // [2n] second buffer
+    int* acc2;   // [2n]
+    int* gapbad; // [n]  1 when the merge owning gap g has distance > cutoff; then inclusive prefix sums
+    int* owner;  // [n]  internal node owning gap g
+    int* newc;   // [n]  cluster starts, then inclusive prefix sums = labels by position
+};
+
+__global__ void __launch_bounds__(1024)
+    fcluster_par_kernel(const double* __restrict__ Z, int n, double cutoff, FcWork w, int use_smem,
+                        int* __restrict__ T, int* __restrict__ num_out, int* __restrict__ nan_flag) {
+    extern __shared__ __align__(16) unsigned char fc_smem[];
+    __shared__ int warp_tot[32];
+    __shared__ int s_nan, s_live;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if (n < 2) {
+        if (tid == 0) {
+            if (n == 1) T[0] = 1;
+            *num_out = n;
+            *nan_flag = 0;
+        }
+        return;
+    }
+    const int nodes = 2 * n - 1;
+    if (use_smem) {
+        int* p = reinterpret_cast<int*>(fc_smem);
+        w.up = p;
+        p += 2 * n;
+        w.acc = p;
+        p += 2 * n;
+        w.up2 = p;
+        p += 2 * n;
+        w.acc2 = p;
+        p += 2 * n;
+        w.gapbad = p;
+        p += n;
+        w.owner = p;
+        p += n;
+        w.newc = p;
+    }
+    if (tid == 0) s_nan = 0;
+    for (int g = tid; g < n; g += nt) {
+        w.gapbad[g] = 0;
+        w.owner[g] = -1;
+    }
+    if (tid == 0) {
+        w.up[nodes - 1] = -1;  // root
+        w.acc[nodes - 1] = 0;
+    }
+    __syncthreads();
+    // per-edge offsets inside the parent's block
+    for (int k = tid; k < n - 1; k += nt) {
+        const int lc = (int)Z[4 * (size_t)k], rc = (int)Z[4 * (size_t)k + 1];
+        const double d = Z[4 * (size_t)k + 2];
+        if (isnan(d)) s_nan = 1;
+        const int szl = lc >= n ? (int)Z[4 * (size_t)(lc - n) + 3] : 1;
+        const int szr = rc >= n ? (int)Z[4 * (size_t)(rc - n) + 3] : 1;
+        int offl, offr;
+        if (lc >= n) {  // internal left child goes first
+            offl = 0;
+            offr = szl;
+        } else if (rc >= n) {  // leaf left child follows the internal right subtree
+            offr = 0;
+            offl = szr;
+        } else {
+            offl = 0;
+            offr = 1;
+        }
+        w.up[lc] = n + k;
+        w.acc[lc] = offl;
+        w.up[rc] = n + k;
+        w.acc[rc] = offr;
+    }
+    __syncthreads();
+    if (s_nan) {
+        if (tid == 0) *nan_flag = 1;
+        return;
+    }
+    // start[node] = sum of offsets up to the root: pointer jumping between two buffers
+    int *upA = w.up, *accA = w.acc, *upB = w.up2, *accB = w.acc2;
+    for (;;) {
+        if (tid == 0) s_live = 0;
+        __syncthreads();
+        int live = 0;
+        for (int v = tid; v < nodes; v += nt) {
+            const int u = upA[v];
+            int nu = -1, na = accA[v];
+            if (u >= 0) {
+                nu = upA[u];
+                na += accA[u];
+            }
+            upB[v] = nu;
+            accB[v] = na;
+            live |= nu >= 0;
+        }
+        if (live) s_live = 1;
+        __syncthreads();
+        int* t = upA;
+        upA = upB;
+        upB = t;
+        t = accA;
+        accA = accB;
+        accB = t;
+        if (!s_live) break;
+    }
+    w.acc = accA;  // start[] of every node
+    // gaps: node k splits [start, start + size) at start + size(first block)
+    for (int k = tid; k < n - 1; k += nt) {
+        const int lc = (int)Z[4 * (size_t)k], rc = (int)Z[4 * (size_t)k + 1];
+        const double d = Z[4 * (size_t)k + 2];
+        const int szl = lc >= n ? (int)Z[4 * (size_t)(lc - n) + 3] : 1;
+        const int szr = rc >= n ? (int)Z[4 * (size_t)(rc - n) + 3] : 1;
+        const int first = (lc >= n) ? szl : ((rc >= n) ? szr : 1);
+        const int g = w.acc[n + k] + first;
+        w.owner[g] = k;
+        w.gapbad[g] = !(d <= cutoff);
+    }
+    __syncthreads();
+    block_inclusive_scan(w.gapbad, n, warp_tot);
+    // cluster starts by position
+    for (int p = tid; p < n; p += nt) {
+        int nc = 1;
+        if (p > 0) {
+            const int k = w.owner[p];
+            const int st = w.acc[n + k];
+            const int sz = (int)Z[4 * (size_t)k + 3];
+            nc = (w.gapbad[st + sz - 1] - w.gapbad[st]) > 0;  // bad gaps strictly inside the interval
+        }
+        w.newc[p] = nc;
+    }
+    __syncthreads();
+    block_inclusive_scan(w.newc, n, warp_tot);
+    for (int leaf = tid; leaf < n; leaf += nt) T[leaf] = w.newc[w.acc[leaf]];
+    if (tid == 0) {
+        *num_out = w.newc[n - 1];
+        *nan_flag = 0;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Cluster::cluster post-processing and Cluster::assign_embeddings
 // ------------------------------------------------------------------------------------------------
@@ -550,32 +1273,75 @@ struct PostWork {
     int* rank;         // [K+1]
     double* sums;      // [K][D]
     int* num_clusters; // out: max label + 1
+    int* need_means;   // out of phase 1: 1 when small clusters must be re-assigned
     int* status;
 };
 
-// Per-cluster sums in index order (calculateClusterMeans, speakerDiarizer.cpp:443-473; assign_embeddings
-// 2147-2167): thread j owns dimension j and walks the rows once, so each cluster's sum is formed in
-// increasing row order exactly like the reference, then divided by the count.
-__device__ void cluster_means(const double* x, const int* labels, int N, int D, int K, const int* count,
-                              double* sums) {
-    for (long e = threadIdx.x; e < (long)K * D; e += blockDim.x) sums[e] = 0.0;
-    __syncthreads();
-    for (int j = threadIdx.x; j < D; j += blockDim.x) {
-        for (int i = 0; i < N; ++i) {
-            const int l = labels[i];
-            double* s = sums + (size_t)l * D + j;
-            *s = __dadd_rn(*s, x[(size_t)i * D + j]);
+// Cluster means in index order (calculateClusterMeans, speakerDiarizer.cpp:443-473; assign_embeddings
+// 2147-2167).  One CTA per cluster, one thread per dimension: the member rows of the cluster are compacted
+// in increasing row order, then added one by one into a register -- the same sequence of fp64 additions as the
+// reference -- with the loads issued eight at a time so their latency is off the dependent add chain.
+constexpr int CM_TILE = 1024;
+__global__ void __launch_bounds__(512)
+    cluster_means_kernel(const double* __restrict__ x, const int* __restrict__ labels, int N, int D, int K,
+                         const int* __restrict__ enable, double* __restrict__ means) {
+    __shared__ int list[CM_TILE];
+    __shared__ int wcount[16];
+    __shared__ int s_total;
+    if (enable && !*enable) return;
+    const int k = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    double acc[2] = {0.0, 0.0};  // dimensions tid and tid + blockDim.x (D <= 1024)
+    long members = 0;
+    for (int i0 = 0; i0 < N; i0 += CM_TILE) {
+        // ordered compaction of the rows of this tile that belong to cluster k
+        int base = 0;
+        for (int r0 = 0; r0 < CM_TILE; r0 += blockDim.x) {
+            const int i = i0 + r0 + tid;
+            const bool mine = (r0 + tid < CM_TILE) && i < N && labels[i] == k;
+            const unsigned bal = __ballot_sync(0xffffffffu, mine);
+            if (lane == 0) wcount[warp] = __popc(bal);
+            __syncthreads();
+            int off = base;
+            for (int w2 = 0; w2 < warp; ++w2) off += wcount[w2];
+            if (mine) list[off + __popc(bal & ((1u << lane) - 1u))] = i;
+            int tot = 0;
+            for (int w2 = 0; w2 < nwarp; ++w2) tot += wcount[w2];
+            base += tot;
+            __syncthreads();
         }
+        const int cnt = base;
+        members += cnt;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = tid + h * blockDim.x;
+            if (j < D) {
+                int m = 0;
+                for (; m + 8 <= cnt; m += 8) {
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = x[(size_t)list[m + u] * D + j];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc[h] = __dadd_rn(acc[h], v[u]);
+                }
+                for (; m < cnt; ++m) acc[h] = __dadd_rn(acc[h], x[(size_t)list[m] * D + j]);
+            }
+        }
+        __syncthreads();
     }
+    if (tid == 0) s_total = (int)members;
     __syncthreads();
-    for (long e = threadIdx.x; e < (long)K * D; e += blockDim.x) sums[e] = __ddiv_rn(sums[e], (double)count[e / D]);
-    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int j = tid + h * blockDim.x;
+        if (j < D) means[(size_t)k * D + j] = __ddiv_rn(acc[h], (double)s_total);  // 0/0 -> NaN like the reference
+    }
 }
 
-__global__ void __launch_bounds__(1024) cluster_post_kernel(PostWork w, int N, int D, int K, int min_cluster_size) {
-    __shared__ int s_nl, s_ns, s_next;
+// phase 1 of Cluster::cluster's post-processing: labels - 1, counts, large/small split
+__global__ void __launch_bounds__(1024) cluster_post1_kernel(PostWork w, int N, int K, int min_cluster_size) {
+    __shared__ int s_nl, s_ns;
     const int tid = threadIdx.x;
-    // labels - 1, counts (speakerDiarizer.cpp:2324-2341)
     for (int l = tid; l <= K; l += blockDim.x) {
         w.count[l] = 0;
         w.map[l] = l;
@@ -585,14 +1351,13 @@ __global__ void __launch_bounds__(1024) cluster_post_kernel(PostWork w, int N, i
         s_ns = 0;
     }
     __syncthreads();
-    for (int i = tid; i < N; i += blockDim.x) {
+    for (int i = tid; i < N; i += blockDim.x) {  // speakerDiarizer.cpp:2324-2341
         const int l = w.labels[i] - 1;
         w.labels[i] = l;
         atomicAdd(&w.count[l], 1);
     }
     __syncthreads();
-    // min_cluster_size heuristic (speakerDiarizer.cpp:2308-2309)
-    long mcs = (long)round(0.1 * (double)N);
+    long mcs = (long)round(0.1 * (double)N);  // speakerDiarizer.cpp:2308-2309
     if (mcs < 1) mcs = 1;
     if (mcs > min_cluster_size) mcs = min_cluster_size;
     for (int l = tid; l < K; l += blockDim.x) {
@@ -605,16 +1370,28 @@ __global__ void __launch_bounds__(1024) cluster_post_kernel(PostWork w, int N, i
     const int nl = s_nl, ns = s_ns;
     if (nl == 0) {  // speakerDiarizer.cpp:2371-2375
         for (int i = tid; i < N; i += blockDim.x) w.labels[i] = 0;
-        if (tid == 0) *w.num_clusters = 1;
+        if (tid == 0) {
+            *w.num_clusters = 1;
+            *w.need_means = 0;
+        }
         return;
     }
-    if (ns == 0) {  // speakerDiarizer.cpp:2377-2380: labels as they are (all K clusters are large and present)
-        if (tid == 0) *w.num_clusters = K;
-        return;
+    if (tid == 0) {
+        *w.num_clusters = K;  // speakerDiarizer.cpp:2377-2380 when there is no small cluster
+        *w.need_means = ns > 0;
     }
-    cluster_means(w.x, w.labels, N, D, K, w.count, w.sums);
-    // each small cluster -> nearest large cluster by centroid cosine distance, float running minimum
-    // (speakerDiarizer.cpp:2390-2415); large clusters are visited in ascending label order
+}
+
+// phase 2: each small cluster -> nearest large cluster by centroid cosine distance with a float running
+// minimum (speakerDiarizer.cpp:2390-2415; large clusters visited in ascending label order), then the rank of
+// each surviving label among the sorted unique labels (speakerDiarizer.cpp:519-548)
+__global__ void __launch_bounds__(1024) cluster_post2_kernel(PostWork w, int N, int D, int K, int min_cluster_size) {
+    __shared__ int s_next;
+    if (!*w.need_means) return;
+    const int tid = threadIdx.x;
+    long mcs = (long)round(0.1 * (double)N);
+    if (mcs < 1) mcs = 1;
+    if (mcs > min_cluster_size) mcs = min_cluster_size;
     for (int b = tid; b < K; b += blockDim.x) {
         if (w.count[b] == 0 || w.count[b] >= mcs) continue;
         float best = FLT_MAX;
@@ -634,7 +1411,6 @@ __global__ void __launch_bounds__(1024) cluster_post_kernel(PostWork w, int N, i
         if (arg >= 0) w.map[b] = arg;
     }
     __syncthreads();
-    // rank of each surviving label among the sorted unique labels (speakerDiarizer.cpp:519-548)
     if (tid == 0) {
         int next = 0;
         for (int l = 0; l < K; ++l) w.rank[l] = (w.count[l] >= mcs) ? next++ : -1;
@@ -649,7 +1425,6 @@ struct AssignWork {
     const double* emb;   // [R][D] all embeddings (NaN rows included)
     const double* x;     // [N][D] filtered, un-normalised
     const int* labels;   // [N]
-    int* count;          // [K]
     double* cent;        // [K][D]
     double* soft;        // optional [R][soft_k_cap]
     int* hard;           // [R]
@@ -657,44 +1432,51 @@ struct AssignWork {
     int* status;
 };
 
-// centroids (one CTA; see cluster_means)
-__global__ void __launch_bounds__(1024) centroid_kernel(AssignWork w, int N, int D, int K) {
-    for (int l = threadIdx.x; l < K; l += blockDim.x) w.count[l] = 0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < N; i += blockDim.x) atomicAdd(&w.count[w.labels[i]], 1);
-    __syncthreads();
-    cluster_means(w.x, w.labels, N, D, K, w.count, w.cent);
+// one thread per (embedding row, centroid): cosine distance in the reference's sequential order
+// (speakerDiarizer.cpp:2180-2203); soft = 2 - d
+__global__ void __launch_bounds__(256) assign_dist_kernel(AssignWork w, int R, int D, int K, double* __restrict__ soft,
+                                                         int ld_soft) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)R * K) return;
+    const int r = (int)(idx / K), k = (int)(idx - (long)r * K);
+    double d;
+    if (!cosine_distance(w.emb + (size_t)r * D, w.cent + (size_t)k * D, D, &d)) {
+        atomicExch(w.status, SD_ERR_ZERO_MAGNITUDE);
+        d = NAN;
+    }
+    soft[(size_t)r * ld_soft + k] = __dsub_rn(2.0, d);
 }
 
-// one thread per embedding row: distances to every centroid in order, soft = 2 - d, first strict maximum
-// (speakerDiarizer.cpp:2180-2211), then the inactive-speaker mask (3166-3191)
-__global__ void __launch_bounds__(128)
-    assign_kernel(AssignWork w, int R, int S, int D, int K, int F, int soft_k_cap) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per embedding row: first strict maximum over the centroids (Helper::argmax, speakerDiarizer.cpp:
+// 293-316; an all-NaN row gives 0), then the inactive-speaker mask (3166-3191): the reference sums the 0/1
+// activity of the speaker over the chunk's frames in float, which is exact in any order
+__global__ void __launch_bounds__(256) assign_argmax_kernel(AssignWork w, int R, int S, int K, int F,
+                                                           const double* __restrict__ soft, int ld_soft,
+                                                           int user_cap) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (r >= R) return;
-    const double* e = w.emb + (size_t)r * D;
     int arg = 0;
-    double best = -DBL_MAX;
-    for (int k = 0; k < K; ++k) {
-        double d;
-        if (!cosine_distance(e, w.cent + (size_t)k * D, D, &d)) {
-            atomicExch(w.status, SD_ERR_ZERO_MAGNITUDE);
-            d = NAN;
-        }
-        const double soft = __dsub_rn(2.0, d);
-        if (w.soft && k < soft_k_cap) w.soft[(size_t)r * soft_k_cap + k] = soft;
-        if (soft > best) {
-            best = soft;
-            arg = k;
+    if (lane == 0) {
+        double best = -DBL_MAX;
+        for (int k = 0; k < K; ++k) {
+            const double v = soft[(size_t)r * ld_soft + k];
+            if (w.soft && k < user_cap) w.soft[(size_t)r * user_cap + k] = v;
+            if (v > best) {
+                best = v;
+                arg = k;
+            }
         }
     }
     if (w.binarized) {
         const int c = r / S, s = r - c * S;
-        float acc = 0.0f;  // the reference accumulates 0/1 values in float (exact)
-        for (int f = 0; f < F; ++f) acc += (float)w.binarized[((size_t)c * F + f) * S + s];
+        float acc = 0.0f;
+        for (int f = lane; f < F; f += 32) acc += (float)w.binarized[((size_t)c * F + f) * S + s];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (fabsf(acc) < DBL_EPSILON) arg = -2;
     }
-    w.hard[r] = arg;
+    if (lane == 0) w.hard[r] = arg;
 }
 
 __global__ void fill_int_kernel(int* p, long n, int v) {
@@ -719,10 +1501,17 @@ __global__ void inactive_mask_kernel(const double* __restrict__ binarized, int C
 int upload_small(sd_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int means_threads(int D) {
+    int t = (D + 31) / 32 * 32;
+    if (t > 512) t = 512;
+    if (t < 64) t = 64;
+    return t;
+}
 
 struct LinkLayout {
     long ld;
-    size_t off_D, off_size, off_cid, off_nbr, off_lb, off_pos, off_key, off_hval, off_bitmap, off_work, off_n, total;
+    size_t off_D, off_size, off_cid, off_nbr, off_lb, off_cur, off_pos, off_key, off_hval, off_bitmap, off_work, off_n,
+        off_fast, total;
 };
 
 static LinkLayout link_layout(int N) {
@@ -739,6 +1528,8 @@ static LinkLayout link_layout(int N) {
     o += align_up((size_t)N * sizeof(int), 256);
     L.off_lb = o;
     o += align_up((size_t)N * sizeof(double), 256);
+    L.off_cur = o;
+    o += align_up((size_t)N * sizeof(double), 256);
     L.off_pos = o;
     o += align_up((size_t)N * sizeof(int), 256);
     L.off_key = o;
@@ -751,6 +1542,8 @@ static LinkLayout link_layout(int N) {
     o += align_up(sizeof(LinkWork), 256);
     L.off_n = o;
     o += 256;
+    L.off_fast = o;
+    o += align_up(linkfast_smem_bytes(N), 256);
     L.total = o;
     return L;
 }
@@ -761,14 +1554,66 @@ static int pdist_square(sd_ctx* ctx, const double* d_xn, int N, int D, char** ba
     char* base = (char*)ctx->scratch(BUF_CL_DIST, L.total);
     if (!base) return SD_ERR_NOMEM;
     dim3 grid((N + PD_TILE - 1) / PD_TILE, (N + PD_TILE - 1) / PD_TILE);
-    pdist_f64_kernel<<<grid, 256, 0, ctx->stream>>>(d_xn, N, D, reinterpret_cast<double*>(base + L.off_D), L.ld);
+    pdist_f64_kernel<<<grid, 256, 0, ctx->stream>>>(d_xn, N, D, reinterpret_cast<double*>(base + L.off_D), L.ld, nullptr);
     SD_LAUNCH_CHECK(ctx);
     *base_out = base;
     *L_out = L;
     return SD_OK;
 }
 
-static int linkage_on_square(sd_ctx* ctx, char* base, const LinkLayout& L, int N, double* d_Z) {
+template <int MODE>
+static int linkage_launch_mode(sd_ctx* ctx, const LinkWork* d_works, const int* d_ns, int problems, int max_n,
+                               const int* d_run_flags) {
+    const size_t smem = link_smem_bytes(MODE, max_n);
+    static size_t configured = 0;
+    if (smem > configured) {
+        SD_CUDA(ctx, cudaFuncSetAttribute(linkage_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)(MODE == LK_GLOBAL ? smem : (size_t)227 * 1024 - 1024)));
+        configured = (size_t)227 * 1024;
+    }
+    linkage_kernel<MODE><<<problems, LK_THREADS, smem, ctx->stream>>>(d_works, d_ns, d_run_flags);
+    SD_LAUNCH_CHECK(ctx);
+    return SD_OK;
+}
+
+// picks where the merge state lives from the largest problem in the launch
+static int linkage_dispatch(sd_ctx* ctx, const LinkWork* d_works, const int* d_ns, int problems, int max_n,
+                            const int* d_run_flags) {
+    const size_t budget = (size_t)227 * 1024 - 2048;  // static shared memory of the kernel comes on top
+    if (link_smem_bytes(LK_SMEM_ALL, max_n) <= budget)
+        return linkage_launch_mode<LK_SMEM_ALL>(ctx, d_works, d_ns, problems, max_n, d_run_flags);
+    if (link_smem_bytes(LK_SMEM_HEAP, max_n) <= budget)
+        return linkage_launch_mode<LK_SMEM_HEAP>(ctx, d_works, d_ns, problems, max_n, d_run_flags);
+    return linkage_launch_mode<LK_GLOBAL>(ctx, d_works, d_ns, problems, max_n, d_run_flags);
+}
+
+template <int MODE, int T>
+static int linkage_fast_launch_mode(sd_ctx* ctx, const LinkWork* d_works, const int* d_ns, int problems, int max_n,
+                                    int* d_need_exact) {
+    const size_t smem = MODE == LF_SMEM ? linkfast_smem_bytes(max_n) : 64;
+    static bool configured = false;
+    if (!configured) {
+        SD_CUDA(ctx, cudaFuncSetAttribute(linkage_fast_kernel<MODE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          220 * 1024));
+        configured = true;
+    }
+    linkage_fast_kernel<MODE, T><<<problems, T, smem, ctx->stream>>>(d_works, d_ns, d_need_exact);
+    SD_LAUNCH_CHECK(ctx);
+    return SD_OK;
+}
+
+static int linkage_fast_dispatch(sd_ctx* ctx, const LinkWork* d_works, const int* d_ns, int problems, int max_n,
+                                 int* d_need_exact) {
+    const bool fits = linkfast_smem_bytes(max_n) <= (size_t)220 * 1024;
+    const int threads = ctx->linkage_threads ? ctx->linkage_threads : (max_n <= 4096 ? 512 : 1024);
+    if (fits && threads == 512) return linkage_fast_launch_mode<LF_SMEM, 512>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
+    if (fits) return linkage_fast_launch_mode<LF_SMEM, 1024>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
+    return linkage_fast_launch_mode<LF_GLOBAL, 1024>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
+}
+
+// d_x: the rows the distance matrix was built from (needed to rebuild it if the exact kernel must run)
+static int linkage_on_square(sd_ctx* ctx, char* base, const LinkLayout& L, const double* d_x, int N, int D,
+                             double* d_Z) {
     LinkWork w;
     w.D = reinterpret_cast<double*>(base + L.off_D);
     w.ld = L.ld;
@@ -776,26 +1621,41 @@ static int linkage_on_square(sd_ctx* ctx, char* base, const LinkLayout& L, int N
     w.cid = reinterpret_cast<int*>(base + L.off_cid);
     w.nbr = reinterpret_cast<int*>(base + L.off_nbr);
     w.lb = reinterpret_cast<double*>(base + L.off_lb);
+    w.cur = reinterpret_cast<double*>(base + L.off_cur);
     w.pos_of = reinterpret_cast<int*>(base + L.off_pos);
     w.key_at = reinterpret_cast<int*>(base + L.off_key);
     w.hval = reinterpret_cast<double*>(base + L.off_hval);
     w.bitmap = reinterpret_cast<unsigned*>(base + L.off_bitmap);
     w.Z = d_Z;
     w.status = ctx->d_status;
+    w.stats = ctx->d_stats;
+    w.fast_scratch = base + L.off_fast;
     int rc = upload_small(ctx, base + L.off_work, &w, sizeof(w));
     if (rc) return rc;
     rc = upload_small(ctx, base + L.off_n, &N, sizeof(int));
     if (rc) return rc;
-    rowmin_init_kernel<<<(unsigned)(((long)N * 32 + 255) / 256), 256, 0, ctx->stream>>>(w, N);
+    const LinkWork* d_work = reinterpret_cast<const LinkWork*>(base + L.off_work);
+    const int* d_n = reinterpret_cast<const int*>(base + L.off_n);
+    int* d_need_exact = reinterpret_cast<int*>(base + L.off_n) + 8;
+    const unsigned rm_grid = (unsigned)(((long)N * 32 + 255) / 256);
+    rowmin_init_kernel<<<rm_grid, 256, 0, ctx->stream>>>(w, N, nullptr);
     SD_LAUNCH_CHECK(ctx);
-    linkage_kernel<<<1, LK_THREADS, 0, ctx->stream>>>(reinterpret_cast<const LinkWork*>(base + L.off_work),
-                                                      reinterpret_cast<const int*>(base + L.off_n));
-    SD_LAUNCH_CHECK(ctx);
-    return SD_OK;
+    if (!ctx->force_exact_linkage) {
+        rc = linkage_fast_dispatch(ctx, d_work, d_n, 1, N, d_need_exact);
+        if (rc) return rc;
+        // exact chain, skipped on the device unless the fast kernel met a tied minimum
+        dim3 grid((N + PD_TILE - 1) / PD_TILE, (N + PD_TILE - 1) / PD_TILE);
+        pdist_f64_kernel<<<grid, 256, 0, ctx->stream>>>(d_x, N, D, w.D, L.ld, d_need_exact);
+        SD_LAUNCH_CHECK(ctx);
+        rowmin_init_kernel<<<rm_grid, 256, 0, ctx->stream>>>(w, N, d_need_exact);
+        SD_LAUNCH_CHECK(ctx);
+        return linkage_dispatch(ctx, d_work, d_n, 1, N, d_need_exact);
+    }
+    return linkage_dispatch(ctx, d_work, d_n, 1, N, nullptr);
 }
 
 int normalize_launch(sd_ctx* ctx, const double* d_x, int N, int D, double* d_xn) {
-    gather_normalize_kernel<<<(N + 127) / 128, 128, 0, ctx->stream>>>(d_x, nullptr, N, D, nullptr, d_xn);
+    gather_normalize_kernel<<<(unsigned)(((long)N * 32 + 255) / 256), 256, 0, ctx->stream>>>(d_x, nullptr, N, D, nullptr, d_xn);
     SD_LAUNCH_CHECK(ctx);
     return SD_OK;
 }
@@ -818,20 +1678,42 @@ int linkage_launch(sd_ctx* ctx, const double* d_x, int N, int D, double* d_Z) {
     LinkLayout L;
     int rc = pdist_square(ctx, d_x, N, D, &base, &L);
     if (rc) return rc;
-    return linkage_on_square(ctx, base, L, N, d_Z);
+    return linkage_on_square(ctx, base, L, d_x, N, D, d_Z);
 }
 
 // Clustering::fcluster; d_T[N] labels 1..K, d_num receives K
 int fcluster_launch(sd_ctx* ctx, const double* d_Z, int N, double cutoff, int* d_T, int* d_num) {
-    size_t bytes = align_up((size_t)N * sizeof(double), 256) + align_up((size_t)N * sizeof(int), 256) +
-                   align_up((size_t)N, 256);
+    // workspace: [flag | par: up, acc (2N each), gapbad, owner, newc (N each) | seq: MD, stack, stage]
+    const size_t o_par = 256;
+    const size_t par_bytes = align_up(sizeof(int) * (size_t)(11 * (size_t)N + 8), 256);
+    const size_t o_md = o_par + par_bytes;
+    const size_t o_stack = o_md + align_up((size_t)N * sizeof(double), 256);
+    const size_t o_stage = o_stack + align_up((size_t)N * sizeof(int), 256);
+    const size_t bytes = o_stage + align_up((size_t)N, 256);
     char* base = (char*)ctx->scratch(BUF_CL_WORK, bytes);
     if (!base) return SD_ERR_NOMEM;
-    double* MD = reinterpret_cast<double*>(base);
-    int* stack = reinterpret_cast<int*>(base + align_up((size_t)N * sizeof(double), 256));
-    unsigned char* stage = reinterpret_cast<unsigned char*>(base + align_up((size_t)N * sizeof(double), 256) +
-                                                            align_up((size_t)N * sizeof(int), 256));
-    fcluster_kernel<<<1, 32, 0, ctx->stream>>>(d_Z, N, cutoff, MD, stack, stage, d_T, d_num);
+    int* d_flag = reinterpret_cast<int*>(base);
+    int* ip = reinterpret_cast<int*>(base + o_par);
+    FcWork w;
+    w.up = ip;
+    w.acc = ip + 2 * (size_t)N;
+    w.up2 = ip + 4 * (size_t)N;
+    w.acc2 = ip + 6 * (size_t)N;
+    w.gapbad = ip + 8 * (size_t)N;
+    w.owner = ip + 9 * (size_t)N;
+    w.newc = ip + 10 * (size_t)N;
+    const size_t smem = sizeof(int) * (11 * (size_t)N + 8);
+    const int use_smem = smem <= (size_t)200 * 1024;
+    static bool configured = false;
+    if (!configured) {
+        SD_CUDA(ctx, cudaFuncSetAttribute(fcluster_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    fcluster_par_kernel<<<1, 1024, use_smem ? smem : 0, ctx->stream>>>(d_Z, N, cutoff, w, use_smem, d_T, d_num, d_flag);
+    SD_LAUNCH_CHECK(ctx);
+    fcluster_seq_kernel<<<1, 32, 0, ctx->stream>>>(d_Z, N, cutoff, reinterpret_cast<double*>(base + o_md),
+                                                   reinterpret_cast<int*>(base + o_stack),
+                                                   reinterpret_cast<unsigned char*>(base + o_stage), d_T, d_num, d_flag);
     SD_LAUNCH_CHECK(ctx);
     return SD_OK;
 }
@@ -868,7 +1750,7 @@ int cluster_labels_launch(sd_ctx* ctx, const double* d_x, int N, int D, const sd
     if (K < 1 || K > N) return ctx->fail(SD_ERR_CUDA, "fcluster produced %d clusters for %d points", K, N);
     const size_t o_count = 0, o_map = align_up(sizeof(int) * (size_t)(K + 1), 256),
                  o_rank = o_map + align_up(sizeof(int) * (size_t)(K + 1), 256),
-                 o_sums = o_rank + align_up(sizeof(int) * (size_t)(K + 1), 256),
+                 o_flag = o_rank + align_up(sizeof(int) * (size_t)(K + 1), 256), o_sums = o_flag + 256,
                  total = o_sums + sizeof(double) * (size_t)K * D;
     char* base = (char*)ctx->scratch(BUF_CL_CENT, total);
     if (!base) return SD_ERR_NOMEM;
@@ -881,7 +1763,13 @@ int cluster_labels_launch(sd_ctx* ctx, const double* d_x, int N, int D, const sd
     w.sums = reinterpret_cast<double*>(base + o_sums);
     w.num_clusters = d_num;
     w.status = ctx->d_status;
-    cluster_post_kernel<<<1, 1024, 0, ctx->stream>>>(w, N, D, K, p->min_cluster_size);
+    w.need_means = reinterpret_cast<int*>(base + o_flag);
+    cluster_post1_kernel<<<1, 1024, 0, ctx->stream>>>(w, N, K, p->min_cluster_size);
+    SD_LAUNCH_CHECK(ctx);
+    if (D > 1024) return ctx->fail(SD_ERR_UNSUPPORTED, "embedding dimension %d > 1024", D);
+    cluster_means_kernel<<<K, means_threads(D), 0, ctx->stream>>>(d_x, d_labels, N, D, K, w.need_means, w.sums);
+    SD_LAUNCH_CHECK(ctx);
+    cluster_post2_kernel<<<1, 1024, 0, ctx->stream>>>(w, N, D, K, p->min_cluster_size);
     SD_LAUNCH_CHECK(ctx);
     return SD_OK;
 }
@@ -916,7 +1804,7 @@ int clustering_launch(sd_ctx* ctx, const double* d_emb, int C, int S, int D, con
     int rc = upload_small(ctx, d_keep, h_keep.data(), sizeof(int) * (size_t)N);
     if (rc) return rc;
     // filter_embeddings (speakerDiarizer.cpp:2214-2259); x is also what cluster_labels normalises again
-    gather_normalize_kernel<<<(N + 127) / 128, 128, 0, ctx->stream>>>(d_emb, d_keep, N, D, d_x, d_xn);
+    gather_normalize_kernel<<<(unsigned)(((long)N * 32 + 255) / 256), 256, 0, ctx->stream>>>(d_emb, d_keep, N, D, d_x, nullptr);
     SD_LAUNCH_CHECK(ctx);
     rc = cluster_labels_launch(ctx, d_x, N, D, p, d_labels, d_num);
     if (rc) return rc;
@@ -928,22 +1816,26 @@ int clustering_launch(sd_ctx* ctx, const double* d_emb, int C, int S, int D, con
         if (*ctx->h_status) return ctx->fail(*ctx->h_status, "Vectors have zero magnitude.");
     }
     if (K < 1 || K > N) return ctx->fail(SD_ERR_CUDA, "cluster post-processing produced %d clusters", K);
-    const size_t o_cent = align_up(sizeof(int) * (size_t)K, 256);
-    char* base = (char*)ctx->scratch(BUF_CL_OUT, o_cent + sizeof(double) * (size_t)K * D);
+    char* base = (char*)ctx->scratch(BUF_CL_OUT, sizeof(double) * (size_t)K * D);
     if (!base) return SD_ERR_NOMEM;
     AssignWork w;
     w.emb = d_emb;
     w.x = d_x;
     w.labels = d_labels;
-    w.count = reinterpret_cast<int*>(base);
-    w.cent = reinterpret_cast<double*>(base + o_cent);
+    w.cent = reinterpret_cast<double*>(base);
     w.soft = d_soft;
     w.hard = d_hard;
     w.binarized = d_binarized;
     w.status = ctx->d_status;
-    centroid_kernel<<<1, 1024, 0, ctx->stream>>>(w, N, D, K);
+    if (D > 1024) return ctx->fail(SD_ERR_UNSUPPORTED, "embedding dimension %d > 1024", D);
+    cluster_means_kernel<<<K, means_threads(D), 0, ctx->stream>>>(d_x, d_labels, N, D, K, nullptr, w.cent);
     SD_LAUNCH_CHECK(ctx);
-    assign_kernel<<<(R + 127) / 128, 128, 0, ctx->stream>>>(w, R, S, D, K, F, soft_k_cap);
+    double* d_softk = (double*)ctx->scratch(BUF_CL_WORK, sizeof(double) * (size_t)R * K);
+    if (!d_softk) return SD_ERR_NOMEM;
+    assign_dist_kernel<<<(unsigned)(((long)R * K + 255) / 256), 256, 0, ctx->stream>>>(w, R, D, K, d_softk, K);
+    SD_LAUNCH_CHECK(ctx);
+    assign_argmax_kernel<<<(unsigned)(((long)R * 32 + 255) / 256), 256, 0, ctx->stream>>>(w, R, S, K, F, d_softk, K,
+                                                                                      soft_k_cap);
     SD_LAUNCH_CHECK(ctx);
     if (num_clusters_out) *num_clusters_out = K;
     return SD_OK;

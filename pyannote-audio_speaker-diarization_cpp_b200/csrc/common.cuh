@@ -75,6 +75,9 @@ struct sd_ctx {
     size_t flush_bytes = 0;
     int* d_status = nullptr;       // device-side status word (zero-magnitude etc.)
     int* h_status = nullptr;       // pinned mirror
+    unsigned long long* d_stats = nullptr;  // diagnostic counters (sd_debug_counters)
+    int force_exact_linkage = 0;            // test hook: skip the heap-free fast path
+    int linkage_threads = 0;                // tuning hook: 0 = auto, 512 or 1024
 
     int fail(int code, const char* fmt, ...) {
         char b[512];

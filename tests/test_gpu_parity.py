@@ -173,6 +173,53 @@ def test_pdist_linkage_fcluster_vs_oracle(ctx, oracle, N, D, seed):
         assert np.array_equal(ctx.cluster(xn, cut), oracle.fcluster(Zo, cut))
 
 
+@pytest.mark.parametrize("N,D,seed", [(3000, 32, 7), (6000, 16, 8), (15000, 8, 9)])
+def test_linkage_state_placement_modes(ctx, oracle, N, D, seed):
+    """N selects where the merge state lives (all shared memory / heap only / global); results must not change."""
+    rng = np.random.default_rng(seed)
+    cen = rng.standard_normal((7, D)) * 3
+    x = cen[rng.integers(0, 7, N)] + rng.standard_normal((N, D))
+    Z = ctx.linkage(x)
+    Zo = oracle.linkage(x)
+    assert np.array_equal(Z, Zo)
+    for cut in (1.0, 2.5, 4.0, 1e9):
+        assert np.array_equal(ctx.fcluster(Z, cut), oracle.fcluster(Zo, cut))
+
+
+def test_fcluster_nan_distances_fall_back_to_sequential(ctx, oracle):
+    """NaN merge distances (negative radicand in the centroid update) take the exact sequential path."""
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((60, 5))
+    Z = oracle.linkage(x)
+    Z[[5, 17, 40], 2] = np.nan
+    for cut in (0.5, 1.5, 3.0):
+        assert np.array_equal(ctx.fcluster(Z, cut), oracle.fcluster(Z, cut))
+
+
+def test_linkage_fast_and_exact_paths_agree(ctx, oracle, pkg, synth):
+    """The heap-free kernel (unique minimum proven at every pop) and the heap-driven kernel give the same Z;
+    tie-free data never needs the hand-over, tied data always takes it."""
+    emb, _ = synth.embeddings(31, 300, 3, 192, n_speakers=5, nan_frac=0.0, tiny=(3,))
+    xn = oracle.normalize(emb.reshape(-1, 192))
+    Zo = oracle.linkage(xn)
+    ctx.debug_counters()
+    Zf = ctx.linkage(xn)
+    c = ctx.debug_counters()
+    assert np.array_equal(Zf, Zo) and c[2] == 0
+    ctx.set_option(pkg.SD_OPT_FORCE_EXACT_LINKAGE, 1)
+    try:
+        Ze = ctx.linkage(xn)
+    finally:
+        ctx.set_option(pkg.SD_OPT_FORCE_EXACT_LINKAGE, 0)
+    assert np.array_equal(Ze, Zo)
+    gx, gy = np.meshgrid(np.arange(7.0), np.arange(5.0))
+    grid = np.stack([gx.ravel(), gy.ravel()], 1)
+    ctx.debug_counters()
+    Zg = ctx.linkage(grid)
+    c = ctx.debug_counters()
+    assert np.array_equal(Zg, oracle.linkage(grid)) and c[2] == 1  # tied minimum -> handed to the heap kernel
+
+
 def test_linkage_golden_toy_and_ties(ctx, golden_dir):
     d = g(golden_dir, "linkage_small.npz")
     assert np.array_equal(ctx.linkage(d["toy"]), d["toy_Z"])
