@@ -1,0 +1,369 @@
+// sdb200_host.hpp -- C++ host shim: the reference's function-level API on top of the libsdb200 C-ABI.
+//
+// The reference (leohuang2013/pyannote-audio_speaker-diarization_cpp) has no plugin interface; its hot path is
+// a set of C++ functions taking and returning nested std::vector by value.  Every function below
+// keeps the name, argument order, defaults and error behaviour of the reference function it replaces
+// (file:line relative to the reference checkout, SD = pipeline/src/speakerDiarizer.cpp,
+// CL = pipeline/src/clustering/clustering.cpp), converts nested vectors <-> flat row-major buffers and calls the
+// C-ABI.  There is no CPU implementation behind it: without a CUDA device every call throws.
+//
+// `SlidingWindow`-typed parameters are templates: any type with public members start, step, duration,
+// num_samples works, in particular the reference's own class (SD:1029), so the shim can be included in the
+// reference translation unit and called from speakerDiarization() (SD:2937) unchanged -- see INTEGRATION.md.
+//
+// Errors: the reference asserts or throws std::runtime_error; the shim throws std::runtime_error carrying
+// sd_last_error().  SD_ERR_ZERO_MAGNITUDE maps to the reference's message "Vectors have zero magnitude.".
+#pragma once
+
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/sdb200.h"
+
+namespace sdb200 {
+
+using vec1f = std::vector<float>;
+using vec2f = std::vector<std::vector<float>>;
+using vec3f = std::vector<std::vector<std::vector<float>>>;
+using vec4f = std::vector<std::vector<std::vector<std::vector<float>>>>;
+using vec1d = std::vector<double>;
+using vec2d = std::vector<std::vector<double>>;
+using vec3d = std::vector<std::vector<std::vector<double>>>;
+
+// One context per host thread (the reference is single-threaded and non-re-entrant).
+class Context {
+public:
+    explicit Context(int device = 0) {
+        if (sd_ctx_create(device, &ctx_) != SD_OK)
+            throw std::runtime_error("sdb200: no usable CUDA device (this library has no CPU fallback)");
+    }
+    ~Context() { sd_ctx_destroy(ctx_); }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    sd_ctx* get() const { return ctx_; }
+    void check(int rc) const {
+        if (rc == SD_OK) return;
+        if (rc == SD_ERR_ZERO_MAGNITUDE) throw std::runtime_error("Vectors have zero magnitude.");  // SD:494
+        throw std::runtime_error(std::string("sdb200: ") + sd_last_error(ctx_));
+    }
+
+private:
+    sd_ctx* ctx_ = nullptr;
+};
+
+inline Context& context() {
+    static thread_local Context c(0);
+    return c;
+}
+
+namespace detail {
+template <typename T, typename U>
+std::vector<U> flatten3(const std::vector<std::vector<std::vector<T>>>& v) {
+    std::vector<U> out;
+    if (v.empty() || v[0].empty()) return out;
+    out.reserve(v.size() * v[0].size() * v[0][0].size());
+    for (const auto& a : v)
+        for (const auto& b : a)
+            for (T c : b) out.push_back(static_cast<U>(c));
+    return out;
+}
+template <typename T, typename U>
+std::vector<U> flatten2(const std::vector<std::vector<T>>& v) {
+    std::vector<U> out;
+    if (v.empty()) return out;
+    out.reserve(v.size() * v[0].size());
+    for (const auto& a : v)
+        for (T c : a) out.push_back(static_cast<U>(c));
+    return out;
+}
+template <typename U, typename T>
+std::vector<std::vector<std::vector<T>>> unflatten3(const std::vector<U>& f, size_t a, size_t b, size_t c) {
+    std::vector<std::vector<std::vector<T>>> v(a, std::vector<std::vector<T>>(b, std::vector<T>(c)));
+    size_t n = 0;
+    for (size_t i = 0; i < a; ++i)
+        for (size_t j = 0; j < b; ++j)
+            for (size_t k = 0; k < c; ++k) v[i][j][k] = static_cast<T>(f[n++]);
+    return v;
+}
+template <typename U, typename T>
+std::vector<std::vector<T>> unflatten2(const std::vector<U>& f, size_t a, size_t b) {
+    std::vector<std::vector<T>> v(a, std::vector<T>(b));
+    size_t n = 0;
+    for (size_t i = 0; i < a; ++i)
+        for (size_t j = 0; j < b; ++j) v[i][j] = static_cast<T>(f[n++]);
+    return v;
+}
+template <class SW>
+sd_window to_window(const SW& w) {
+    sd_window r;
+    r.start = w.start;
+    r.step = w.step;
+    r.duration = w.duration;
+    r.num_samples = static_cast<int64_t>(w.num_samples);
+    return r;
+}
+template <class SW>
+void from_window(const sd_window& r, SW& w) {
+    w.start = r.start;
+    w.step = r.step;
+    w.duration = r.duration;
+    w.num_samples = static_cast<decltype(w.num_samples)>(r.num_samples);
+}
+}  // namespace detail
+
+// ---------------------------------------------------------------------------------------------------
+// Embedding stage front-end
+// ---------------------------------------------------------------------------------------------------
+
+// What EmbeddingModel1::infer (SD:1977-2036) + the packing of _infer (SD:1889-1917) hand to emd4.onnx:
+// `audio` is the flat [32][T][201][2] tensor (rows beyond data.size() are zero), `wav_lens` the 32 relative
+// lengths (1.0 beyond lens.size()), `dims` the four tensor dimensions for Ort::Value::CreateTensor.
+struct EmbeddingInput {
+    std::vector<float> audio;
+    std::vector<float> wav_lens;
+    int64_t dims[4];
+};
+
+inline EmbeddingInput embedding_input(const vec2f& data, const vec1f& lens, int batch_size = 32) {
+    Context& c = context();
+    const int B = static_cast<int>(data.size());
+    const int L = static_cast<int>(data[0].size());
+    sd_stft_params p;
+    sd_stft_default_params(&p);
+    p.pad_batch_to = batch_size;
+    const int64_t T = sd_stft_num_frames(L, p.hop);
+    const int rows = B > batch_size ? B : batch_size;
+    EmbeddingInput out;
+    out.audio.resize(static_cast<size_t>(rows) * T * (p.n_fft / 2 + 1) * 2);
+    out.wav_lens.resize(batch_size);
+    std::vector<float> flat = detail::flatten2<float, float>(data);
+    c.check(sd_stft(c.get(), flat.data(), B, L, &p, out.audio.data()));
+    if (sd_pack_wav_lens(lens.data(), static_cast<int>(lens.size()), batch_size, out.wav_lens.data()) != SD_OK)
+        throw std::runtime_error("sdb200: more wav_lens than batch rows");
+    out.dims[0] = rows;
+    out.dims[1] = T;
+    out.dims[2] = p.n_fft / 2 + 1;
+    out.dims[3] = 2;
+    return out;
+}
+
+// The 4-D vector the reference builds at SD:2018-2036 ([B][T][201][2]); kept for callers that want that shape.
+inline vec4f stft(const vec2f& data) {
+    Context& c = context();
+    const int B = static_cast<int>(data.size());
+    const int L = static_cast<int>(data[0].size());
+    sd_stft_params p;
+    sd_stft_default_params(&p);
+    const int64_t T = sd_stft_num_frames(L, p.hop);
+    const int bins = p.n_fft / 2 + 1;
+    std::vector<float> flat = detail::flatten2<float, float>(data), out(static_cast<size_t>(B) * T * bins * 2);
+    c.check(sd_stft(c.get(), flat.data(), B, L, &p, out.data()));
+    vec4f r(B, vec3f(T, vec2f(bins, vec1f(2))));
+    size_t n = 0;
+    for (int b = 0; b < B; ++b)
+        for (int64_t t = 0; t < T; ++t)
+            for (int f = 0; f < bins; ++f) {
+                r[b][t][f][0] = out[n++];
+                r[b][t][f][1] = out[n++];
+            }
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// PipelineHelper::aggregate, SD:1167-1311
+// ---------------------------------------------------------------------------------------------------
+template <class SW>
+vec2d aggregate(const vec3d& scoreData, const SW& scores_frames, const SW& pre_frames, SW& post_frames,
+                bool hamming = false, double missing = NAN, bool skip_average = false,
+                double epsilon = std::numeric_limits<double>::epsilon()) {
+    Context& c = context();
+    const int C = static_cast<int>(scoreData.size());
+    const int F = static_cast<int>(scoreData[0].size());
+    const int K = static_cast<int>(scoreData[0][0].size());
+    const sd_window cw = detail::to_window(scores_frames), fw = detail::to_window(pre_frames);
+    const int64_t NF = sd_aggregate_num_frames(C, &cw, &fw);
+    std::vector<double> flat = detail::flatten3<double, double>(scoreData), out(static_cast<size_t>(NF) * K);
+    int64_t n = 0;
+    sd_window post;
+    c.check(sd_aggregate(c.get(), flat.data(), C, F, K, &cw, &fw, hamming ? 1 : 0, missing, skip_average ? 1 : 0,
+                         epsilon, out.data(), NF, &n, &post, nullptr, nullptr));
+    detail::from_window(post, post_frames);
+    return detail::unflatten2<double, double>(out, static_cast<size_t>(NF), static_cast<size_t>(K));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SegmentModel::binarize_swf / binarize_ndarray / trim / speaker_count, Helper::cleanSegmentations
+// ---------------------------------------------------------------------------------------------------
+constexpr double kOnset = 0.4442333667381752;  // SegmentModel::m_diarization_segmentation_threashold, SD:1339
+
+inline vec3d binarize_swf(const vec3f& scores, bool initial_state = false, double onset = kOnset) {  // SD:1506
+    Context& c = context();
+    const int C = static_cast<int>(scores.size()), F = static_cast<int>(scores[0].size()),
+              K = static_cast<int>(scores[0][0].size());
+    std::vector<float> flat = detail::flatten3<float, float>(scores);
+    std::vector<double> out(flat.size());
+    c.check(sd_binarize(c.get(), flat.data(), C, F, K, onset, initial_state ? 1 : 0, out.data()));
+    return detail::unflatten3<double, double>(out, C, F, K);
+}
+
+inline std::vector<std::vector<bool>> binarize_ndarray(const vec2d& scores, double onset = 0.5,
+                                                       bool initialState = false) {  // SD:1565
+    Context& c = context();
+    const int R = static_cast<int>(scores.size()), F = static_cast<int>(scores[0].size());
+    std::vector<double> flat = detail::flatten2<double, double>(scores);
+    std::vector<uint8_t> out(flat.size());
+    c.check(sd_binarize_rows(c.get(), flat.data(), R, F, onset, initialState ? 1 : 0, out.data()));
+    std::vector<std::vector<bool>> r(R, std::vector<bool>(F));
+    for (int i = 0; i < R; ++i)
+        for (int j = 0; j < F; ++j) r[i][j] = out[static_cast<size_t>(i) * F + j] != 0;
+    return r;
+}
+
+template <class SW>
+vec3d trim(const vec3d& binarized, double left, double right, const SW& before_trim, SW& trimmed_frames) {  // SD:1742
+    Context& c = context();
+    const int C = static_cast<int>(binarized.size()), F = static_cast<int>(binarized[0].size()),
+              K = static_cast<int>(binarized[0][0].size());
+    const int64_t Ft = sd_trim_num_frames(F, left, right);
+    std::vector<double> flat = detail::flatten3<double, double>(binarized), out(static_cast<size_t>(C) * Ft * K);
+    const sd_window bw = detail::to_window(before_trim);
+    sd_window tw;
+    c.check(sd_trim(c.get(), flat.data(), C, F, K, left, right, &bw, out.data(), &tw));
+    detail::from_window(tw, trimmed_frames);
+    return detail::unflatten3<double, double>(out, C, static_cast<size_t>(Ft), K);
+}
+
+// SD:1665-1738.  `segmentations` and `num_samples` are unused by the reference body as well; the chunk window is
+// SegmentModel's (0.0, m_step = 0.5, m_duration = 5.0) unless overridden.
+template <class SW>
+std::vector<int> speaker_count(const vec3f& /*segmentations*/, const vec3d& binarized, const SW& pre_frame,
+                               SW& count_frames, int /*num_samples*/, double chunk_step = 0.5,
+                               double chunk_duration = 5.0) {
+    Context& c = context();
+    const int C = static_cast<int>(binarized.size()), F = static_cast<int>(binarized[0].size()),
+              K = static_cast<int>(binarized[0][0].size());
+    sd_window cw;
+    cw.start = 0.0;
+    cw.step = chunk_step;
+    cw.duration = chunk_duration;
+    cw.num_samples = 1;
+    const sd_window fw = detail::to_window(pre_frame);
+    std::vector<double> flat = detail::flatten3<double, double>(binarized);
+    const int64_t cap = static_cast<int64_t>((C * chunk_step + chunk_duration) / fw.step) + F + 64;
+    std::vector<int32_t> out(static_cast<size_t>(cap));
+    int64_t n = 0;
+    sd_window cf;
+    c.check(sd_speaker_count(c.get(), flat.data(), C, F, K, &cw, &fw, out.data(), cap, &n, &cf));
+    detail::from_window(cf, count_frames);
+    return std::vector<int>(out.begin(), out.begin() + n);
+}
+
+inline vec3d cleanSegmentations(const vec3d& data) {  // Helper::cleanSegmentations, SD:710
+    Context& c = context();
+    const int C = static_cast<int>(data.size()), F = static_cast<int>(data[0].size()),
+              K = static_cast<int>(data[0][0].size());
+    std::vector<double> flat = detail::flatten3<double, double>(data), out(flat.size());
+    c.check(sd_clean_segmentations(c.get(), flat.data(), C, F, K, out.data()));
+    return detail::unflatten3<double, double>(out, C, F, K);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Clustering library (clustering.h:4-12) and Helper::normalizeEmbeddings (SD:344)
+// ---------------------------------------------------------------------------------------------------
+inline void normalizeEmbeddings(vec2d& embeddings) {
+    Context& c = context();
+    const int N = static_cast<int>(embeddings.size()), D = static_cast<int>(embeddings[0].size());
+    std::vector<double> flat = detail::flatten2<double, double>(embeddings);
+    c.check(sd_normalize(c.get(), flat.data(), N, D));
+    embeddings = detail::unflatten2<double, double>(flat, N, D);
+}
+
+struct Clustering {
+    static void linkage(const vec2d& input, vec2d& dendrogram) {  // CL:417
+        Context& c = context();
+        const int N = static_cast<int>(input.size()), D = static_cast<int>(input[0].size());
+        std::vector<double> flat = detail::flatten2<double, double>(input), Z(static_cast<size_t>(N - 1) * 4);
+        c.check(sd_linkage(c.get(), flat.data(), N, D, Z.data()));
+        dendrogram = detail::unflatten2<double, double>(Z, static_cast<size_t>(N - 1), 4);
+    }
+    static void fcluster(const vec2d& Z, double cutoff, std::vector<int>& clusters) {  // CL:442
+        Context& c = context();
+        const int N = static_cast<int>(Z.size()) + 1;
+        std::vector<double> flat = detail::flatten2<double, double>(Z);
+        std::vector<int32_t> T(static_cast<size_t>(N));
+        c.check(sd_fcluster(c.get(), flat.data(), N, cutoff, T.data()));
+        clusters.assign(T.begin(), T.end());
+    }
+    static std::vector<int> cluster(const vec2d& input, double cutoff) {  // CL:459
+        Context& c = context();
+        const int N = static_cast<int>(input.size()), D = static_cast<int>(input[0].size());
+        std::vector<double> flat = detail::flatten2<double, double>(input);
+        std::vector<int32_t> T(static_cast<size_t>(N));
+        c.check(sd_cluster(c.get(), flat.data(), N, D, cutoff, T.data()));
+        return std::vector<int>(T.begin(), T.end());
+    }
+};
+
+// Helper::cosineSimilarity (cosine *distance*), SD:502
+inline vec2d cosineSimilarity(const vec2d& a, const vec2d& b) {
+    Context& c = context();
+    const int na = static_cast<int>(a.size()), nb = static_cast<int>(b.size()), D = static_cast<int>(a[0].size());
+    if (b[0].size() != a[0].size()) throw std::runtime_error("Vector sizes must be equal.");  // SD:480
+    std::vector<double> fa = detail::flatten2<double, double>(a), fb = detail::flatten2<double, double>(b),
+                        out(static_cast<size_t>(na) * nb);
+    c.check(sd_cosine_cdist(c.get(), fa.data(), na, fb.data(), nb, D, out.data()));
+    return detail::unflatten2<double, double>(out, na, nb);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Cluster (SD:2044-2425)
+// ---------------------------------------------------------------------------------------------------
+class Cluster {
+public:
+    // Cluster::clustering, SD:2063.  `segmentations` is unused by the reference body too.  When `binarized` is
+    // given, the inactive-speaker pass of speakerDiarization() (SD:3166-3191, hard = -2) is applied as well.
+    void clustering(const vec3d& embeddings, const vec3d& /*segmentations*/, std::vector<std::vector<int>>& hard_clusters,
+                    int num_clusters = -1, int min_clusters = -1, int max_clusters = -1,
+                    const vec3d* binarized = nullptr) {
+        Context& c = context();
+        const int C = static_cast<int>(embeddings.size()), S = static_cast<int>(embeddings[0].size()),
+                  D = static_cast<int>(embeddings[0][0].size());
+        sd_cluster_params p;
+        sd_cluster_default_params(&p);
+        p.num_clusters = num_clusters;
+        p.min_clusters = min_clusters;
+        p.max_clusters = max_clusters;
+        std::vector<double> flat = detail::flatten3<double, double>(embeddings), bin;
+        int F = 0;
+        if (binarized) {
+            bin = detail::flatten3<double, double>(*binarized);
+            F = static_cast<int>((*binarized)[0].size());
+        }
+        std::vector<int32_t> hard(static_cast<size_t>(C) * S);
+        int k = 0;
+        c.check(sd_clustering(c.get(), flat.data(), C, S, D, &p, binarized ? bin.data() : nullptr, F, hard.data(),
+                              nullptr, 0, &k));
+        hard_clusters = detail::unflatten2<int32_t, int>(hard, C, S);
+    }
+
+    // Cluster::cluster, SD:2300 (labels of already-filtered embeddings)
+    std::vector<int> cluster(const vec2d& embeddings, int min_clusters, int max_clusters, int num_clusters) {
+        Context& c = context();
+        const int N = static_cast<int>(embeddings.size()), D = static_cast<int>(embeddings[0].size());
+        sd_cluster_params p;
+        sd_cluster_default_params(&p);
+        p.num_clusters = num_clusters;
+        p.min_clusters = min_clusters;
+        p.max_clusters = max_clusters;
+        std::vector<double> flat = detail::flatten2<double, double>(embeddings);
+        std::vector<int32_t> lab(static_cast<size_t>(N));
+        c.check(sd_cluster_labels(c.get(), flat.data(), N, D, &p, lab.data()));
+        return std::vector<int>(lab.begin(), lab.end());
+    }
+};
+
+}  // namespace sdb200
