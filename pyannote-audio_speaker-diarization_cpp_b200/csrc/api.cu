@@ -224,6 +224,9 @@ int sd_ctx_set_option(sd_ctx* ctx, int option, int value) {
         case SD_OPT_FORCE_EXACT_LINKAGE:
             ctx->force_exact_linkage = value != 0;
             return SD_OK;
+        case SD_OPT_STFT_VARIANT:
+            ctx->stft_variant = value;
+            return SD_OK;
         case SD_OPT_LINKAGE_THREADS:
             if (value != 0 && value != 512 && value != 1024)
                 return ctx->fail(SD_ERR_INVALID, "SD_OPT_LINKAGE_THREADS must be 0, 512 or 1024");

@@ -112,6 +112,50 @@ SD_HD void stft_phase1(const float* sig, int fa_off, int fb_off, const float (&w
     }
 }
 
+// Padded staging: PAD extra floats are inserted after every kHop samples of the tile, so frame f starts at
+// f * (kHop + PAD) and sample 20*n1 + r of a frame sits kSigPad(n1) floats further.  With PAD = 10 the frame-pair
+// bases of consecutive 20-thread groups differ by 340 = 20 (mod 32) banks: the lanes of the two groups that share
+// a warp then cover all 32 banks exactly once -> conflict-free 4-byte reads.  PAD = 12 is used instead: the segment
+// stride (172 floats = 688 B) stays 16-byte aligned, which the bulk (TMA) copies need, at the price of a 2-way
+// conflict on 4 of the 32 lanes.
+constexpr int kPad = 12;
+constexpr int kHopP = kHop + kPad;
+SD_HD constexpr int sig_pad(int n1) { return kPad * ((20 * n1) / kHop); }
+
+// phase 1 with the window (wtab[20*n1 + r]) and the twiddles (twT[k1*20 + r]) in shared tables
+SD_HD void stft_phase1_tab(const float* sig, int fa_off, int fb_off, const float* wtab, const float2* twT, int g, int r,
+                           float2* xchg) {
+    float2 v[20];
+#pragma unroll
+    for (int n1 = 0; n1 < 20; ++n1) {
+        const int o = 20 * n1 + r;
+        const float w = wtab[o];
+        v[n1] = make_float2(sig[fa_off + o + sig_pad(n1)] * w, sig[fb_off + o + sig_pad(n1)] * w);
+    }
+    dft20(v);
+    float2* dst = xchg + g * kGroupStride + r;
+#pragma unroll
+    for (int k1 = 0; k1 < 20; ++k1) {
+        float2 y = v[dft20_slot(k1)];
+        if (k1 > 0) y = cmul(y, twT[k1 * 20 + r]);
+        dst[k1 * kXchgRow] = y;
+    }
+}
+
+// phase 2 split in two so that the exchange buffer can be reused for the spectrum: load + transform ...
+SD_HD void stft_phase2_load(const float2* xchg, int g, int r, float2 (&v)[20]) {
+    const float2* src = xchg + g * kGroupStride + r * kXchgRow;
+#pragma unroll
+    for (int n2 = 0; n2 < 20; ++n2) v[n2] = src[n2];
+    dft20(v);
+}
+// ... (barrier) ... then write Z[r + 20*k2] into the same buffer
+SD_HD void stft_phase2_store(const float2 (&v)[20], int g, int r, float2* zbuf) {
+    float2* dst = zbuf + g * kGroupStride + r;
+#pragma unroll
+    for (int k2 = 0; k2 < 20; ++k2) dst[20 * k2] = v[dft20_slot(k2)];
+}
+
 SD_HD void stft_phase2(const float2* xchg, int g, int r, float2* zbuf) {
     float2 v[20];
     const float2* src = xchg + g * kGroupStride + r * kXchgRow;
@@ -136,6 +180,73 @@ SD_HD void stft_phase3(const float2* zbuf, int g, int r, float* outA, float* out
             if (outA) reinterpret_cast<float2*>(outA)[k] = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
             if (outB) reinterpret_cast<float2*>(outB)[k] = make_float2(0.5f * (zk.y + zm.y), 0.5f * (zm.x - zk.x));
         }
+    }
+}
+
+// Phase 3 for a spectrum that is already scaled by 1/2 (the factor is folded into the window table):
+//   A[k] = Z[k] + conj Z[400-k],  B[k] = -i (Z[k] - conj Z[400-k]).
+// Thread r handles k = r + 20 m, m = 0..9 (k = 0 and k = 200 are the two extra bins of thread 0), so the partner
+// index 400 - k is a compile-time offset from a per-thread base and there is no per-bin branch.
+template <bool HAS_A, bool HAS_B>
+SD_HD void stft_phase3_fast(const float2* zbuf, int g, int r, float* outA, float* outB) {
+    const float2* z = zbuf + g * kGroupStride;
+    float2* oa = reinterpret_cast<float2*>(outA);
+    float2* ob = reinterpret_cast<float2*>(outB);
+    if (r == 0) {  // purely real bins: partner of Z[0] is Z[0], of Z[200] is Z[200]
+        const float2 z0 = z[0], zn = z[200];
+        if (HAS_A) {
+            oa[0] = make_float2(z0.x + z0.x, 0.f);
+            oa[200] = make_float2(zn.x + zn.x, 0.f);
+        }
+        if (HAS_B) {
+            ob[0] = make_float2(z0.y + z0.y, 0.f);
+            ob[200] = make_float2(zn.y + zn.y, 0.f);
+        }
+    }
+    const float2* zk = z + r;
+    const float2* zm = z + kNfft - r;
+#pragma unroll
+    for (int m = 0; m < 10; ++m) {
+        if (m == 0 && r == 0) continue;
+        const float2 a = zk[20 * m];
+        const float2 b = zm[-20 * m];
+        if (HAS_A) oa[r + 20 * m] = make_float2(a.x + b.x, a.y - b.y);
+        if (HAS_B) ob[r + 20 * m] = make_float2(a.y + b.y, b.x - a.x);
+    }
+}
+
+// ---- compact second exchange -----------------------------------------------------------------------------
+// After phase 2 thread r holds Z[r + 20*k2] (k2 = 0..19) in registers.  The one-sided bins k <= 200 of the two
+// real frames need Z[k] (own registers, k2 = m <= 9) and Z[400 - k] (held by thread 20 - r as k2 = 19 - m >= 10).
+// So only the upper half Z[j], j >= 200, ever crosses threads: thread r publishes its k2 = 10..19 values
+// (and Z[0] for the k = 0 bin) into a 201-entry buffer indexed by j - 200.
+constexpr int kZStride = 212;  // float2 units per group (201 used); 212 - 20 = 12 * 16 keeps the stores conflict-free
+
+SD_HD void stft_publish_upper(const float2 (&v)[20], int g, int r, float2* zup) {
+    float2* dst = zup + g * kZStride + r;
+#pragma unroll
+    for (int k2 = 10; k2 < 20; ++k2) dst[20 * (k2 - 10)] = v[dft20_slot(k2)];  // Z[200 + r + 20 (k2 - 10)]
+    if (r == 0) dst[200] = v[dft20_slot(0)];                                   // Z[400] == Z[0] (periodicity)
+}
+
+// Spectrum scaled by 1/2 (folded into the window): A[k] = Z[k] + conj Z[400-k], B[k] = -i (Z[k] - conj Z[400-k]).
+template <bool HAS_A, bool HAS_B>
+SD_HD void stft_split_store(const float2 (&v)[20], const float2* zup, int g, int r, float* outA, float* outB) {
+    const float2* zu = zup + g * kZStride;  // zu[j - 200] = Z[j]
+    float2* oa = reinterpret_cast<float2*>(outA);
+    float2* ob = reinterpret_cast<float2*>(outB);
+    const float2* zm = zu + 200 - r;  // Z[400 - (r + 20 m)] = zu[200 - r - 20 m]
+#pragma unroll
+    for (int m = 0; m < 10; ++m) {
+        const float2 a = v[dft20_slot(m)];
+        const float2 b = zm[-20 * m];
+        if (HAS_A) oa[r + 20 * m] = make_float2(a.x + b.x, a.y - b.y);
+        if (HAS_B) ob[r + 20 * m] = make_float2(a.y + b.y, b.x - a.x);
+    }
+    if (r == 0) {  // k = 200: partner of Z[200] is itself
+        const float2 a = v[dft20_slot(10)];
+        if (HAS_A) oa[200] = make_float2(a.x + a.x, 0.f);
+        if (HAS_B) ob[200] = make_float2(a.y + a.y, 0.f);
     }
 }
 

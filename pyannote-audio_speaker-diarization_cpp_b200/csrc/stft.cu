@@ -22,9 +22,14 @@ struct StftCfg {
     static constexpr int kThreads = GROUPS * kRadix;
     static constexpr int kTileFrames = GROUPS * 2;
     static constexpr int kSigFloats = (kTileFrames - 1) * kHop + kNfft;  // samples covered by one tile
-    static constexpr int kSigChunks = kSigFloats / 4;                    // 16-byte chunks (kSigFloats % 4 == 0)
-    static constexpr size_t kSmemBytes =
-        2 * kSigFloats * sizeof(float) + 2 * (size_t)GROUPS * kGroupStride * sizeof(float2);
+    static constexpr int kSigHops = (kSigFloats + kHop - 1) / kHop;      // hop-sized segments, each padded
+    static constexpr int kSigPadded = kSigFloats + kPad * kSigHops + 4;  // staged floats
+    static constexpr size_t kSigBytes = (size_t)((kSigPadded + 3) / 4 * 4) * sizeof(float);
+    static constexpr size_t kZBytes = (size_t)GROUPS * kZStride * sizeof(float2);
+    // the upper-spectrum buffer shares storage with the staged samples (dead after phase 1)
+    static constexpr size_t kSmemBytes = (kSigBytes > kZBytes ? kSigBytes : kZBytes) +
+                                         (size_t)GROUPS * kGroupStride * sizeof(float2) + kNfft * sizeof(float) +
+                                         kNfft * sizeof(float2);
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -41,9 +46,9 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
-// Stage the samples of tile `tile` (item b, frames [t0, t0 + kTileFrames)) into sig[0 .. kSigFloats).
-// Sample index of sig[j] inside the item: t0*hop - n_fft/2 + j; out-of-range samples are the zeros of
-// torch::stft's centre padding (pad_mode "constant").
+// Stage the samples of an edge tile (item b, frames [t0, t0 + kTileFrames)) into the padded buffer: sample j of
+// the tile (item index t0*hop - n_fft/2 + j) goes to sig[j + kPad * (j / kHop)].  Out-of-range samples are the
+// zeros of torch::stft's centre padding (pad_mode "constant").  16-byte pieces never straddle a hop boundary.
 template <int GROUPS>
 __device__ __forceinline__ void stage_tile(float* sig, const float* __restrict__ wav, int L, long tile,
                                            int tiles_per_item, bool aligned16) {
@@ -53,82 +58,146 @@ __device__ __forceinline__ void stage_tile(float* sig, const float* __restrict__
     const long s0 = (long)ti * Cfg::kTileFrames * kHop - kNfft / 2;
     const float* src = wav + (size_t)b * L;
     if (aligned16) {
-        for (int c = threadIdx.x; c < Cfg::kSigChunks; c += Cfg::kThreads) {
-            const long s = s0 + 4L * c;
+        for (int c = threadIdx.x; c < Cfg::kSigFloats / 4; c += Cfg::kThreads) {
+            const int j = 4 * c;
+            const long s = s0 + j;
+            float* dst = sig + j + kPad * (j / kHop);
             if (s >= 0 && s + 3 < L)
-                cp_async16(sig + 4 * c, src + s);
+                cp_async16(dst, src + s);
             else {
                 float4 v;
                 v.x = (s >= 0 && s < L) ? src[s] : 0.f;
                 v.y = (s + 1 >= 0 && s + 1 < L) ? src[s + 1] : 0.f;
                 v.z = (s + 2 >= 0 && s + 2 < L) ? src[s + 2] : 0.f;
                 v.w = (s + 3 >= 0 && s + 3 < L) ? src[s + 3] : 0.f;
-                *reinterpret_cast<float4*>(sig + 4 * c) = v;
+                *reinterpret_cast<float4*>(dst) = v;
             }
         }
     } else {
         for (int j = threadIdx.x; j < Cfg::kSigFloats; j += Cfg::kThreads) {
             const long s = s0 + j;
+            float* dst = sig + j + kPad * (j / kHop);
             if (s >= 0 && s < L)
-                cp_async4(sig + j, src + s);
+                cp_async4(dst, src + s);
             else
-                sig[j] = 0.f;
+                dst[0] = 0.f;
         }
     }
 }
 
-template <int GROUPS>
-__global__ void __launch_bounds__(GROUPS* kRadix)
+// ---- mbarrier / bulk-copy (TMA) helpers ----
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(bytes));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(a),
+        "r"(parity));
+}
+__device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+template <int GROUPS, int MINB>
+__global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     stft400_kernel(const float* __restrict__ wav, float* __restrict__ out, int L, int T, int tiles_per_item,
                    long total_tiles, const float* __restrict__ window, const float2* __restrict__ twiddle,
                    int aligned16) {
     using Cfg = StftCfg<GROUPS>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* sig0 = reinterpret_cast<float*>(smem_raw);
-    float* sig1 = sig0 + Cfg::kSigFloats;
-    float2* xchg = reinterpret_cast<float2*>(sig1 + Cfg::kSigFloats);
-    float2* zbuf = xchg + GROUPS * kGroupStride;
+    float2* xbuf = reinterpret_cast<float2*>(smem_raw);                 // phase 1 -> phase 2 transpose
+    float2* twT = xbuf + GROUPS * kGroupStride;                         // twT[k1*20 + r]
+    float* wtab = reinterpret_cast<float*>(twT + kNfft);                // window, pre-scaled by 1/2
+    float* sig = wtab + kNfft;                                          // padded samples of the tile
+    float2* zup = reinterpret_cast<float2*>(sig);                       // upper half of the spectrum (aliases sig)
+    __shared__ __align__(8) uint64_t bar;
 
     const int g = threadIdx.x / kRadix;
     const int r = threadIdx.x - g * kRadix;
-
-    // per-thread constants: this thread always plays role r
-    float win[20];
-    float2 tw[20];
-#pragma unroll
-    for (int i = 0; i < 20; ++i) {
-        win[i] = window[20 * i + r];
-        tw[i] = twiddle[r * 20 + i];
+    for (int i = threadIdx.x; i < kNfft; i += Cfg::kThreads) {
+        wtab[i] = 0.5f * window[i];  // exact scaling; lets phase 3 drop its multiplications
+        const int k1 = i / 20, rr = i - k1 * 20;
+        twT[i] = twiddle[rr * 20 + k1];
     }
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+    }
+    __syncthreads();
 
+    // A tile is "interior" when all its samples exist: it is then fetched by one thread with bulk (TMA) copies,
+    // one per hop-sized segment (the padded layout), completing on an mbarrier.
+    auto interior = [&](long tile) -> bool {
+        const int ti = (int)(tile % tiles_per_item);
+        const long s0 = (long)ti * Cfg::kTileFrames * kHop - kNfft / 2;
+        return aligned16 && s0 >= 0 && s0 + Cfg::kSigFloats <= L;
+    };
+    auto issue_bulk = [&](long tile) {  // thread 0 only
+        const int b = (int)(tile / tiles_per_item);
+        const int ti = (int)(tile - (long)b * tiles_per_item);
+        const long s0 = (long)ti * Cfg::kTileFrames * kHop - kNfft / 2;
+        const float* src = wav + (size_t)b * L + s0;
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // earlier generic reads of sig vs async writes
+        mbar_expect_tx(&bar, Cfg::kSigFloats * sizeof(float));
+#pragma unroll 1
+        for (int j = 0; j < Cfg::kSigFloats; j += kHop) {
+            const int n = (Cfg::kSigFloats - j) < kHop ? (Cfg::kSigFloats - j) : kHop;
+            bulk_g2s(sig + j + kPad * (j / kHop), src + j, n * sizeof(float), &bar);
+        }
+    };
+
+    unsigned parity = 0;
     long tile = blockIdx.x;
-    if (tile >= total_tiles) return;
-    stage_tile<GROUPS>(sig0, wav, L, tile, tiles_per_item, aligned16 != 0);
-    cp_async_commit();
-    int cur = 0;
+    bool fetched = false;
+    if (tile < total_tiles && interior(tile)) {
+        if (threadIdx.x == 0) issue_bulk(tile);
+        fetched = true;
+    }
     for (; tile < total_tiles; tile += gridDim.x) {
-        float* sig = cur ? sig1 : sig0;
-        const long next = tile + gridDim.x;
-        if (next < total_tiles) stage_tile<GROUPS>(cur ? sig0 : sig1, wav, L, next, tiles_per_item, aligned16 != 0);
-        cp_async_commit();
-        cp_async_wait<1>();  // everything but the group just committed has landed
-        __syncthreads();
-
-        stft_phase1(sig, (2 * g) * kHop, (2 * g + 1) * kHop, win, tw, g, r, xchg);
-        __syncthreads();
-        stft_phase2(xchg, g, r, zbuf);
-        __syncthreads();
+        if (fetched) {
+            mbar_wait(&bar, parity);
+            parity ^= 1;
+        } else {
+            stage_tile<GROUPS>(sig, wav, L, tile, tiles_per_item, aligned16 != 0);
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
+        }
+        stft_phase1_tab(sig, (2 * g) * kHopP, (2 * g + 1) * kHopP, wtab, twT, g, r, xbuf);
+        __syncthreads();  // sig is free again, the transpose is complete
+        float2 v[20];
+        stft_phase2_load(xbuf, g, r, v);
+        stft_publish_upper(v, g, r, zup);
+        __syncthreads();  // upper halves are visible; xbuf may be overwritten by the next tile's phase 1
 
         const int b = (int)(tile / tiles_per_item);
         const int ti = (int)(tile - (long)b * tiles_per_item);
         const int tA = ti * Cfg::kTileFrames + 2 * g;
         float* rowA = out + ((size_t)b * T + tA) * (kBins * 2);
-        stft_phase3(zbuf, g, r, tA < T ? rowA : nullptr, tA + 1 < T ? rowA + kBins * 2 : nullptr);
-        cur ^= 1;
-        // No barrier here: the next iteration's first __syncthreads already orders this iteration's reads of
-        // zbuf (phase 3), xchg (phase 2) and sig (phase 1) against their next writes.
+        if (tA + 1 < T)
+            stft_split_store<true, true>(v, zup, g, r, rowA, rowA + kBins * 2);
+        else if (tA < T)
+            stft_split_store<true, false>(v, zup, g, r, rowA, nullptr);
+        __syncthreads();  // zup (which aliases sig) is consumed: the next tile's samples may land
+        const long next = tile + gridDim.x;
+        fetched = next < total_tiles && interior(next);
+        if (fetched && threadIdx.x == 0) issue_bulk(next);
     }
-    cp_async_wait<0>();
 }
 
 static void make_window(int kind, const float* custom, std::vector<float>& w) {
@@ -176,14 +245,14 @@ static int ensure_tables(sd_ctx* ctx, const sd_stft_params* p) {
     return SD_OK;
 }
 
-template <int GROUPS>
+template <int GROUPS, int MINB>
 static int launch_cfg(sd_ctx* ctx, const float* d_wav, int B, int L, int T, float* d_out) {
     using Cfg = StftCfg<GROUPS>;
     static int blocks_per_sm = 0;
     if (!blocks_per_sm) {
-        SD_CUDA(ctx, cudaFuncSetAttribute(stft400_kernel<GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        SD_CUDA(ctx, cudaFuncSetAttribute(stft400_kernel<GROUPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)Cfg::kSmemBytes));
-        SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, stft400_kernel<GROUPS>,
+        SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, stft400_kernel<GROUPS, MINB>,
                                                                    Cfg::kThreads, Cfg::kSmemBytes));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
@@ -192,7 +261,7 @@ static int launch_cfg(sd_ctx* ctx, const float* d_wav, int B, int L, int T, floa
     long grid = (long)ctx->num_sms * blocks_per_sm;
     if (grid > total) grid = total;
     const int aligned = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_wav) & 15) == 0);
-    stft400_kernel<GROUPS><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream>>>(
+    stft400_kernel<GROUPS, MINB><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream>>>(
         d_wav, d_out, L, T, tiles_per_item, total, ctx->d_window, reinterpret_cast<const float2*>(ctx->d_twiddle),
         aligned);
     SD_LAUNCH_CHECK(ctx);
@@ -209,7 +278,7 @@ int stft_launch(sd_ctx* ctx, const float* d_wav, int B, int L, const sd_stft_par
     int rc = ensure_tables(ctx, p);
     if (rc) return rc;
     const int T = 1 + L / kHop;
-    rc = launch_cfg<8>(ctx, d_wav, B, L, T, d_out);
+    rc = ctx->stft_variant == 1 ? launch_cfg<8, 3>(ctx, d_wav, B, L, T, d_out) : launch_cfg<8, 4>(ctx, d_wav, B, L, T, d_out);
     if (rc) return rc;
     if (p->pad_batch_to > B) {  // _infer: rows beyond the real batch are zeros (speakerDiarizer.cpp:1904)
         size_t row = (size_t)T * kBins * 2 * sizeof(float);

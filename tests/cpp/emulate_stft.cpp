@@ -26,6 +26,7 @@ int main() {
             ts[t].tw[k1] = make_float2((float)cos(a), (float)sin(a));
         }
     }
+    // variant A: per-thread window / twiddle registers, unpadded samples, two exchange buffers
     for (int t = 0; t < nthreads; ++t) {
         int g = t / kRadix, r = t % kRadix;
         stft_phase1(sig.data(), (2 * g) * kHop, (2 * g + 1) * kHop, ts[t].win, ts[t].tw, g, r, xchg.data());
@@ -35,6 +36,43 @@ int main() {
         int g = t / kRadix;
         stft_phase3(zbuf.data(), g, t % kRadix, &out[(2 * g) * kBins * 2], &out[(2 * g + 1) * kBins * 2]);
     }
+    // variant B (the kernel's): padded staging, shared window / twiddle tables, one exchange buffer
+    std::vector<float> sigp(nsig + kPad * (nsig / kHop + 1) + 8, 0.f), out2(frames * kBins * 2, 0.f), wtab(w);
+    for (auto& v : wtab) v *= 0.5f;  // the kernel folds the 1/2 of the real-pair split into the window
+    for (int j = 0; j < nsig; ++j) sigp[j + kPad * (j / kHop)] = sig[j];
+    std::vector<float2> twT(kNfft), xb(groups * kGroupStride);
+    for (int k1 = 0; k1 < 20; ++k1)
+        for (int r = 0; r < 20; ++r) {
+            double a = -2.0 * M_PI * (double)(r * k1) / kNfft;
+            twT[k1 * 20 + r] = make_float2((float)cos(a), (float)sin(a));
+        }
+    std::vector<std::vector<float2>> regs(nthreads, std::vector<float2>(20));
+    for (int t = 0; t < nthreads; ++t) {
+        int g = t / kRadix, r = t % kRadix;
+        stft_phase1_tab(sigp.data(), (2 * g) * kHopP, (2 * g + 1) * kHopP, wtab.data(), twT.data(), g, r, xb.data());
+    }
+    for (int t = 0; t < nthreads; ++t) {
+        float2 v[20];
+        stft_phase2_load(xb.data(), t / kRadix, t % kRadix, v);
+        for (int i = 0; i < 20; ++i) regs[t][i] = v[i];
+    }
+    std::vector<float2> zup(groups * kZStride);
+    for (int t = 0; t < nthreads; ++t) {  // compact second exchange: only Z[200..400] crosses threads
+        float2 v[20];
+        for (int i = 0; i < 20; ++i) v[i] = regs[t][i];
+        stft_publish_upper(v, t / kRadix, t % kRadix, zup.data());
+    }
+    for (int t = 0; t < nthreads; ++t) {
+        int g = t / kRadix;
+        float2 v[20];
+        for (int i = 0; i < 20; ++i) v[i] = regs[t][i];
+        stft_split_store<true, true>(v, zup.data(), g, t % kRadix, &out2[(2 * g) * kBins * 2], &out2[(2 * g + 1) * kBins * 2]);
+    }
+    for (size_t i = 0; i < out.size(); ++i)
+        if (out[i] != out2[i] && !(out[i] == 0.f && out2[i] == 0.f)) {
+            printf("variant mismatch at %zu\n", i);
+            return 2;
+        }
     double maxerr = 0, maxabs = 0;
     for (int f = 0; f < frames; ++f)
         for (int k = 0; k < kBins; ++k) {
