@@ -122,8 +122,29 @@ constexpr int kPad = 12;
 constexpr int kHopP = kHop + kPad;
 SD_HD constexpr int sig_pad(int n1) { return kPad * ((20 * n1) / kHop); }
 
-// phase 1 with the window (wtab[20*n1 + r]) and the twiddles (twT[k1*20 + r]) in shared tables
-SD_HD void stft_phase1_tab(const float* sig, int fa_off, int fb_off, const float* wtab, const float2* twT, int g, int r,
+// Twiddle table layout.  A row of 20 float2 does not fit the 16 eight-byte banks: in a half-warp that holds
+// lanes r = a..19 of one group and r' = 0..a-5 of the next, roles 16..19 would alias roles 0..3.  So roles 0..15
+// read T0[k1*16 + r] and roles 16..19 read one of four copies T1[k1*16 + 4c + (r-16)], c = (a-4)/4, placed on
+// exactly the four banks their half-warp leaves free.  kTwRow = 16 for both, so each thread just keeps a base
+// pointer and indexes it with k1 * kTwRow.
+constexpr int kTwRow = 16;
+constexpr int kTwTableUnits = 2 * 20 * kTwRow;  // T0 then T1
+SD_HD int tw_thread_offset(int tid) {  // float2 units from the start of the table for thread `tid` of the CTA
+    const int g = tid / kRadix, r = tid - g * kRadix;
+    if (r < 16) return r;
+    const int a = 16 * (tid >> 4) - 20 * g;  // first role of this group inside the thread's half-warp (4, 8, 12, 16)
+    return 20 * kTwRow + (a - 4) + (r - 16);
+}
+// fills the table from tw[r*20 + k1] = exp(-2 pi i r k1 / 400); entry index e in [0, kTwTableUnits)
+SD_HD int tw_table_source(int e) {  // returns r*20 + k1 of the value stored at table entry e
+    const int half = e / (20 * kTwRow), rem = e - half * 20 * kTwRow;
+    const int k1 = rem / kTwRow, c = rem - k1 * kTwRow;
+    const int r = half == 0 ? c : 16 + (c & 3);
+    return r * 20 + k1;
+}
+
+// phase 1 with the window (wtab[20*n1 + r]) in a shared table and the twiddles behind a per-thread base pointer
+SD_HD void stft_phase1_tab(const float* sig, int fa_off, int fb_off, const float* wtab, const float2* twp, int g, int r,
                            float2* xchg) {
     float2 v[20];
 #pragma unroll
@@ -137,7 +158,7 @@ SD_HD void stft_phase1_tab(const float* sig, int fa_off, int fb_off, const float
 #pragma unroll
     for (int k1 = 0; k1 < 20; ++k1) {
         float2 y = v[dft20_slot(k1)];
-        if (k1 > 0) y = cmul(y, twT[k1 * 20 + r]);
+        if (k1 > 0) y = cmul(y, twp[k1 * kTwRow]);
         dst[k1 * kXchgRow] = y;
     }
 }

@@ -29,7 +29,7 @@ struct StftCfg {
     // the upper-spectrum buffer shares storage with the staged samples (dead after phase 1)
     static constexpr size_t kSmemBytes = (kSigBytes > kZBytes ? kSigBytes : kZBytes) +
                                          (size_t)GROUPS * kGroupStride * sizeof(float2) + kNfft * sizeof(float) +
-                                         kNfft * sizeof(float2);
+                                         kTwTableUnits * sizeof(float2);
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -121,19 +121,18 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     using Cfg = StftCfg<GROUPS>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xbuf = reinterpret_cast<float2*>(smem_raw);                 // phase 1 -> phase 2 transpose
-    float2* twT = xbuf + GROUPS * kGroupStride;                         // twT[k1*20 + r]
-    float* wtab = reinterpret_cast<float*>(twT + kNfft);                // window, pre-scaled by 1/2
+    float2* twT = xbuf + GROUPS * kGroupStride;                         // twiddle table (see tw_thread_offset)
+    float* wtab = reinterpret_cast<float*>(twT + kTwTableUnits);        // window, pre-scaled by 1/2
     float* sig = wtab + kNfft;                                          // padded samples of the tile
     float2* zup = reinterpret_cast<float2*>(sig);                       // upper half of the spectrum (aliases sig)
     __shared__ __align__(8) uint64_t bar;
 
     const int g = threadIdx.x / kRadix;
     const int r = threadIdx.x - g * kRadix;
-    for (int i = threadIdx.x; i < kNfft; i += Cfg::kThreads) {
+    for (int i = threadIdx.x; i < kNfft; i += Cfg::kThreads)
         wtab[i] = 0.5f * window[i];  // exact scaling; lets phase 3 drop its multiplications
-        const int k1 = i / 20, rr = i - k1 * 20;
-        twT[i] = twiddle[rr * 20 + k1];
-    }
+    for (int e = threadIdx.x; e < kTwTableUnits; e += Cfg::kThreads) twT[e] = twiddle[tw_table_source(e)];
+    const float2* twp = twT + tw_thread_offset(threadIdx.x);
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
@@ -178,7 +177,7 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
             cp_async_wait<0>();
             __syncthreads();
         }
-        stft_phase1_tab(sig, (2 * g) * kHopP, (2 * g + 1) * kHopP, wtab, twT, g, r, xbuf);
+        stft_phase1_tab(sig, (2 * g) * kHopP, (2 * g + 1) * kHopP, wtab, twp, g, r, xbuf);
         __syncthreads();  // sig is free again, the transpose is complete
         float2 v[20];
         stft_phase2_load(xbuf, g, r, v);

@@ -40,16 +40,26 @@ int main() {
     std::vector<float> sigp(nsig + kPad * (nsig / kHop + 1) + 8, 0.f), out2(frames * kBins * 2, 0.f), wtab(w);
     for (auto& v : wtab) v *= 0.5f;  // the kernel folds the 1/2 of the real-pair split into the window
     for (int j = 0; j < nsig; ++j) sigp[j + kPad * (j / kHop)] = sig[j];
-    std::vector<float2> twT(kNfft), xb(groups * kGroupStride);
-    for (int k1 = 0; k1 < 20; ++k1)
-        for (int r = 0; r < 20; ++r) {
-            double a = -2.0 * M_PI * (double)(r * k1) / kNfft;
-            twT[k1 * 20 + r] = make_float2((float)cos(a), (float)sin(a));
+    std::vector<float2> twT(kTwTableUnits), xb(groups * kGroupStride);
+    for (int e = 0; e < kTwTableUnits; ++e) {
+        const int src = tw_table_source(e), r = src / 20, k1 = src % 20;
+        double a = -2.0 * M_PI * (double)(r * k1) / kNfft;
+        twT[e] = make_float2((float)cos(a), (float)sin(a));
+    }
+    // bank check of the twiddle layout: every half-warp must hit 16 distinct 8-byte banks (or equal addresses)
+    for (int h = 0; h < nthreads / 16; ++h) {
+        int owner[16];
+        for (int b = 0; b < 16; ++b) owner[b] = -1;
+        for (int t = 16 * h; t < 16 * h + 16; ++t) {
+            const int u = tw_thread_offset(t), bank = u % 16;
+            if (owner[bank] != -1 && owner[bank] != u) { printf("twiddle bank conflict in half-warp %d\n", h); return 3; }
+            owner[bank] = u;
         }
+    }
     std::vector<std::vector<float2>> regs(nthreads, std::vector<float2>(20));
     for (int t = 0; t < nthreads; ++t) {
         int g = t / kRadix, r = t % kRadix;
-        stft_phase1_tab(sigp.data(), (2 * g) * kHopP, (2 * g + 1) * kHopP, wtab.data(), twT.data(), g, r, xb.data());
+        stft_phase1_tab(sigp.data(), (2 * g) * kHopP, (2 * g + 1) * kHopP, wtab.data(), twT.data() + tw_thread_offset(t), g, r, xb.data());
     }
     for (int t = 0; t < nthreads; ++t) {
         float2 v[20];
