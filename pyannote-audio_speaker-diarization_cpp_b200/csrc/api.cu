@@ -53,8 +53,18 @@ using namespace sdb;
 
 struct CtxExtra {
     Ring ring;
+    // copy streams / events of the pipelined host-pointer STFT
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {};
+    bool pipe_ready = false;
 };
 static std::vector<std::pair<sd_ctx*, CtxExtra*>> g_extras;  // contexts are few; linear search is fine
+
+static CtxExtra* extra_of(sd_ctx* ctx) {
+    for (auto& e : g_extras)
+        if (e.first == ctx) return e.second;
+    return nullptr;
+}
 
 namespace sdb {
 static Ring* ring_of(sd_ctx* ctx) {
@@ -133,6 +143,15 @@ void sd_ctx_destroy(sd_ctx* ctx) {
             if (ex->ring.base) {
                 for (int k = 0; k < kRingSlots; ++k) cudaEventDestroy(ex->ring.ev[k]);
                 cudaFreeHost(ex->ring.base);
+            }
+            if (ex->pipe_ready) {
+                for (int k = 0; k < 2; ++k) {
+                    cudaEventDestroy(ex->ev_in[k]);
+                    cudaEventDestroy(ex->ev_comp[k]);
+                    cudaEventDestroy(ex->ev_out[k]);
+                }
+                cudaStreamDestroy(ex->s_in);
+                cudaStreamDestroy(ex->s_out);
             }
             delete ex;
             g_extras.erase(g_extras.begin() + i);
@@ -276,21 +295,61 @@ int sd_stft_dev(sd_ctx* ctx, const float* d_wav, int B, int L, const sd_stft_par
     return stft_launch(ctx, d_wav, B, L, p, d_out);
 }
 
+// Host-pointer STFT.  The batch is cut into chunks that flow through a three-stage pipeline -- H2D of chunk
+// i+1, the kernel on chunk i and D2H of chunk i-1 run concurrently on three streams with double-buffered device
+// chunks -- so a PCIe-bound call costs about max(H2D, D2H) instead of their sum.  (Pinned host buffers are needed
+// for the copies to be truly asynchronous; pageable ones still work, just serialised by the driver.)
 int sd_stft(sd_ctx* ctx, const float* wav, int B, int L, const sd_stft_params* p, float* out) {
     if (!ctx) return SD_ERR_INVALID;
     SD_REQUIRE(ctx, wav && out && p, "sd_stft: null pointer");
     SD_REQUIRE(ctx, B > 0 && L > 0, "sd_stft: B and L must be positive");
     const int64_t T = sd_stft_num_frames(L, p->hop);
-    const int rows = std::max(B, p->pad_batch_to);
-    const size_t in_bytes = sizeof(float) * (size_t)B * L;
-    const size_t out_bytes = sizeof(float) * (size_t)rows * T * (p->n_fft / 2 + 1) * 2;
-    float* d_in = (float*)ctx->scratch(BUF_STFT_IN, in_bytes);
-    float* d_out = (float*)ctx->scratch(BUF_STFT_OUT, out_bytes);
+    const size_t in_item = sizeof(float) * (size_t)L;
+    const size_t out_item = sizeof(float) * (size_t)T * (p->n_fft / 2 + 1) * 2;
+    CtxExtra* ex = extra_of(ctx);
+    if (!ex) return ctx->fail(SD_ERR_INVALID, "sd_stft: unknown context");
+    if (!ex->pipe_ready) {
+        SD_CUDA(ctx, cudaStreamCreateWithFlags(&ex->s_in, cudaStreamNonBlocking));
+        SD_CUDA(ctx, cudaStreamCreateWithFlags(&ex->s_out, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            SD_CUDA(ctx, cudaEventCreateWithFlags(&ex->ev_in[k], cudaEventDisableTiming));
+            SD_CUDA(ctx, cudaEventCreateWithFlags(&ex->ev_comp[k], cudaEventDisableTiming));
+            SD_CUDA(ctx, cudaEventCreateWithFlags(&ex->ev_out[k], cudaEventDisableTiming));
+        }
+        ex->pipe_ready = true;
+    }
+    // ~192 MB of output per chunk keeps every copy long enough to run at full PCIe rate
+    int chunk = (int)std::max<size_t>(1, ((size_t)192 << 20) / out_item);
+    if (chunk > B) chunk = B;
+    float* d_in = (float*)ctx->scratch(BUF_STFT_IN, 2 * in_item * chunk);
+    float* d_out = (float*)ctx->scratch(BUF_STFT_OUT, 2 * out_item * chunk);
     if (!d_in || !d_out) return SD_ERR_NOMEM;
-    SD_CUDA(ctx, cudaMemcpyAsync(d_in, wav, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = stft_launch(ctx, d_in, B, L, p, d_out);
-    if (rc) return rc;
-    SD_CUDA(ctx, cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    sd_stft_params q = *p;
+    q.pad_batch_to = 0;
+    // work queued on the context stream before this call must finish before the buffers are reused
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int idx = 0;
+    for (int b0 = 0; b0 < B; b0 += chunk, ++idx) {
+        const int nb = std::min(chunk, B - b0);
+        const int slot = idx & 1;
+        float* din = d_in + (size_t)slot * chunk * L;
+        float* dout = d_out + (size_t)slot * chunk * (out_item / sizeof(float));
+        if (idx >= 2) SD_CUDA(ctx, cudaStreamWaitEvent(ex->s_in, ex->ev_comp[slot], 0));  // input slot consumed
+        SD_CUDA(ctx, cudaMemcpyAsync(din, wav + (size_t)b0 * L, in_item * nb, cudaMemcpyHostToDevice, ex->s_in));
+        SD_CUDA(ctx, cudaEventRecord(ex->ev_in[slot], ex->s_in));
+        SD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ex->ev_in[slot], 0));
+        if (idx >= 2) SD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ex->ev_out[slot], 0));  // output slot drained
+        int rc = stft_launch(ctx, din, nb, L, &q, dout);
+        if (rc) return rc;
+        SD_CUDA(ctx, cudaEventRecord(ex->ev_comp[slot], ctx->stream));
+        SD_CUDA(ctx, cudaStreamWaitEvent(ex->s_out, ex->ev_comp[slot], 0));
+        SD_CUDA(ctx, cudaMemcpyAsync(out + (size_t)b0 * (out_item / sizeof(float)), dout, out_item * nb,
+                                     cudaMemcpyDeviceToHost, ex->s_out));
+        SD_CUDA(ctx, cudaEventRecord(ex->ev_out[slot], ex->s_out));
+    }
+    if (p->pad_batch_to > B)  // _infer: rows beyond the real batch are zeros (speakerDiarizer.cpp:1904)
+        std::memset(out + (size_t)B * (out_item / sizeof(float)), 0, out_item * (size_t)(p->pad_batch_to - B));
+    SD_CUDA(ctx, cudaStreamSynchronize(ex->s_out));
     SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SD_OK;
 }
