@@ -13,7 +13,9 @@
 #include "common.cuh"
 #include "fft400.cuh"
 
+#include <algorithm>
 #include <cmath>
+#include <cstring>
 
 namespace sdb {
 
@@ -199,6 +201,234 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Fused log-mel front-end: same tile pipeline as stft400_kernel, but the one-sided spectra never
+// leave the SM.  Epilogue per tile: |X|^2 -> shared memory, triangular mel projection (each bin feeds at most
+// two filters, so the matrix is kept as per-filter bin ranges), 10 log10(max(., amin)), coalesced [T][n_mels]
+// stores, and the utterance maximum (needed by the top_db clamp) through one atomicMax per warp.
+// Spec: embeddings/threeModel.py:212-221 (spectral_magnitude -> Filterbank(n_mels=80) -> MyNormalization);
+// parity unpinned (speechbrain 0.5.14 is not vendored) -- checked against oracle/sd_oracle.c only.
+struct MelTable {       // device copy lives in ctx->d_mel
+    int lo[128];        // first bin of filter m
+    int cnt[128];       // number of bins with non-zero weight
+    int off[128];       // offset of its weights in w[]
+    float w[1024];      // packed non-zero weights
+};
+
+__device__ __forceinline__ int float_order_key(float v) {  // monotone float -> int map for atomicMax
+    const int i = __float_as_int(v);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__host__ __device__ __forceinline__ float float_from_order_key(int k) {
+    const int i = k >= 0 ? k : k ^ 0x7fffffff;
+#if defined(__CUDA_ARCH__)
+    return __int_as_float(i);
+#else
+    float f;
+    memcpy(&f, &i, 4);
+    return f;
+#endif
+}
+
+template <int GROUPS, int MINB>
+__global__ void __launch_bounds__(GROUPS* kRadix, MINB)
+    fbank400_kernel(const float* __restrict__ wav, float* __restrict__ out, int L, int T, int tiles_per_item,
+                    long total_tiles, const float* __restrict__ window, const float2* __restrict__ twiddle,
+                    int aligned16, const MelTable* __restrict__ mel, int n_mels, float amin, int* __restrict__ item_max) {
+    using Cfg = StftCfg<GROUPS>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* xbuf = reinterpret_cast<float2*>(smem_raw);
+    float2* twT = xbuf + GROUPS * kGroupStride;
+    float* wtab = reinterpret_cast<float*>(twT + kTwTableUnits);
+    float* sig = wtab + kNfft;
+    float2* zup = reinterpret_cast<float2*>(sig);
+    float* pw = reinterpret_cast<float*>(xbuf);  // power spectra [frame][201], aliases the transpose buffer
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ MelTable smel;
+
+    const int g = threadIdx.x / kRadix;
+    const int r = threadIdx.x - g * kRadix;
+    for (int i = threadIdx.x; i < kNfft; i += Cfg::kThreads) wtab[i] = 0.5f * window[i];
+    for (int e = threadIdx.x; e < kTwTableUnits; e += Cfg::kThreads) twT[e] = twiddle[tw_table_source(e)];
+    for (int i = threadIdx.x; i < (int)(sizeof(MelTable) / 4); i += Cfg::kThreads)
+        reinterpret_cast<int*>(&smel)[i] = reinterpret_cast<const int*>(mel)[i];
+    const float2* twp = twT + tw_thread_offset(threadIdx.x);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+    }
+    __syncthreads();
+
+    auto interior = [&](long tile) -> bool {
+        const int ti = (int)(tile % tiles_per_item);
+        const long s0 = (long)ti * Cfg::kTileFrames * kHop - kNfft / 2;
+        return aligned16 && s0 >= 0 && s0 + Cfg::kSigFloats <= L;
+    };
+    auto issue_bulk = [&](long tile) {
+        const int b = (int)(tile / tiles_per_item);
+        const int ti = (int)(tile - (long)b * tiles_per_item);
+        const long s0 = (long)ti * Cfg::kTileFrames * kHop - kNfft / 2;
+        const float* src = wav + (size_t)b * L + s0;
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        mbar_expect_tx(&bar, Cfg::kSigFloats * sizeof(float));
+#pragma unroll 1
+        for (int j = 0; j < Cfg::kSigFloats; j += kHop) {
+            const int n = (Cfg::kSigFloats - j) < kHop ? (Cfg::kSigFloats - j) : kHop;
+            bulk_g2s(sig + j + kPad * (j / kHop), src + j, n * sizeof(float), &bar);
+        }
+    };
+
+    unsigned parity = 0;
+    long tile = blockIdx.x;
+    bool fetched = false;
+    if (tile < total_tiles && interior(tile)) {
+        if (threadIdx.x == 0) issue_bulk(tile);
+        fetched = true;
+    }
+    for (; tile < total_tiles; tile += gridDim.x) {
+        if (fetched) {
+            mbar_wait(&bar, parity);
+            parity ^= 1;
+        } else {
+            stage_tile<GROUPS>(sig, wav, L, tile, tiles_per_item, aligned16 != 0);
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads();
+        }
+        stft_phase1_tab(sig, (2 * g) * kHopP, (2 * g + 1) * kHopP, wtab, twp, g, r, xbuf);
+        __syncthreads();
+        float2 v[20];
+        stft_phase2_load(xbuf, g, r, v);
+        stft_publish_upper(v, g, r, zup);
+        __syncthreads();  // xbuf is dead from here: it receives the power spectra
+
+        // |X|^2 of both frames of the pair into pw[frame][bin]
+        {
+            float* pa = pw + (2 * g) * kBins;
+            float* pb = pa + kBins;
+            const float2* zm = zup + g * kZStride + 200 - r;
+#pragma unroll
+            for (int m = 0; m < 10; ++m) {
+                const float2 a = v[dft20_slot(m)];
+                const float2 c = zm[-20 * m];
+                const float ar = a.x + c.x, ai = a.y - c.y, br = a.y + c.y, bi = c.x - a.x;
+                pa[r + 20 * m] = ar * ar + ai * ai;
+                pb[r + 20 * m] = br * br + bi * bi;
+            }
+            if (r == 0) {
+                const float2 a = v[dft20_slot(10)];
+                pa[200] = 4.f * a.x * a.x;
+                pb[200] = 4.f * a.y * a.y;
+            }
+        }
+        __syncthreads();  // power spectra complete; zup (aliasing sig) is consumed
+        const long next = tile + gridDim.x;
+        fetched = next < total_tiles && interior(next);
+        if (fetched && threadIdx.x == 0) issue_bulk(next);
+
+        // mel projection + dB.  Thread -> one mel filter (fastest index, so stores are coalesced) and one half of the
+        // tile's frames: the filter's weights are read once and reused for every frame.
+        const int b = (int)(tile / tiles_per_item);
+        const int ti = (int)(tile - (long)b * tiles_per_item);
+        const int t0 = ti * Cfg::kTileFrames;
+        float vmax = -INFINITY;
+        constexpr int kFramesPerPass = Cfg::kThreads / 80 > 0 ? Cfg::kThreads / 80 : 1;  // frame slots per pass
+        for (int m0 = 0; m0 < n_mels; m0 += 80) {
+            const int m = m0 + (int)(threadIdx.x % 80), slot = threadIdx.x / 80;
+            if (m < n_mels && slot < kFramesPerPass) {
+                const int lo = smel.lo[m], cnt = smel.cnt[m];
+                const float* wq = smel.w + smel.off[m];
+                float acc[Cfg::kTileFrames / kFramesPerPass];
+#pragma unroll
+                for (int j = 0; j < Cfg::kTileFrames / kFramesPerPass; ++j) acc[j] = 0.f;
+                for (int i = 0; i < cnt; ++i) {
+                    const float wv = wq[i];
+                    const float* p = pw + lo + i;
+#pragma unroll
+                    for (int j = 0; j < Cfg::kTileFrames / kFramesPerPass; ++j)
+                        acc[j] = fmaf(p[(slot + j * kFramesPerPass) * kBins], wv, acc[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < Cfg::kTileFrames / kFramesPerPass; ++j) {
+                    const int f = slot + j * kFramesPerPass;
+                    if (t0 + f < T) {
+                        // 10 log10(x) = (10 / log2(10)) log2(x); MUFU.LG2 is accurate to ~1e-6 dB here
+                        const float db = 3.01029995663981195f * __log2f(fmaxf(acc[j], amin));
+                        out[((size_t)b * T + t0 + f) * n_mels + m] = db;
+                        vmax = fmaxf(vmax, db);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        if ((threadIdx.x & 31) == 0 && vmax > -INFINITY) atomicMax(item_max + b, float_order_key(vmax));
+        __syncthreads();  // pw consumed before the next tile's phase 1 writes xbuf
+    }
+}
+
+// top_db clamp and sentence-level mean normalisation (MyNormalization, threeModel.py:333-369): one CTA per item,
+// thread -> (mel, frame slot) so that every access is coalesced and column sums need no atomics.
+// Sweep 1 accumulates the clamped column sums of the first round(len * T) frames; sweep 2 re-reads the block (an L2
+// hit: it is <= 320 KB and was just touched), clamps, subtracts the mean and writes in place -- one DRAM read and one
+// DRAM write per element.
+constexpr int FN_THREADS = 960;
+__global__ void __launch_bounds__(FN_THREADS)
+    fbank_norm_kernel(float* __restrict__ feats, int T, int n_mels, const int* __restrict__ item_max,
+                      const float* __restrict__ wav_lens, float top_db, int mean_norm) {
+    extern __shared__ double colsum[];  // [slots][n_mels] partial sums, then [n_mels] means
+    const int b = blockIdx.x;
+    float* x = feats + (size_t)b * T * n_mels;
+    const float floor_db = float_from_order_key(item_max[b]) - top_db;
+    long n = lrintf(wav_lens[b] * (float)T);  // torch.round: half to even
+    if (n > T) n = T;
+    const int slots = FN_THREADS / n_mels;  // frames handled per pass
+    const int m = threadIdx.x % n_mels, slot = threadIdx.x / n_mels;
+    const bool active = slot < slots;
+    if (mean_norm) {
+        double acc = 0.0;
+        if (active) {
+            int f = slot;
+            for (; f + 7 * slots < n; f += 8 * slots) {  // eight independent loads in flight
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = x[(size_t)(f + u * slots) * n_mels + m];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc += (double)fmaxf(v[u], floor_db);
+            }
+            for (; f < n; f += slots) acc += (double)fmaxf(x[(size_t)f * n_mels + m], floor_db);
+            colsum[slot * n_mels + m] = acc;
+        }
+        __syncthreads();
+        if (threadIdx.x < n_mels) {
+            double s2 = 0.0;
+            for (int q = 0; q < slots; ++q) s2 += colsum[q * n_mels + threadIdx.x];
+            colsum[threadIdx.x] = n > 0 ? s2 / (double)n : (double)NAN;
+        }
+        __syncthreads();
+    }
+    if (active) {
+        const float mean = mean_norm ? (float)colsum[m] : 0.f;
+        int f = slot;
+        for (; f + 7 * slots < T; f += 8 * slots) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = x[(size_t)(f + u * slots) * n_mels + m];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[(size_t)(f + u * slots) * n_mels + m] = fmaxf(v[u], floor_db) - mean;
+        }
+        for (; f < T; f += slots) {
+            const size_t e = (size_t)f * n_mels + m;
+            x[e] = fmaxf(x[e], floor_db) - mean;
+        }
+    }
+}
+
+__global__ void fill_int_kernel2(int* p, int n, int v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 static void make_window(int kind, const float* custom, std::vector<float>& w) {
     w.resize(kNfft);
     if (kind == SD_WINDOW_CUSTOM) {
@@ -284,6 +514,94 @@ int stft_launch(sd_ctx* ctx, const float* d_wav, int B, int L, const sd_stft_par
         SD_CUDA(ctx, cudaMemsetAsync(reinterpret_cast<char*>(d_out) + (size_t)B * row, 0,
                                      (size_t)(p->pad_batch_to - B) * row, ctx->stream));
     }
+    return SD_OK;
+}
+
+// speechbrain 0.5.14 Filterbank (triangular, fp32 arithmetic like the torch module): mel points
+// linspace(mel(f_min), mel(f_max), n_mels + 2); centre = hz[1..n_mels]; band = hz[m+1] - hz[m] for both slopes.
+static int build_mel_table(const sd_fbank_params* p, MelTable& t) {
+    const int n_bins = kBins, n_mels = p->n_mels, np = n_mels + 2;
+    if (n_mels < 1 || n_mels > 128) return SD_ERR_UNSUPPORTED;
+    std::vector<float> hz(np);
+    const float mlo = (float)(2595.0 * std::log10(1.0 + (double)p->f_min / 700.0));
+    const float mhi = (float)(2595.0 * std::log10(1.0 + (double)p->f_max / 700.0));
+    for (int i = 0; i < np; ++i) {
+        const float mel = mlo + (mhi - mlo) * (float)i / (float)(np - 1);
+        hz[i] = 700.0f * (std::pow(10.0f, mel / 2595.0f) - 1.0f);
+    }
+    int used = 0;
+    for (int m = 0; m < n_mels; ++m) {
+        const float fc = hz[m + 1], band = hz[m + 1] - hz[m];
+        int lo = -1, hi = -1;
+        std::vector<float> wts(n_bins);
+        for (int f = 0; f < n_bins; ++f) {
+            const float freq = (float)(p->sample_rate / 2) * (float)f / (float)(n_bins - 1);
+            const float slope = (freq - fc) / band;
+            const float l = slope + 1.0f, r = -slope + 1.0f;
+            const float v = std::max(0.0f, std::min(l, r));
+            wts[f] = v;
+            if (v > 0.0f) {
+                if (lo < 0) lo = f;
+                hi = f;
+            }
+        }
+        t.lo[m] = lo < 0 ? 0 : lo;
+        t.cnt[m] = lo < 0 ? 0 : hi - lo + 1;
+        t.off[m] = used;
+        if (used + t.cnt[m] > 1024) return SD_ERR_UNSUPPORTED;
+        for (int i = 0; i < t.cnt[m]; ++i) t.w[used + i] = wts[t.lo[m] + i];
+        used += t.cnt[m];
+    }
+    return SD_OK;
+}
+
+int fbank_launch(sd_ctx* ctx, const float* d_wav, int B, int L, const float* d_lens, const sd_fbank_params* p,
+                 float* d_out) {
+    const sd_stft_params* sp = &p->stft;
+    if (sp->n_fft != kNfft || sp->hop != kHop)
+        return ctx->fail(SD_ERR_UNSUPPORTED, "sd_fbank: only n_fft=400 / hop=160 has a kernel");
+    if (sp->preemph != 0.f) return ctx->fail(SD_ERR_UNSUPPORTED, "sd_fbank: pre-emphasis is not implemented yet");
+    int rc = ensure_tables(ctx, sp);
+    if (rc) return rc;
+    const int key = p->n_mels * 1000003 + (int)p->f_min * 7919 + (int)p->f_max + p->sample_rate * 31;
+    if (!ctx->d_mel || ctx->mel_key != key) {
+        MelTable t;
+        std::memset(&t, 0, sizeof(t));
+        rc = build_mel_table(p, t);
+        if (rc) return ctx->fail(rc, "sd_fbank: unsupported mel configuration (n_mels=%d)", p->n_mels);
+        if (!ctx->d_mel) SD_CUDA(ctx, cudaMalloc(&ctx->d_mel, sizeof(MelTable)));
+        SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        SD_CUDA(ctx, cudaMemcpy(ctx->d_mel, &t, sizeof(MelTable), cudaMemcpyHostToDevice));
+        ctx->mel_key = key;
+    }
+    const int T = 1 + L / kHop;
+    int* d_max = (int*)ctx->scratch(BUF_FB_TMP, sizeof(int) * (size_t)B);
+    if (!d_max) return SD_ERR_NOMEM;
+    fill_int_kernel2<<<(B + 255) / 256, 256, 0, ctx->stream>>>(d_max, B, (int)0x80000000);  // below every key
+    SD_LAUNCH_CHECK(ctx);
+    using Cfg = StftCfg<8>;
+    static int blocks_per_sm = 0;
+    if (!blocks_per_sm) {
+        SD_CUDA(ctx, cudaFuncSetAttribute(fbank400_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)Cfg::kSmemBytes));
+        SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fbank400_kernel<8, 3>, Cfg::kThreads,
+                                                                   Cfg::kSmemBytes));
+        if (blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    const int tiles_per_item = (T + Cfg::kTileFrames - 1) / Cfg::kTileFrames;
+    const long total = (long)B * tiles_per_item;
+    long grid = (long)ctx->num_sms * blocks_per_sm;
+    if (grid > total) grid = total;
+    const int aligned = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_wav) & 15) == 0);
+    fbank400_kernel<8, 3><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream>>>(
+        d_wav, d_out, L, T, tiles_per_item, total, ctx->d_window, reinterpret_cast<const float2*>(ctx->d_twiddle),
+        aligned, reinterpret_cast<const MelTable*>(ctx->d_mel), p->n_mels, p->amin, d_max);
+    SD_LAUNCH_CHECK(ctx);
+    const int total_e = T * p->n_mels;
+    const size_t nsm = sizeof(double) * (size_t)FN_THREADS;
+    (void)total_e;
+    fbank_norm_kernel<<<B, FN_THREADS, nsm, ctx->stream>>>(d_out, T, p->n_mels, d_max, d_lens, p->top_db, p->mean_norm);
+    SD_LAUNCH_CHECK(ctx);
     return SD_OK;
 }
 

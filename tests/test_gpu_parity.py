@@ -68,6 +68,40 @@ def test_stft_spot_frames_full_size(ctx, oracle, synth):
         assert np.abs(got[b, t0:t0 + 5] - want).max() < STFT_TOL
 
 
+# ------------------------------------------------------------------ a3 (parity unpinned: oracle restatement only)
+@pytest.mark.parametrize("B,L", [(3, 16000), (5, 80000), (2, 160000)])
+def test_fbank_fused_vs_oracle(ctx, oracle, synth, B, L):
+    """Fused |X|^2 -> mel(80) -> dB -> top_db -> mean-norm against the C restatement of
+    embeddings/threeModel.py:212-221 applied to the oracle's own STFT.  The STFT differs from the fp64 one by a
+    few 1e-6 absolute, so dB values of near-silent mel bins (within ~60 dB of the clamp) carry that noise: the bar is
+    1e-3 dB on bins at least 1e-5 of the utterance peak and 5e-2 dB elsewhere."""
+    wav = synth.fbank_items(B + L, B, L)
+    wav[0, L // 2:] = 0.0
+    lens = np.linspace(1.0, 0.35, B).astype(np.float32)
+    got = ctx.fbank(wav, lens)
+    st = oracle.stft(wav)
+    want = oracle.fbank_tail(st, lens)
+    assert got.shape == want.shape == (B, 1 + L // 160, 80)
+    W = oracle.mel_matrix()
+    mel = (st[..., 0].astype(np.float64) ** 2 + st[..., 1].astype(np.float64) ** 2) @ W.astype(np.float64)
+    strong = mel > 1e-5 * mel.max(axis=(1, 2), keepdims=True)
+    err = np.abs(got - want)
+    assert err[strong].max() < 1e-3
+    assert err.max() < 5e-2
+
+
+def test_fbank_without_mean_norm_and_clamp_floor(ctx, oracle, synth):
+    wav = synth.fbank_items(5, 2, 32000)
+    wav[1, 4000:] = 0.0  # long digital silence -> clamped at (max - 80 dB)
+    p = ctx.fbank_params()
+    p.mean_norm = 0
+    got = ctx.fbank(wav, np.ones(2, np.float32), p)
+    assert np.isfinite(got).all()
+    for b in range(2):
+        assert abs(got[b].min() - (got[b].max() - 80.0)) < 1e-4 or got[b].min() > got[b].max() - 80.0
+    assert abs(got[1].min() - (got[1].max() - 80.0)) < 1e-4
+
+
 # ------------------------------------------------------------------ a4-a7
 def test_segmentation_postprocessing_golden(ctx, golden_dir):
     d = g(golden_dir, "segpost_ref.npz")
