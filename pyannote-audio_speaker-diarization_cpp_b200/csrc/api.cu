@@ -9,8 +9,8 @@
 
 namespace sdb {
 int normalize_launch(sd_ctx* ctx, const double* d_x, int N, int D, double* d_xn);
-int pdist_condensed_launch(sd_ctx* ctx, const double* d_x, int N, int D, double* d_cond);
-int linkage_launch(sd_ctx* ctx, const double* d_x, int N, int D, double* d_Z);
+int pdist_condensed_launch(sd_ctx* ctx, const double* d_x, int N, int D, int mode, double* d_cond);
+int linkage_launch(sd_ctx* ctx, const double* d_x, int N, int D, double* d_Z, int mode);
 int fcluster_launch(sd_ctx* ctx, const double* d_Z, int N, double cutoff, int* d_T, int* d_num);
 int cosine_cdist_launch(sd_ctx* ctx, const double* d_a, int na, const double* d_b, int nb, int D, double* d_out);
 int cluster_labels_launch(sd_ctx* ctx, const double* d_x, int N, int D, const sd_cluster_params* p, int* d_labels,
@@ -644,14 +644,13 @@ int sd_pdist(sd_ctx* ctx, const double* x, int N, int D, int mode, double* conde
     if (!ctx) return SD_ERR_INVALID;
     SD_REQUIRE(ctx, x && condensed, "sd_pdist: null pointer");
     SD_REQUIRE(ctx, N > 1 && D > 0, "sd_pdist: need N > 1, D > 0");
-    if (mode != SD_PDIST_EXACT_F64) return ctx->fail(SD_ERR_UNSUPPORTED, "sd_pdist: mode %d not available", mode);
     const size_t bytes = sizeof(double) * (size_t)N * D;
     const size_t cbytes = sizeof(double) * ((size_t)N * (N - 1) / 2);
     double* d_x = (double*)ctx->scratch(BUF_CL_X, bytes);
     double* d_c = (double*)ctx->scratch(BUF_GENERIC_B, cbytes);
     if (!d_x || !d_c) return SD_ERR_NOMEM;
     SD_CUDA(ctx, cudaMemcpyAsync(d_x, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    int rc = pdist_condensed_launch(ctx, d_x, N, D, d_c);
+    int rc = pdist_condensed_launch(ctx, d_x, N, D, mode, d_c);
     if (rc) return rc;
     SD_CUDA(ctx, cudaMemcpyAsync(condensed, d_c, cbytes, cudaMemcpyDeviceToHost, ctx->stream));
     SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -664,7 +663,7 @@ int sd_linkage_dev(sd_ctx* ctx, const double* d_x, int N, int D, double* d_Z) {
     SD_REQUIRE(ctx, N > 1 && D > 0, "sd_linkage_dev: need N > 1, D > 0");
     int rc = reset_status(ctx);
     if (rc) return rc;
-    return linkage_launch(ctx, d_x, N, D, d_Z);
+    return linkage_launch(ctx, d_x, N, D, d_Z, SD_PDIST_EXACT_F64);
 }
 
 int sd_linkage(sd_ctx* ctx, const double* x, int N, int D, double* Z) {
@@ -709,7 +708,7 @@ int sd_cluster(sd_ctx* ctx, const double* x, int N, int D, double cutoff, int32_
     SD_CUDA(ctx, cudaMemcpyAsync(d_x, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
     int rc = reset_status(ctx);
     if (rc) return rc;
-    rc = linkage_launch(ctx, d_x, N, D, d_Z);
+    rc = linkage_launch(ctx, d_x, N, D, d_Z, SD_PDIST_EXACT_F64);
     if (rc) return rc;
     rc = fcluster_launch(ctx, d_Z, N, cutoff, d_T, d_T + N);
     if (rc) return rc;

@@ -1548,14 +1548,26 @@ static LinkLayout link_layout(int N) {
     return L;
 }
 
-// pdist (exact) into the square matrix of the linkage workspace; returns the workspace base
-static int pdist_square(sd_ctx* ctx, const double* d_xn, int N, int D, char** base_out, LinkLayout* L_out) {
+int pdist_tc_launch(sd_ctx* ctx, const double* d_xn, int N, int D, double* Dm, long ld, double refine_below);
+
+// squared distance below which the tensor-core mode recomputes a pair exactly (d < 0.3)
+constexpr double kTcRefineBelow = 0.09;
+
+// pdist into the square matrix of the linkage workspace; returns the workspace base
+static int pdist_square(sd_ctx* ctx, const double* d_xn, int N, int D, int mode, char** base_out, LinkLayout* L_out) {
     LinkLayout L = link_layout(N);
     char* base = (char*)ctx->scratch(BUF_CL_DIST, L.total);
     if (!base) return SD_ERR_NOMEM;
-    dim3 grid((N + PD_TILE - 1) / PD_TILE, (N + PD_TILE - 1) / PD_TILE);
-    pdist_f64_kernel<<<grid, 256, 0, ctx->stream>>>(d_xn, N, D, reinterpret_cast<double*>(base + L.off_D), L.ld, nullptr);
-    SD_LAUNCH_CHECK(ctx);
+    if (mode == SD_PDIST_GEMM_TF32X3) {
+        int rc = pdist_tc_launch(ctx, d_xn, N, D, reinterpret_cast<double*>(base + L.off_D), L.ld, kTcRefineBelow);
+        if (rc) return rc;
+    } else if (mode == SD_PDIST_EXACT_F64) {
+        dim3 grid((N + PD_TILE - 1) / PD_TILE, (N + PD_TILE - 1) / PD_TILE);
+        pdist_f64_kernel<<<grid, 256, 0, ctx->stream>>>(d_xn, N, D, reinterpret_cast<double*>(base + L.off_D), L.ld,
+                                                        nullptr);
+        SD_LAUNCH_CHECK(ctx);
+    } else
+        return ctx->fail(SD_ERR_UNSUPPORTED, "unknown pdist mode %d", mode);
     *base_out = base;
     *L_out = L;
     return SD_OK;
@@ -1660,10 +1672,10 @@ int normalize_launch(sd_ctx* ctx, const double* d_x, int N, int D, double* d_xn)
     return SD_OK;
 }
 
-int pdist_condensed_launch(sd_ctx* ctx, const double* d_x, int N, int D, double* d_cond) {
+int pdist_condensed_launch(sd_ctx* ctx, const double* d_x, int N, int D, int mode, double* d_cond) {
     char* base;
     LinkLayout L;
-    int rc = pdist_square(ctx, d_x, N, D, &base, &L);
+    int rc = pdist_square(ctx, d_x, N, D, mode, &base, &L);
     if (rc) return rc;
     dim3 grid((N + 255) / 256, N);
     condense_kernel<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<double*>(base + L.off_D), L.ld, N, d_cond);
@@ -1672,11 +1684,11 @@ int pdist_condensed_launch(sd_ctx* ctx, const double* d_x, int N, int D, double*
 }
 
 // Clustering::linkage on device rows d_x[N][D] (already normalised by the caller, as in the reference)
-int linkage_launch(sd_ctx* ctx, const double* d_x, int N, int D, double* d_Z) {
+int linkage_launch(sd_ctx* ctx, const double* d_x, int N, int D, double* d_Z, int mode) {
     if (N < 2) return SD_OK;
     char* base;
     LinkLayout L;
-    int rc = pdist_square(ctx, d_x, N, D, &base, &L);
+    int rc = pdist_square(ctx, d_x, N, D, mode, &base, &L);
     if (rc) return rc;
     return linkage_on_square(ctx, base, L, d_x, N, D, d_Z);
 }
@@ -1738,9 +1750,7 @@ int cluster_labels_launch(sd_ctx* ctx, const double* d_x, int N, int D, const sd
     if (rc) return rc;
     double* d_Z = (double*)ctx->scratch(BUF_CL_Z, sizeof(double) * 4 * (size_t)N);
     if (!d_Z) return SD_ERR_NOMEM;
-    if (p->pdist_mode != SD_PDIST_EXACT_F64)
-        return ctx->fail(SD_ERR_UNSUPPORTED, "pdist_mode %d is not available in this build", p->pdist_mode);
-    rc = linkage_launch(ctx, d_xn, N, D, d_Z);
+    rc = linkage_launch(ctx, d_xn, N, D, d_Z, p->pdist_mode);
     if (rc) return rc;
     rc = fcluster_launch(ctx, d_Z, N, (double)p->threshold, d_labels, d_num);  // float threshold, SD:2049/2323
     if (rc) return rc;

@@ -43,6 +43,7 @@ enum BufTag {
     BUF_FB_LENS,
     BUF_GENERIC_A,
     BUF_GENERIC_B,
+    BUF_TC_OPERANDS,
     BUF_COUNT
 };
 
