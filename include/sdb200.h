@@ -201,6 +201,52 @@ int sd_clustering_dev(sd_ctx* ctx, const double* d_embeddings, int C, int S, int
                       const double* d_binarized, int F, int32_t* d_hard, double* d_soft, int soft_k_cap,
                       int* num_clusters);
 
+/* ---- "next" rows --------------------------------------------------------------------------
+ * f1: pre-embedding masking.
+ * sd_mask_compact      : Helper::interpolate (SD:746) + Helper::padSequence (SD:770) + the wav_lens / too-short logic
+ *                        of getEmbedding (SD:2466-2510) for one batch: wav[B][L], masks[B][F] ->
+ *                        signals[B][L] (compacted, zero tail), wav_lens[B], too_short[B]; *all_too_short = 1 when the
+ *                        longest item is shorter than min_num_samples (the reference then returns NaN embeddings).
+ * sd_select_masks_dev  : per (chunk, speaker) choice between the clean and the raw mask (SD:3056-3078);
+ *                        binarized[C][F][K] fp64 -> masks[C*K][F] fp32.
+ * sd_mask_compact_file_dev : whole file, device resident: chunk c of the waveform is samples [c*step, c*step + L)
+ *                        (zero beyond num_samples, SegmentModel::crop SD:1641); items are (chunk, speaker) pairs in
+ *                        chunk-major order, wav_lens are normalised per consecutive `batch` items (32 in the reference),
+ *                        batch_invalid[ceil(C*K/batch)] flags batches whose longest item is too short. */
+int sd_mask_compact(sd_ctx* ctx, const float* wav, const float* masks, int B, int L, int F, int min_num_samples,
+                    float* signals, float* wav_lens, uint8_t* too_short, int* all_too_short);
+int sd_select_masks_dev(sd_ctx* ctx, const double* d_binarized, int C, int F, int K, double min_num_frames,
+                        float* d_masks);
+int sd_mask_compact_file_dev(sd_ctx* ctx, const float* d_wave, int64_t num_samples, int C, int K, int L,
+                             int step_samples, const float* d_masks, int F, int batch, int min_num_samples,
+                             float* d_signals, float* d_wav_lens, uint8_t* d_too_short, uint8_t* d_batch_invalid);
+
+/* f2: reconstruct (SD:2789-2848) + to_diarization (SD:2638-2764) + crop_segment (SD:2568-2635).
+ * segmentations[C][F][K] fp32, hard_clusters[C][K] (-2 = inactive), count[n_count] from sd_speaker_count and its
+ * count_frames window -> binary discrete diarization out[rows][cols] fp64 (cols = max label + 1) and the window of
+ * its rows.  sd_reconstruct_rows gives `rows` from the geometry alone (to size `out`). */
+int sd_reconstruct_rows(int C, const sd_window* chunks, int64_t n_count, const sd_window* count_frames,
+                        int64_t* rows, sd_window* frames_out);
+int sd_reconstruct(sd_ctx* ctx, const float* segmentations, int C, int F, int K, const sd_window* chunks,
+                   const int32_t* hard_clusters, const int32_t* count, int64_t n_count,
+                   const sd_window* count_frames, double* out, int64_t cap_elems, int64_t* rows_out, int* cols_out,
+                   sd_window* frames_out);
+/* device pointers; cols (= max label + 1, at least 1) is supplied by the caller */
+int sd_reconstruct_dev(sd_ctx* ctx, const float* d_segmentations, int C, int F, int K, const sd_window* chunks,
+                       const int32_t* d_hard_clusters, int cols, const int32_t* d_count, int64_t n_count,
+                       const sd_window* count_frames, double* d_out, int64_t cap_elems, int64_t* rows_out,
+                       sd_window* frames_out);
+
+/* f3: to_annotation (SD:2852-2935) + Track::support (SD:911-941) + Track::removeShort (SD:943-953) +
+ * finalResult (SD:962-978).  scores[rows][cols] fp64 -> segments[n][2] (start, end seconds) ordered by start,
+ * labels[n].  Segments with equal start are ordered by label (the reference's std::sort leaves it unspecified). */
+int sd_to_annotation(sd_ctx* ctx, const double* scores, int64_t rows, int cols, const sd_window* frames,
+                     double onset, double offset, double min_duration_on, double min_duration_off,
+                     double* segments, int32_t* labels, int64_t cap, int64_t* n_out);
+int sd_to_annotation_dev(sd_ctx* ctx, const double* d_scores, int64_t rows, int cols, const sd_window* frames,
+                         double onset, double offset, double min_duration_on, double min_duration_off,
+                         double* d_segments, int32_t* d_labels, int64_t cap, int64_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,7 +70,9 @@ EXPORTS = [
     "sd_aggregate", "sd_aggregate_dev", "sd_binarize", "sd_binarize_dev", "sd_binarize_rows", "sd_trim_num_frames",
     "sd_trim", "sd_speaker_count", "sd_speaker_count_dev", "sd_clean_segmentations", "sd_normalize", "sd_pdist",
     "sd_linkage", "sd_linkage_dev", "sd_fcluster", "sd_cluster", "sd_cosine_cdist", "sd_cluster_default_params",
-    "sd_cluster_labels", "sd_clustering", "sd_clustering_dev",
+    "sd_cluster_labels", "sd_clustering", "sd_clustering_dev", "sd_mask_compact", "sd_select_masks_dev",
+    "sd_mask_compact_file_dev", "sd_reconstruct_rows", "sd_reconstruct", "sd_reconstruct_dev", "sd_to_annotation",
+    "sd_to_annotation_dev",
 ]
 
 _lib = None
@@ -141,6 +143,14 @@ def lib():
         "sd_cluster_labels": (i, [vp, vp, i, i, C.POINTER(ClusterParams), vp]),
         "sd_clustering": (i, [vp, vp, i, i, i, C.POINTER(ClusterParams), vp, i, vp, vp, i, c_ip]),
         "sd_clustering_dev": (i, [vp, vp, i, i, i, C.POINTER(ClusterParams), vp, i, vp, vp, i, c_ip]),
+        "sd_mask_compact": (i, [vp, vp, vp, i, i, i, i, vp, vp, vp, c_ip]),
+        "sd_select_masks_dev": (i, [vp, vp, i, i, i, d, vp]),
+        "sd_mask_compact_file_dev": (i, [vp, vp, i64, i, i, i, i, vp, i, i, i, vp, vp, vp, vp]),
+        "sd_reconstruct_rows": (i, [i, W, i64, W, c_lp, W]),
+        "sd_reconstruct": (i, [vp, vp, i, i, i, W, vp, vp, i64, W, vp, i64, c_lp, c_ip, W]),
+        "sd_reconstruct_dev": (i, [vp, vp, i, i, i, W, vp, i, vp, i64, W, vp, i64, c_lp, W]),
+        "sd_to_annotation": (i, [vp, vp, i64, i, W, d, d, d, d, vp, vp, i64, c_lp]),
+        "sd_to_annotation_dev": (i, [vp, vp, i64, i, W, d, d, d, d, vp, vp, i64, c_lp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -448,3 +458,84 @@ class Context:
         if soft_k_cap:
             return hard, soft, k.value
         return hard, k.value
+
+    # ---- next rows
+    def mask_compact(self, wav, masks, min_num_samples=640):
+        """Helper::interpolate + padSequence + wav_lens logic of getEmbedding for one batch."""
+        wav = np.ascontiguousarray(wav, np.float32)
+        masks = np.ascontiguousarray(masks, np.float32)
+        B, Ls = wav.shape
+        sig = np.empty((B, Ls), np.float32)
+        lens = np.empty(B, np.float32)
+        ts = np.zeros(B, np.uint8)
+        inv = C.c_int(0)
+        self._check(self.L.sd_mask_compact(self.h, _ptr(wav), _ptr(masks), B, Ls, masks.shape[1], min_num_samples,
+                                           _ptr(sig), _ptr(lens), _ptr(ts), C.byref(inv)))
+        return inv.value, sig, lens, ts
+
+    def select_masks(self, binarized, min_num_frames):
+        """(chunk, speaker) mask choice of speakerDiarization() (SD:3056-3078): [C][F][K] fp64 -> [C*K][F] fp32."""
+        b = np.ascontiguousarray(binarized, np.float64)
+        Cn, F, K = b.shape
+        d_b = self.to_device(b)
+        d_m = self.malloc(4 * Cn * K * F)
+        try:
+            self._check(self.L.sd_select_masks_dev(self.h, d_b, Cn, F, K, float(min_num_frames), d_m))
+            out = np.empty((Cn * K, F), np.float32)
+            self.d2h(out, d_m)
+        finally:
+            self.free(d_b)
+            self.free(d_m)
+        return out
+
+    def mask_compact_file(self, wave, masks, C_, K, Ls, step_samples, batch=32, min_num_samples=640):
+        """Whole-file masking: chunk c = wave[c*step : c*step + Ls] (zero padded); masks [C*K][F]."""
+        wave = np.ascontiguousarray(wave, np.float32)
+        masks = np.ascontiguousarray(masks, np.float32)
+        R, F = masks.shape
+        assert R == C_ * K
+        ng = (R + batch - 1) // batch
+        d_w, d_m = self.to_device(wave), self.to_device(masks)
+        d_s, d_l, d_t, d_i = self.malloc(4 * R * Ls), self.malloc(4 * R), self.malloc(R), self.malloc(ng)
+        try:
+            self._check(self.L.sd_mask_compact_file_dev(self.h, d_w, wave.size, C_, K, Ls, step_samples, d_m, F, batch,
+                                                        min_num_samples, d_s, d_l, d_t, d_i))
+            sig, lens = np.empty((R, Ls), np.float32), np.empty(R, np.float32)
+            ts, inv = np.empty(R, np.uint8), np.empty(ng, np.uint8)
+            self.d2h(sig, d_s); self.d2h(lens, d_l); self.d2h(ts, d_t); self.d2h(inv, d_i)
+        finally:
+            for p in (d_w, d_m, d_s, d_l, d_t, d_i):
+                self.free(p)
+        return sig, lens, ts, inv
+
+    def reconstruct(self, segmentations, chunks, hard, count, count_frames):
+        """reconstruct + to_diarization: -> (discrete diarization [rows][cols] fp64, Window of its rows)."""
+        seg = np.ascontiguousarray(segmentations, np.float32)
+        hard = np.ascontiguousarray(hard, np.int32)
+        count = np.ascontiguousarray(count, np.int32)
+        Cn, F, K = seg.shape
+        cw, cf = _win(chunks), _win(count_frames)
+        rows = C.c_int64()
+        self._check(self.L.sd_reconstruct_rows(Cn, C.byref(cw), count.shape[0], C.byref(cf), C.byref(rows), None))
+        kc = max(int(hard.max()), 0) + 1
+        out = np.empty((max(rows.value, 0), kc), np.float64)
+        cols = C.c_int(0)
+        fr = Window()
+        self._check(self.L.sd_reconstruct(self.h, _ptr(seg), Cn, F, K, C.byref(cw), _ptr(hard), _ptr(count),
+                                          count.shape[0], C.byref(cf), _ptr(out), out.size, C.byref(rows),
+                                          C.byref(cols), C.byref(fr)))
+        assert cols.value == kc and rows.value == out.shape[0]
+        return out, fr
+
+    def to_annotation(self, scores, frames, onset=0.5, offset=0.5, min_duration_on=0.0,
+                      min_duration_off=float(np.float32(0.5817029604921046)), cap=None):
+        s = np.ascontiguousarray(scores, np.float64)
+        rows, cols = s.shape
+        cap = (rows // 2 + 2) * cols if cap is None else cap
+        seg = np.empty((max(cap, 1), 2), np.float64)
+        lab = np.empty(max(cap, 1), np.int32)
+        n = C.c_int64()
+        fw = _win(frames)
+        self._check(self.L.sd_to_annotation(self.h, _ptr(s), rows, cols, C.byref(fw), onset, offset, min_duration_on,
+                                            min_duration_off, _ptr(seg), _ptr(lab), cap, C.byref(n)))
+        return seg[:n.value].copy(), lab[:n.value].copy()

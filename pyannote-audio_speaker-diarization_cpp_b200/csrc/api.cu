@@ -19,6 +19,19 @@ int clustering_launch(sd_ctx* ctx, const double* d_emb, int C, int S, int D, con
                       const sd_cluster_params* p, const double* d_binarized, int F, int* d_hard, double* d_soft,
                       int soft_k_cap, int* num_clusters_out);
 int row_valid_launch(sd_ctx* ctx, const double* d_emb, int R, int D, unsigned char* d_valid);
+int mask_compact_launch(sd_ctx* ctx, const float* d_wav, const long* d_wav_base, long item_stride, long wav_limit,
+                        const float* d_masks, int R, int L, int F, int batch, int min_num_samples, float* d_signals,
+                        float* d_wav_lens, unsigned char* d_too_short, unsigned char* d_batch_invalid);
+int reconstruct_rows(int C, const sd_window* chunks, int64_t n_count, const sd_window* cf, int64_t* rows,
+                     sd_window* frames_out);
+int reconstruct_launch(sd_ctx* ctx, const float* d_seg, int C, int F, int K, const sd_window* chunks, const int* d_hard,
+                       int Kc, const int* d_count, int64_t n_count, const sd_window* cf, double* d_out,
+                       int64_t cap_elems, int64_t* rows_out, sd_window* frames_out);
+int to_annotation_launch(sd_ctx* ctx, const double* d_scores, int64_t rows, int cols, const sd_window* frames,
+                         double onset, double offset, double min_on, double min_off, double* d_seg, int* d_label,
+                         int64_t cap, long* d_n);
+int select_masks_launch(sd_ctx* ctx, const double* d_binarized, int C, int F, int K, double min_num_frames,
+                        float* d_out);
 
 // Small host -> device parameter uploads go through a ring of pinned slots so that they are truly
 // asynchronous and the caller's buffer can be reused immediately.
@@ -833,6 +846,165 @@ int sd_clustering(sd_ctx* ctx, const double* embeddings, int C, int S, int D, co
         SD_CUDA(ctx, cudaMemcpyAsync(soft, d_soft, sizeof(double) * (size_t)R * soft_k_cap, cudaMemcpyDeviceToHost,
                                      ctx->stream));
     return check_status(ctx);
+}
+
+/* ---------------------------------------------------------------- next rows: masking */
+
+int sd_mask_compact(sd_ctx* ctx, const float* wav, const float* masks, int B, int L, int F, int min_num_samples,
+                    float* signals, float* wav_lens, uint8_t* too_short, int* all_too_short) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, wav && masks && signals && wav_lens && too_short, "sd_mask_compact: null pointer");
+    SD_REQUIRE(ctx, B > 0 && L > 0 && F > 0 && L > F, "sd_mask_compact: need B > 0 and L > F > 0 (SD:753)");
+    const size_t wb = sizeof(float) * (size_t)B * L, mb = sizeof(float) * (size_t)B * F;
+    float* d_wav = (float*)ctx->scratch(BUF_STFT_IN, wb);
+    float* d_sig = (float*)ctx->scratch(BUF_STFT_OUT, wb);
+    char* d_small = (char*)ctx->scratch(BUF_GENERIC_B, mb + sizeof(float) * (size_t)B + 2 * (size_t)B + 64);
+    if (!d_wav || !d_sig || !d_small) return SD_ERR_NOMEM;
+    float* d_masks = reinterpret_cast<float*>(d_small);
+    float* d_lens = reinterpret_cast<float*>(d_small + mb);
+    unsigned char* d_ts = reinterpret_cast<unsigned char*>(d_small + mb + sizeof(float) * (size_t)B);
+    unsigned char* d_inv = d_ts + B;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_wav, wav, wb, cudaMemcpyHostToDevice, ctx->stream));
+    SD_CUDA(ctx, cudaMemcpyAsync(d_masks, masks, mb, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = mask_compact_launch(ctx, d_wav, nullptr, L, (long)B * L, d_masks, B, L, F, B, min_num_samples, d_sig, d_lens,
+                                 d_ts, d_inv);
+    if (rc) return rc;
+    unsigned char inv = 0;
+    SD_CUDA(ctx, cudaMemcpyAsync(signals, d_sig, wb, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaMemcpyAsync(wav_lens, d_lens, sizeof(float) * (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaMemcpyAsync(too_short, d_ts, (size_t)B, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaMemcpyAsync(&inv, d_inv, 1, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (all_too_short) *all_too_short = inv;
+    return SD_OK;
+}
+
+int sd_select_masks_dev(sd_ctx* ctx, const double* d_binarized, int C, int F, int K, double min_num_frames,
+                        float* d_masks) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_binarized && d_masks, "sd_select_masks_dev: null pointer");
+    SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0, "sd_select_masks_dev: C, F, K must be positive");
+    return select_masks_launch(ctx, d_binarized, C, F, K, min_num_frames, d_masks);
+}
+
+int sd_mask_compact_file_dev(sd_ctx* ctx, const float* d_wave, int64_t num_samples, int C, int K, int L,
+                             int step_samples, const float* d_masks, int F, int batch, int min_num_samples,
+                             float* d_signals, float* d_wav_lens, uint8_t* d_too_short, uint8_t* d_batch_invalid) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_wave && d_masks && d_signals && d_wav_lens && d_too_short, "sd_mask_compact_file_dev: null pointer");
+    SD_REQUIRE(ctx, C > 0 && K > 0 && L > F && F > 0 && batch > 0 && step_samples > 0, "sd_mask_compact_file_dev: bad sizes");
+    const int R = C * K;
+    std::vector<long> base((size_t)R);
+    for (int c = 0; c < C; ++c)
+        for (int k = 0; k < K; ++k) base[(size_t)c * K + k] = (long)c * step_samples;
+    long* d_base = (long*)ctx->scratch(BUF_CL_MISC, sizeof(long) * (size_t)R);
+    if (!d_base) return SD_ERR_NOMEM;
+    int rc = upload_small(ctx, d_base, base.data(), sizeof(long) * (size_t)R);
+    if (rc) return rc;
+    return mask_compact_launch(ctx, d_wave, d_base, 0, (long)num_samples, d_masks, R, L, F, batch, min_num_samples,
+                               d_signals, d_wav_lens, d_too_short, d_batch_invalid);
+}
+
+/* ---------------------------------------------------------------- next rows: reconstruct / to_annotation */
+
+int sd_reconstruct_rows(int C, const sd_window* chunks, int64_t n_count, const sd_window* count_frames,
+                        int64_t* rows, sd_window* frames_out) {
+    if (!chunks || !count_frames || C <= 0 || n_count < 0) return SD_ERR_INVALID;
+    return reconstruct_rows(C, chunks, n_count, count_frames, rows, frames_out);
+}
+
+int sd_reconstruct_dev(sd_ctx* ctx, const float* d_seg, int C, int F, int K, const sd_window* chunks,
+                       const int32_t* d_hard, int cols, const int32_t* d_count, int64_t n_count,
+                       const sd_window* count_frames, double* d_out, int64_t cap_elems, int64_t* rows_out,
+                       sd_window* frames_out) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_seg && d_hard && d_count && d_out && chunks && count_frames, "sd_reconstruct_dev: null pointer");
+    SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0 && cols > 0 && n_count > 0, "sd_reconstruct_dev: sizes must be positive");
+    SD_REQUIRE(ctx, chunks->num_samples > 0, "sd_reconstruct: chunk window num_samples must be > 0 (SD:1181)");
+    return reconstruct_launch(ctx, d_seg, C, F, K, chunks, d_hard, cols, d_count, n_count, count_frames, d_out, cap_elems,
+                              rows_out, frames_out);
+}
+
+int sd_reconstruct(sd_ctx* ctx, const float* segmentations, int C, int F, int K, const sd_window* chunks,
+                   const int32_t* hard_clusters, const int32_t* count, int64_t n_count,
+                   const sd_window* count_frames, double* out, int64_t cap_elems, int64_t* rows_out, int* cols_out,
+                   sd_window* frames_out) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, segmentations && hard_clusters && count && out && chunks && count_frames,
+               "sd_reconstruct: null pointer");
+    SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0 && n_count > 0, "sd_reconstruct: sizes must be positive");
+    int Kc = 0;  // SD:2803-2812: max label (floor 0) + 1
+    for (long i = 0; i < (long)C * K; ++i) Kc = hard_clusters[i] > Kc ? hard_clusters[i] : Kc;
+    Kc += 1;
+    if (cols_out) *cols_out = Kc;
+    const size_t seg_b = sizeof(float) * (size_t)C * F * K, hard_b = sizeof(int) * (size_t)C * K,
+                 cnt_b = sizeof(int) * (size_t)n_count;
+    float* d_seg = (float*)ctx->scratch(BUF_BIN_IN, seg_b);
+    char* d_io = (char*)ctx->scratch(BUF_DZ_IO, ((hard_b + 15) / 16) * 16 + cnt_b);
+    int64_t rows = 0;
+    reconstruct_rows(C, chunks, n_count, count_frames, &rows, nullptr);
+    if (rows_out) *rows_out = rows;
+    if (rows * Kc > cap_elems)
+        return ctx->fail(SD_ERR_CAPACITY, "sd_reconstruct: need %lld elements, have %lld", (long long)(rows * Kc),
+                         (long long)cap_elems);
+    double* d_out = (double*)ctx->scratch(BUF_DZ_IO2, sizeof(double) * (size_t)(rows > 0 ? rows : 1) * Kc);
+    if (!d_seg || !d_io || !d_out) return SD_ERR_NOMEM;
+    int* d_hard = reinterpret_cast<int*>(d_io);
+    int* d_count = reinterpret_cast<int*>(d_io + ((hard_b + 15) / 16) * 16);
+    SD_CUDA(ctx, cudaMemcpyAsync(d_seg, segmentations, seg_b, cudaMemcpyHostToDevice, ctx->stream));
+    SD_CUDA(ctx, cudaMemcpyAsync(d_hard, hard_clusters, hard_b, cudaMemcpyHostToDevice, ctx->stream));
+    SD_CUDA(ctx, cudaMemcpyAsync(d_count, count, cnt_b, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = reconstruct_launch(ctx, d_seg, C, F, K, chunks, d_hard, Kc, d_count, n_count, count_frames, d_out,
+                                rows * Kc, nullptr, frames_out);
+    if (rc) return rc;
+    if (rows > 0)
+        SD_CUDA(ctx, cudaMemcpyAsync(out, d_out, sizeof(double) * (size_t)rows * Kc, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+
+int sd_to_annotation_dev(sd_ctx* ctx, const double* d_scores, int64_t rows, int cols, const sd_window* frames,
+                         double onset, double offset, double min_duration_on, double min_duration_off,
+                         double* d_segments, int32_t* d_labels, int64_t cap, int64_t* n_out) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_scores && frames && d_segments && d_labels && n_out, "sd_to_annotation_dev: null pointer");
+    SD_REQUIRE(ctx, rows > 0 && cols > 0 && cap >= 0, "sd_to_annotation_dev: rows and cols must be positive");
+    long* d_n = (long*)ctx->scratch(BUF_GENERIC_A, sizeof(long));
+    if (!d_n) return SD_ERR_NOMEM;
+    int rc = to_annotation_launch(ctx, d_scores, rows, cols, frames, onset, offset, min_duration_on, min_duration_off,
+                                  d_segments, d_labels, cap, d_n);
+    if (rc) return rc;
+    long n = 0;
+    SD_CUDA(ctx, cudaMemcpyAsync(&n, d_n, sizeof(long), cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *n_out = n;
+    if (n > cap) return ctx->fail(SD_ERR_CAPACITY, "sd_to_annotation: %ld segments, capacity %lld", n, (long long)cap);
+    return SD_OK;
+}
+
+int sd_to_annotation(sd_ctx* ctx, const double* scores, int64_t rows, int cols, const sd_window* frames, double onset,
+                     double offset, double min_duration_on, double min_duration_off, double* segments,
+                     int32_t* labels, int64_t cap, int64_t* n_out) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, scores && frames && segments && labels && n_out, "sd_to_annotation: null pointer");
+    SD_REQUIRE(ctx, rows > 0 && cols > 0 && cap >= 0, "sd_to_annotation: rows and cols must be positive");
+    const size_t in_b = sizeof(double) * (size_t)rows * cols;
+    double* d_in = (double*)ctx->scratch(BUF_DZ_IO2, in_b);
+    char* d_o = (char*)ctx->scratch(BUF_DZ_IO, (sizeof(double) * 2 + sizeof(int)) * (size_t)(cap > 0 ? cap : 1));
+    if (!d_in || !d_o) return SD_ERR_NOMEM;
+    double* d_seg = reinterpret_cast<double*>(d_o);
+    int* d_lab = reinterpret_cast<int*>(d_o + sizeof(double) * 2 * (size_t)(cap > 0 ? cap : 1));
+    SD_CUDA(ctx, cudaMemcpyAsync(d_in, scores, in_b, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = sd_to_annotation_dev(ctx, d_in, rows, cols, frames, onset, offset, min_duration_on, min_duration_off, d_seg,
+                                  d_lab, cap, n_out);
+    if (rc) return rc;
+    const int64_t n = *n_out;
+    if (n > 0) {
+        SD_CUDA(ctx, cudaMemcpyAsync(segments, d_seg, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        SD_CUDA(ctx, cudaMemcpyAsync(labels, d_lab, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SD_OK;
 }
 
 }  // extern "C"

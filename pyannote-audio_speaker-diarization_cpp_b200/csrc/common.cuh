@@ -44,6 +44,13 @@ enum BufTag {
     BUF_GENERIC_A,
     BUF_GENERIC_B,
     BUF_TC_OPERANDS,
+    BUF_DZ_CS,
+    BUF_DZ_ACT,
+    BUF_DZ_IO,
+    BUF_DZ_IO2,
+    BUF_AN_FLAGS,
+    BUF_AN_LISTS,
+    BUF_AN_META,
     BUF_COUNT
 };
 
