@@ -366,4 +366,88 @@ public:
     }
 };
 
+// ---------------------------------------------------------------------------------------------------
+// Rows either side of the hot path
+// ---------------------------------------------------------------------------------------------------
+
+// The masking prologue of getEmbedding (SD:2466-2510): Helper::interpolate(masks, num_samples, 0.5) (SD:746),
+// Helper::padSequence(waveforms, imasks) (SD:770), wav_lens = imasks.sum / max and the too-short bookkeeping.
+// Returns false when even the longest item is shorter than min_num_samples -- the reference then fills the
+// embeddings with NaN and skips the model (SD:2479-2486).  `too_short[i]` marks items whose embedding the
+// reference overwrites with NaN after inference (SD:2545-2556).
+inline bool masked_signals(const vec2f& waveforms, const vec2f& masks, int min_num_samples, vec2f& signals,
+                           vec1f& wav_lens, std::vector<bool>& too_short) {
+    Context& c = context();
+    const int B = static_cast<int>(waveforms.size()), L = static_cast<int>(waveforms[0].size()),
+              F = static_cast<int>(masks[0].size());
+    std::vector<float> w = detail::flatten2<float, float>(waveforms), m = detail::flatten2<float, float>(masks);
+    std::vector<float> sig(w.size());
+    std::vector<uint8_t> ts(static_cast<size_t>(B));
+    wav_lens.assign(static_cast<size_t>(B), 0.f);
+    int all_short = 0;
+    c.check(sd_mask_compact(c.get(), w.data(), m.data(), B, L, F, min_num_samples, sig.data(), wav_lens.data(), ts.data(),
+                            &all_short));
+    signals = detail::unflatten2<float, float>(sig, static_cast<size_t>(B), static_cast<size_t>(L));
+    too_short.assign(ts.begin(), ts.end());
+    return all_short == 0;
+}
+
+// reconstruct (SD:2789-2848), including to_diarization (SD:2638) and crop_segment (SD:2568).
+template <class SW>
+vec2d reconstruct(const vec3f& segmentations, const SW& segmentations_frames,
+                  const std::vector<std::vector<int>>& hard_clusters, const std::vector<int>& count_data,
+                  const SW& count_frames, SW& activations_frames) {
+    Context& c = context();
+    const int C = static_cast<int>(segmentations.size()), F = static_cast<int>(segmentations[0].size()),
+              K = static_cast<int>(segmentations[0][0].size());
+    const sd_window cw = detail::to_window(segmentations_frames), cf = detail::to_window(count_frames);
+    std::vector<float> seg = detail::flatten3<float, float>(segmentations);
+    std::vector<int32_t> hard = detail::flatten2<int, int32_t>(hard_clusters);
+    std::vector<int32_t> count(count_data.begin(), count_data.end());
+    int kc = 0;
+    for (int32_t h : hard) kc = h > kc ? h : kc;
+    kc += 1;
+    int64_t rows = 0;
+    c.check(sd_reconstruct_rows(C, &cw, static_cast<int64_t>(count.size()), &cf, &rows, nullptr));
+    std::vector<double> out(static_cast<size_t>(rows > 0 ? rows : 0) * kc + 1);
+    int cols = 0;
+    sd_window fr;
+    c.check(sd_reconstruct(c.get(), seg.data(), C, F, K, &cw, hard.data(), count.data(),
+                           static_cast<int64_t>(count.size()), &cf, out.data(), static_cast<int64_t>(out.size()), &rows,
+                           &cols, &fr));
+    activations_frames.start = fr.start;
+    activations_frames.step = fr.step;
+    activations_frames.duration = fr.duration;
+    out.resize(static_cast<size_t>(rows) * cols);
+    return detail::unflatten2<double, double>(out, static_cast<size_t>(rows), static_cast<size_t>(cols));
+}
+
+// What Annotation::finalResult() (SD:962-978) yields for to_annotation (SD:2852-2935): the speech turns of all
+// clusters ordered by start.  `Result` is any type constructible from (double start, double end, int label),
+// e.g. the reference's Annotation::Result (SD:866).
+struct Turn {
+    double start, end;
+    int label;
+    Turn(double s, double e, int l) : start(s), end(e), label(l) {}
+};
+template <class Result = Turn, class SW>
+std::vector<Result> to_annotation(const vec2d& scores, const SW& frames, double onset, double offset,
+                                  double min_duration_on, double min_duration_off) {
+    Context& c = context();
+    const int64_t rows = static_cast<int64_t>(scores.size());
+    const int cols = static_cast<int>(scores[0].size());
+    const sd_window fw = detail::to_window(frames);
+    std::vector<double> flat = detail::flatten2<double, double>(scores);
+    const int64_t cap = (rows / 2 + 2) * cols;
+    std::vector<double> seg(static_cast<size_t>(cap) * 2);
+    std::vector<int32_t> lab(static_cast<size_t>(cap));
+    int64_t n = 0;
+    c.check(sd_to_annotation(c.get(), flat.data(), rows, cols, &fw, onset, offset, min_duration_on, min_duration_off,
+                             seg.data(), lab.data(), cap, &n));
+    std::vector<Result> out;
+    out.reserve(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i) out.emplace_back(seg[2 * i], seg[2 * i + 1], static_cast<int>(lab[i]));
+    return out;
+}
+
 }  // namespace sdb200

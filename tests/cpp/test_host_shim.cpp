@@ -7,6 +7,7 @@
 #undef main
 
 #include <random>
+#include <tuple>
 
 #include "../../pyannote-audio_speaker-diarization_cpp_b200/host/sdb200_host.hpp"
 
@@ -163,6 +164,53 @@ int main() {
         threw = std::string(e.what()) == "Vectors have zero magnitude.";
     }
     CHECK(threw, "zero magnitude throws like the reference");
+
+    // rows after clustering: reconstruct (+ to_diarization, crop_segment) and to_annotation
+    {
+        SlidingWindow act_ref, act_got;
+        auto rec_ref = reconstruct(seg, sf, hard_ref, ref_cnt, cf_ref, act_ref);
+        auto rec_got = sdb200::reconstruct(seg, sf, hard_ref, ref_cnt, cf_ref, act_got);
+        CHECK(same(rec_ref, rec_got) && act_ref.start == act_got.start && act_ref.step == act_got.step &&
+                  act_ref.duration == act_got.duration,
+              "reconstruct");
+        auto ann = to_annotation(rec_ref, act_ref, 0.5, 0.5, 0.0, 0.5817029604921046f).finalResult();
+        auto turns = sdb200::to_annotation(rec_ref, act_ref, 0.5, 0.5, 0.0, 0.5817029604921046f);
+        auto key = [](double s, double e, int l) { return std::make_tuple(s, e, l); };
+        std::vector<std::tuple<double, double, int>> ka, kb;
+        for (auto& r : ann) ka.push_back(key(r.start, r.end, r.label));
+        for (auto& r : turns) kb.push_back(key(r.start, r.end, r.label));
+        bool sorted = std::is_sorted(turns.begin(), turns.end(), [](const sdb200::Turn& a, const sdb200::Turn& b) { return a.start < b.start; });
+        std::sort(ka.begin(), ka.end());  // std::sort by start leaves equal starts in unspecified order
+        std::sort(kb.begin(), kb.end());
+        CHECK(!ka.empty() && ka == kb && sorted, "to_annotation");
+    }
+
+    // masking prologue of getEmbedding: Helper::interpolate + Helper::padSequence
+    {
+        const int B = 5, L = 80000;
+        std::vector<std::vector<float>> wv(B, std::vector<float>(L)), mk(B, std::vector<float>(F));
+        for (auto& r : wv)
+            for (auto& v : r) v = U(rng) - 0.5f;
+        for (int b = 0; b < B; ++b)
+            for (int f = 0; f < F; ++f) mk[b][f] = (float)ref_bin[b * 3][f][b % K];
+        std::fill(mk[3].begin(), mk[3].end(), 0.f);
+        mk[3][7] = 1.f;  // shorter than min_num_samples -> too short
+        auto imasks = Helper::interpolate(mk, L, 0.5);
+        auto sig_ref = Helper::padSequence(wv, imasks);
+        std::vector<std::vector<float>> sig_got;
+        std::vector<float> wl;
+        std::vector<bool> ts;
+        bool ok = sdb200::masked_signals(wv, mk, 640, sig_got, wl, ts);
+        float mx = 0;
+        std::vector<float> cnt(B);
+        for (int b = 0; b < B; ++b) {
+            cnt[b] = (float)std::count(imasks[b].begin(), imasks[b].end(), true);
+            mx = std::max(mx, cnt[b]);
+        }
+        bool lens_ok = true;
+        for (int b = 0; b < B; ++b) lens_ok = lens_ok && (cnt[b] < 640 ? (wl[b] == 1.0f && ts[b]) : (wl[b] == cnt[b] / mx && !ts[b]));
+        CHECK(ok && same(sig_ref, sig_got) && lens_ok, "masked_signals (interpolate + padSequence + wav_lens)");
+    }
 
     // STFT front-end: what reaches emd4.onnx (captured by the ORT stub) vs the shim
     std::vector<std::vector<float>> wav(3, std::vector<float>(16000));
