@@ -247,6 +247,21 @@ int sd_to_annotation_dev(sd_ctx* ctx, const double* d_scores, int64_t rows, int 
                          double onset, double offset, double min_duration_on, double min_duration_off,
                          double* d_segments, int32_t* d_labels, int64_t cap, int64_t* n_out);
 
+/* f4: ingest.
+ * sd_ingest_pcm16     : int16 PCM -> float (frontend/wav.h:98-104) scaled by 1/32768 (SD:2948-2951).
+ * sd_slide_geometry   : the chunk loop of SegmentModel::slide (SD:1407-1470): number of full windows and the start /
+ *                       length (samples) of the shorter tail chunk (tail_start = -1 when there is none).
+ * sd_crop_chunks(_dev): SegmentModel::crop (SD:1641-1662) for n_chunks windows starting at starts_s[] seconds (host
+ *                       array): out[n_chunks][floor(duration*sample_rate)], zero padded outside the file. */
+int sd_ingest_pcm16(sd_ctx* ctx, const int16_t* pcm, int64_t n, float* out);
+int sd_ingest_pcm16_dev(sd_ctx* ctx, const int16_t* d_pcm, int64_t n, float* d_out);
+int sd_slide_geometry(int64_t num_samples, double duration, double step, int64_t* full_chunks, int64_t* tail_start,
+                      int64_t* tail_len);
+int sd_crop_chunks(sd_ctx* ctx, const float* wave, int64_t num_samples, const double* starts_s, int n_chunks,
+                   double duration, int sample_rate, float* out);
+int sd_crop_chunks_dev(sd_ctx* ctx, const float* d_wave, int64_t num_samples, const double* starts_s, int n_chunks,
+                       double duration, int sample_rate, float* d_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,6 +97,23 @@ def main():
     np.savez_compressed(os.path.join(OUT, "next_ref.npz"), masks=masks, mc_rc=rc, sig_nonzero=(sig != 0).sum(1),
                         sig_sum=sig.astype(np.float64).sum(1), lens=lens, too_short=ts, rec=rec.astype(np.uint8), fr=fr,
                         segs=segs, labs=labs)
+    # 8. ingest: a PCM16 mono WAV with a LIST sub-chunk between "fmt " and "data" (wav.h:84-91), read by WavReader
+    import struct
+    pcm = (synth.waveform(12, 0.25)[:4000] * 20000).astype(np.int16)
+    pcm[:4] = [-32768, 32767, 0, -1]
+    lst = b"INFOISFT" + struct.pack("<I", 6) + b"synth\0"
+    body = (b"WAVE" + b"fmt " + struct.pack("<IHHIIHH", 16, 1, 1, 16000, 32000, 2, 16) + b"LIST" +
+            struct.pack("<I", len(lst)) + lst + b"data" + struct.pack("<I", pcm.size * 2) + pcm.tobytes())
+    with open(os.path.join(OUT, "tiny_list.wav"), "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", len(body)) + body)
+    wav_f, meta = r.wav_load(os.path.join(OUT, "tiny_list.wav"))
+    assert wav_f.size == 4000 and meta == (1, 16, 16000)
+    long_wave = synth.waveform(13, 7.3)
+    crop_starts = np.array([0.0, 0.5, 2.30001, 3.0, 6.9, 7.29])
+    crops = np.stack([r.crop(long_wave, t) for t in crop_starts])
+    np.savez_compressed(os.path.join(OUT, "ingest_ref.npz"), pcm=pcm, wav=wav_f, meta=np.array(meta),
+                        crop_starts=crop_starts, crop_sum=crops.astype(np.float64).sum(1),
+                        crop_nonzero=(crops != 0).sum(1), crop_first=crops[:, :4], crop_last=crops[:, -4:])
     tot = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("golden written to", OUT, "%.1f KB" % (tot / 1024))
 

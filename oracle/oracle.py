@@ -95,6 +95,13 @@ class Oracle:
         L.sdo_reconstruct.argtypes = [c_fp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_long,
                                       c_ip, c_ip, C.c_long, C.c_double, C.c_double, C.c_double, C.c_long, c_dp,
                                       C.c_long, c_ip, c_dp]
+        L.sdo_ingest_pcm16.restype = None
+        L.sdo_ingest_pcm16.argtypes = [C.POINTER(C.c_short), C.c_long, c_fp]
+        L.sdo_crop.restype = C.c_long
+        L.sdo_crop.argtypes = [c_fp, C.c_long, C.c_double, C.c_double, C.c_int, c_fp]
+        L.sdo_slide_geometry.restype = None
+        L.sdo_slide_geometry.argtypes = [C.c_long, C.c_double, C.c_double, C.POINTER(C.c_long), C.POINTER(C.c_long),
+                                         C.POINTER(C.c_long)]
         L.sdo_to_annotation.restype = C.c_long
         L.sdo_to_annotation.argtypes = [c_dp, C.c_long, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
                                         C.c_double, C.c_double, C.c_double, c_dp, c_ip, C.c_long]
@@ -304,6 +311,24 @@ class Oracle:
                                        min_duration_on, min_duration_off, _p(seg, c_dp), _p(lab, c_ip), cap)
         assert n >= 0
         return seg[:n].copy(), lab[:n].copy()
+
+
+    def ingest_pcm16(self, pcm):
+        pcm = np.ascontiguousarray(pcm, np.int16)
+        out = np.empty(pcm.shape, np.float32)
+        self.lib.sdo_ingest_pcm16(_p(pcm, C.POINTER(C.c_short)), pcm.size, _p(out, c_fp))
+        return out
+
+    def crop(self, wave, start, duration=5.0, sample_rate=16000):
+        wave = _f32(wave)
+        out = np.empty(int(duration * sample_rate) + 8, np.float32)
+        n = self.lib.sdo_crop(_p(wave, c_fp), wave.size, float(start), float(duration), sample_rate, _p(out, c_fp))
+        return out[:n].copy()
+
+    def slide_geometry(self, num_samples, duration=5.0, step=0.5):
+        a, b, c = C.c_long(), C.c_long(), C.c_long()
+        self.lib.sdo_slide_geometry(num_samples, duration, step, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
 
 
 class Ref:
@@ -522,3 +547,20 @@ class Ref:
                                        min_duration_on, min_duration_off, _p(seg, c_dp), _p(lab, c_ip), cap)
         assert n >= 0
         return seg[:n].copy(), lab[:n].copy()
+
+    def wav_load(self, path, cap=1 << 24):
+        self.lib.ref_wav_load.restype = C.c_long
+        self.lib.ref_wav_load.argtypes = [C.c_char_p, c_fp, C.c_long, C.POINTER(C.c_int)]
+        out = np.empty(cap, np.float32)
+        meta = (C.c_int * 3)()
+        n = self.lib.ref_wav_load(path.encode(), _p(out, c_fp), cap, meta)
+        assert n >= 0
+        return out[:n].copy(), tuple(meta)
+
+    def crop(self, wave, start):
+        self.lib.ref_crop.restype = C.c_long
+        self.lib.ref_crop.argtypes = [c_fp, C.c_long, C.c_double, c_fp]
+        wave = _f32(wave)
+        out = np.empty(80000 + 8, np.float32)
+        n = self.lib.ref_crop(_p(wave, c_fp), wave.size, float(start), _p(out, c_fp))
+        return out[:n].copy()

@@ -385,4 +385,36 @@ long ref_to_annotation(const double* scores, long rows, int cols, double f_start
     return (long)res.size();
 }
 
+// ---- f4: ingest ----
+
+// wav::WavReader (frontend/wav.h:62-126) + the /32768 scaling of speakerDiarization() (2939-2951).
+// meta = {num_channels, bits_per_sample, sample_rate}; returns num_samples (or -1 when cap is too small).
+long ref_wav_load(const char* path, float* out, long cap, int* meta) {
+    wav::WavReader wav_reader(path);
+    meta[0] = wav_reader.num_channels();
+    meta[1] = wav_reader.bits_per_sample();
+    meta[2] = wav_reader.sample_rate();
+    const float* audio = wav_reader.data();
+    int num_samples = wav_reader.num_samples();
+    if (num_samples > cap) return -1;
+    std::vector<float> input_wav{audio, audio + num_samples};
+    for (int i = 0; i < num_samples; ++i) input_wav[i] = input_wav[i] * 1.0f / 32768.0;
+    std::copy(input_wav.begin(), input_wav.end(), out);
+    return num_samples;
+}
+
+// SegmentModel::crop (1641-1662); the model's duration is 5.0 s.
+long ref_crop(const float* wave, long n, double start, float* out) {
+    SegmentModel* mm;
+    {
+        Quiet q;
+        static SegmentModel model("segment2.onnx");
+        mm = &model;
+    }
+    std::vector<float> w(wave, wave + n);
+    auto c = mm->crop(w, std::make_pair(start, start + 5.0));
+    std::copy(c.begin(), c.end(), out);
+    return (long)c.size();
+}
+
 }  // extern "C"

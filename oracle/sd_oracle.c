@@ -1008,3 +1008,46 @@ long sdo_to_annotation(const double* scores, long rows, int cols, double f_start
     free(segs);
     return res;
 }
+
+/* ------------------------------------------------------------------ f4: ingest / chunker */
+
+void sdo_ingest_pcm16(const short* pcm, long n, float* out) {
+    for (long i = 0; i < n; ++i) {
+        float v = (float)pcm[i];                 /* wav.h:100-104 */
+        out[i] = (float)((double)(v * 1.0f) / 32768.0); /* SD:2948-2951 */
+    }
+}
+
+long sdo_crop(const float* wave, long n, double start, double duration, int sample_rate, float* out) {
+    int start_frame = (int)floor(start * sample_rate);
+    int frames = (int)n;
+    int num_frames = (int)floor(duration * sample_rate);
+    int end_frame = start_frame + num_frames;
+    int pad_start = -(start_frame < 0 ? start_frame : 0);
+    int pad_end = (end_frame > frames ? end_frame : frames) - frames;
+    if (start_frame < 0) start_frame = 0;
+    if (end_frame > frames) end_frame = frames;
+    long w = 0;
+    for (int i = 0; i < pad_start; ++i) out[w++] = 0.0f;
+    for (int i = start_frame; i < end_frame; ++i) out[w++] = wave[i];
+    for (int i = 0; i < pad_end; ++i) out[w++] = 0.0f;
+    return w;
+}
+
+void sdo_slide_geometry(long num_samples, double duration, double step, long* full_chunks, long* tail_start,
+                        long* tail_len) {
+    int window_size = (int)round(duration * 16000), step_size = (int)round(step * 16000);
+    size_t i = 0, n = 0;
+    while (i + (size_t)window_size < (size_t)num_samples) { /* SD:1419 */
+        ++n;
+        i += (size_t)step_size;
+    }
+    *full_chunks = (long)n;
+    if (i + 1 < (size_t)num_samples) { /* SD:1451: at least one sample remains */
+        *tail_start = (long)i;
+        *tail_len = num_samples - (long)i;
+    } else {
+        *tail_start = -1;
+        *tail_len = 0;
+    }
+}

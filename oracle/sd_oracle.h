@@ -93,6 +93,15 @@ long sdo_to_annotation(const double* scores, long rows, int cols, double f_start
                        double onset, double offset, double min_duration_on, double min_duration_off, double* seg_out,
                        int* label_out, long cap);
 
+/* f4: ingest.  wav.h:98-104 (int16 -> float) + SD:2948-2951 (x * 1.0f / 32768.0, stored as float) */
+void sdo_ingest_pcm16(const short* pcm, long n, float* out);
+/* SegmentModel::crop, SD:1641-1662: window [floor(start*sr), +floor(duration*sr)) of the waveform, zero padded on
+ * both sides; returns the chunk length */
+long sdo_crop(const float* wave, long n, double start, double duration, int sample_rate, float* out);
+/* the chunk loop of SegmentModel::slide, SD:1407-1470: number of full windows and the zero-padded tail chunk */
+void sdo_slide_geometry(long num_samples, double duration, double step, long* full_chunks, long* tail_start,
+                        long* tail_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,7 +72,8 @@ EXPORTS = [
     "sd_linkage", "sd_linkage_dev", "sd_fcluster", "sd_cluster", "sd_cosine_cdist", "sd_cluster_default_params",
     "sd_cluster_labels", "sd_clustering", "sd_clustering_dev", "sd_mask_compact", "sd_select_masks_dev",
     "sd_mask_compact_file_dev", "sd_reconstruct_rows", "sd_reconstruct", "sd_reconstruct_dev", "sd_to_annotation",
-    "sd_to_annotation_dev",
+    "sd_to_annotation_dev", "sd_ingest_pcm16", "sd_ingest_pcm16_dev", "sd_slide_geometry", "sd_crop_chunks",
+    "sd_crop_chunks_dev",
 ]
 
 _lib = None
@@ -151,6 +152,11 @@ def lib():
         "sd_reconstruct_dev": (i, [vp, vp, i, i, i, W, vp, i, vp, i64, W, vp, i64, c_lp, W]),
         "sd_to_annotation": (i, [vp, vp, i64, i, W, d, d, d, d, vp, vp, i64, c_lp]),
         "sd_to_annotation_dev": (i, [vp, vp, i64, i, W, d, d, d, d, vp, vp, i64, c_lp]),
+        "sd_ingest_pcm16": (i, [vp, vp, i64, vp]),
+        "sd_ingest_pcm16_dev": (i, [vp, vp, i64, vp]),
+        "sd_slide_geometry": (i, [i64, d, d, c_lp, c_lp, c_lp]),
+        "sd_crop_chunks": (i, [vp, vp, i64, vp, i, d, i, vp]),
+        "sd_crop_chunks_dev": (i, [vp, vp, i64, vp, i, d, i, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -539,3 +545,25 @@ class Context:
         self._check(self.L.sd_to_annotation(self.h, _ptr(s), rows, cols, C.byref(fw), onset, offset, min_duration_on,
                                             min_duration_off, _ptr(seg), _ptr(lab), cap, C.byref(n)))
         return seg[:n.value].copy(), lab[:n.value].copy()
+
+    def ingest_pcm16(self, pcm):
+        pcm = np.ascontiguousarray(pcm, np.int16)
+        out = np.empty(pcm.shape, np.float32)
+        self._check(self.L.sd_ingest_pcm16(self.h, _ptr(pcm), pcm.size, _ptr(out)))
+        return out
+
+    def slide_geometry(self, num_samples, duration=5.0, step=0.5):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        rc = self.L.sd_slide_geometry(int(num_samples), duration, step, C.byref(a), C.byref(b), C.byref(c))
+        if rc:
+            raise SdError(rc, "sd_slide_geometry: invalid arguments")
+        return a.value, b.value, c.value
+
+    def crop_chunks(self, wave, starts_s, duration=5.0, sample_rate=16000):
+        wave = np.ascontiguousarray(wave, np.float32)
+        starts = np.ascontiguousarray(starts_s, np.float64)
+        Ls = int(np.floor(duration * sample_rate))
+        out = np.empty((starts.size, Ls), np.float32)
+        self._check(self.L.sd_crop_chunks(self.h, _ptr(wave), wave.size, _ptr(starts), starts.size, duration, sample_rate,
+                                          _ptr(out)))
+        return out

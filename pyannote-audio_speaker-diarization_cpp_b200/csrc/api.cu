@@ -30,6 +30,9 @@ int reconstruct_launch(sd_ctx* ctx, const float* d_seg, int C, int F, int K, con
 int to_annotation_launch(sd_ctx* ctx, const double* d_scores, int64_t rows, int cols, const sd_window* frames,
                          double onset, double offset, double min_on, double min_off, double* d_seg, int* d_label,
                          int64_t cap, long* d_n);
+int ingest_pcm16_launch(sd_ctx* ctx, const short* d_pcm, long n, float* d_out);
+int crop_chunks_launch(sd_ctx* ctx, const float* d_wave, long n, const double* starts_s, int n_chunks, double duration,
+                       int sample_rate, float* d_out);
 int select_masks_launch(sd_ctx* ctx, const double* d_binarized, int C, int F, int K, double min_num_frames,
                         float* d_out);
 
@@ -1004,6 +1007,69 @@ int sd_to_annotation(sd_ctx* ctx, const double* scores, int64_t rows, int cols, 
         SD_CUDA(ctx, cudaMemcpyAsync(labels, d_lab, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
         SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    return SD_OK;
+}
+
+/* ---------------------------------------------------------------- next rows: ingest */
+
+int sd_ingest_pcm16_dev(sd_ctx* ctx, const int16_t* d_pcm, int64_t n, float* d_out) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_pcm && d_out && n > 0, "sd_ingest_pcm16_dev: null pointer or empty input");
+    return ingest_pcm16_launch(ctx, d_pcm, (long)n, d_out);
+}
+
+int sd_ingest_pcm16(sd_ctx* ctx, const int16_t* pcm, int64_t n, float* out) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, pcm && out && n > 0, "sd_ingest_pcm16: null pointer or empty input");
+    short* d_in = (short*)ctx->scratch(BUF_GENERIC_A, sizeof(short) * (size_t)n);
+    float* d_out = (float*)ctx->scratch(BUF_GENERIC_B, sizeof(float) * (size_t)n);
+    if (!d_in || !d_out) return SD_ERR_NOMEM;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_in, pcm, sizeof(short) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = ingest_pcm16_launch(ctx, d_in, (long)n, d_out);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(out, d_out, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SD_OK;
+}
+
+int sd_slide_geometry(int64_t num_samples, double duration, double step, int64_t* full_chunks, int64_t* tail_start,
+                      int64_t* tail_len) {
+    if (num_samples < 0 || !(duration > 0) || !(step > 0)) return SD_ERR_INVALID;
+    const int64_t window = (int64_t)std::round(duration * 16000), hop = (int64_t)std::round(step * 16000);  // SD:1411
+    if (hop <= 0) return SD_ERR_INVALID;
+    // while (i + window < num_samples) i += hop  (SD:1419) in closed form
+    const int64_t full = num_samples > window ? (num_samples - window - 1) / hop + 1 : 0;
+    const int64_t i = full * hop;
+    if (full_chunks) *full_chunks = full;
+    const bool tail = i + 1 < num_samples;  // SD:1451
+    if (tail_start) *tail_start = tail ? i : -1;
+    if (tail_len) *tail_len = tail ? num_samples - i : 0;
+    return SD_OK;
+}
+
+int sd_crop_chunks_dev(sd_ctx* ctx, const float* d_wave, int64_t num_samples, const double* starts_s, int n_chunks,
+                       double duration, int sample_rate, float* d_out) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, d_wave && starts_s && d_out, "sd_crop_chunks_dev: null pointer");
+    SD_REQUIRE(ctx, num_samples > 0 && n_chunks > 0 && n_chunks <= 65535 && duration > 0 && sample_rate > 0,
+               "sd_crop_chunks_dev: bad sizes (1..65535 chunks per call)");
+    return crop_chunks_launch(ctx, d_wave, (long)num_samples, starts_s, n_chunks, duration, sample_rate, d_out);
+}
+
+int sd_crop_chunks(sd_ctx* ctx, const float* wave, int64_t num_samples, const double* starts_s, int n_chunks,
+                   double duration, int sample_rate, float* out) {
+    if (!ctx) return SD_ERR_INVALID;
+    SD_REQUIRE(ctx, wave && starts_s && out, "sd_crop_chunks: null pointer");
+    SD_REQUIRE(ctx, num_samples > 0 && n_chunks > 0 && duration > 0 && sample_rate > 0, "sd_crop_chunks: bad sizes");
+    const size_t L = (size_t)std::floor(duration * sample_rate);
+    float* d_w = (float*)ctx->scratch(BUF_STFT_IN, sizeof(float) * (size_t)num_samples);
+    float* d_o = (float*)ctx->scratch(BUF_STFT_OUT, sizeof(float) * L * (size_t)n_chunks);
+    if (!d_w || !d_o) return SD_ERR_NOMEM;
+    SD_CUDA(ctx, cudaMemcpyAsync(d_w, wave, sizeof(float) * (size_t)num_samples, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = sd_crop_chunks_dev(ctx, d_w, num_samples, starts_s, n_chunks, duration, sample_rate, d_o);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaMemcpyAsync(out, d_o, sizeof(float) * L * (size_t)n_chunks, cudaMemcpyDeviceToHost, ctx->stream));
+    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SD_OK;
 }
 

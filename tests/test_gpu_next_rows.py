@@ -157,3 +157,29 @@ def test_to_annotation_capacity_error(ctx, pkg, synth):
     with pytest.raises(pkg.SdError) as e:
         ctx.to_annotation(scores, (0.0, 0.016875, 0.016875, 0), 0.5, 0.5, 0.0, 0.0, cap=3)
     assert e.value.code == 6
+
+
+# ------------------------------------------------------------------ f4
+
+def test_ingest_pcm16(ctx, oracle, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ingest_ref.npz"))
+    assert np.array_equal(ctx.ingest_pcm16(g["pcm"]), g["wav"])
+    rng = np.random.default_rng(3)
+    for n in (1, 7, 8, 9, 4097, 1 << 20):
+        pcm = rng.integers(-32768, 32768, n).astype(np.int16)
+        assert np.array_equal(ctx.ingest_pcm16(pcm), oracle.ingest_pcm16(pcm))
+
+
+def test_slide_geometry_and_crop(ctx, oracle, synth, golden_dir):
+    for n in (1, 2, 79999, 80000, 80001, 88000, 88001, 16000 * 60, 16000 * 600 + 123):
+        assert ctx.slide_geometry(n) == oracle.slide_geometry(n), n
+    assert ctx.slide_geometry(16000 * 600, 10.0, 1.0) == oracle.slide_geometry(16000 * 600, 10.0, 1.0)
+    g = np.load(os.path.join(golden_dir, "ingest_ref.npz"))
+    wave = synth.waveform(13, 7.3)
+    got = ctx.crop_chunks(wave, g["crop_starts"])
+    assert np.array_equal(got.astype(np.float64).sum(1), g["crop_sum"])
+    assert np.array_equal(got[:, :4], g["crop_first"]) and np.array_equal(got[:, -4:], g["crop_last"])
+    starts = np.concatenate([g["crop_starts"], [-0.75, -4.99, 7.2999]])   # starts past the end are UB in the reference
+    got = ctx.crop_chunks(wave, starts)
+    for row, t in zip(got, starts):
+        assert np.array_equal(row, oracle.crop(wave, t))

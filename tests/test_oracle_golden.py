@@ -140,3 +140,17 @@ def test_cosine_zero_magnitude_is_an_error(oracle):
     b = np.zeros((1, 8))
     rc, _ = oracle.cosine_cdist(a, b)
     assert rc == 2
+
+
+def test_ingest_golden(oracle, golden_dir):
+    """f4: WavReader + /32768 scaling and SegmentModel::crop, vectors generated by the reference itself."""
+    import os
+    g = np.load(os.path.join(golden_dir, "ingest_ref.npz"))
+    assert np.array_equal(oracle.ingest_pcm16(g["pcm"]), g["wav"])
+    raw = open(os.path.join(golden_dir, "tiny_list.wav"), "rb").read()
+    at = raw.index(b"data") + 8
+    assert np.array_equal(np.frombuffer(raw[at:at + 8000], np.int16), g["pcm"])
+    assert oracle.slide_geometry(16000 * 60) == (110, 880000, 80000)
+    assert oracle.slide_geometry(80000) == (0, 0, 80000)
+    assert oracle.slide_geometry(80001) == (1, 8000, 72001)
+    assert oracle.slide_geometry(1) == (0, -1, 0)

@@ -112,3 +112,15 @@ def test_next_rows(oracle, ref, synth):
     masks = (synth.segmentations(6, 3, 293, 1)[:, :, 0] > 0.4).astype(np.float32)
     a, b2 = oracle.mask_compact(wav, masks), ref.mask_compact(wav, masks)
     assert a[0] == b2[0] and all(np.array_equal(p, q) for p, q in zip(a[1:], b2[1:]))
+
+
+def test_ingest_rows(oracle, ref, synth, golden_dir):
+    import os
+    g = np.load(os.path.join(golden_dir, "ingest_ref.npz"))
+    wav, meta = ref.wav_load(os.path.join(golden_dir, "tiny_list.wav"))
+    assert meta == (1, 16, 16000) and np.array_equal(wav, oracle.ingest_pcm16(g["pcm"]))
+    wave = synth.waveform(13, 7.3)
+    for t, s, nz in zip(g["crop_starts"], g["crop_sum"], g["crop_nonzero"]):
+        a, b = oracle.crop(wave, t), ref.crop(wave, t)
+        assert a.shape == b.shape == (80000,) and np.array_equal(a, b)
+        assert a.astype(np.float64).sum() == s and (a != 0).sum() == nz
