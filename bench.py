@@ -271,6 +271,7 @@ def run_product(args, rank, world):
         if world > 1:
             dist.destroy_process_group()
         return
+    next_rows = next_rows_timing(ctx, pkg, synth, geo, d_seg, d_bin, d_hard, chunks, frames) if world == 1 else None
     peak, peak_src = measured_peaks()
     stft_ms = stage_ms[1] / args.steps
     stft_bytes = items * (4 * L + 4 * T * 201 * 2)
@@ -296,11 +297,71 @@ def run_product(args, rank, world):
                     "bound": "latency (N-1 dependent merges)"},
         "clocks": clocks,
     }
+    if next_rows:
+        line["next_rows_ms"] = next_rows
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(geo, wav_items, seg, emb, diar)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def next_rows_timing(ctx, pkg, synth, geo, d_seg, d_bin, d_hard, chunks, frames, reps=5):
+    """SURVEY 8f rows either side of the hot path, device resident, same file geometry; reported beside the step
+    (they are not part of the headline metric)."""
+    import ctypes as C
+    vp = C.c_void_p
+    C_, F, S, L = geo["C"], geo["F"], geo["S"], geo["L"]
+    n = int(WORKLOAD["audio_seconds"] * 16000)
+    step = int(WORKLOAD["step_s"] * 16000)
+    R = C_ * S
+    pcm = (synth.waveform(5, 10.0) * 20000).astype(np.int16)
+    pcm = np.tile(pcm, n // pcm.size + 1)[:n].copy()
+    d_pcm, d_wave = ctx.to_device(pcm), ctx.malloc(4 * n)
+    d_masks, d_sig = ctx.malloc(4 * R * F), ctx.malloc(4 * R * L)
+    d_lens, d_ts, d_inv = ctx.malloc(4 * R), ctx.malloc(R), ctx.malloc((R + 31) // 32)
+    n_cnt, cf, kc = C.c_int64(), pkg.Window(), C.c_int()
+    cap_cnt = ctx.L.sd_aggregate_num_frames(C_, C.byref(chunks), C.byref(frames)) + 64
+    d_cnt = ctx.malloc(4 * cap_cnt)
+    ctx._check(ctx.L.sd_speaker_count_dev(ctx.h, vp(d_bin), C_, F, S, C.byref(chunks), C.byref(frames), vp(d_cnt), cap_cnt,
+                                          C.byref(n_cnt), C.byref(cf)))
+    hard = np.empty(R, np.int32)
+    ctx.d2h(hard, d_hard)
+    cols = max(int(hard.max()), 0) + 1
+    rows, fr = C.c_int64(), pkg.Window()
+    ctx._check(ctx.L.sd_reconstruct_rows(C_, C.byref(chunks), n_cnt.value, C.byref(cf), C.byref(rows), C.byref(fr)))
+    d_rec = ctx.malloc(8 * max(rows.value, 1) * cols)
+    cap = (rows.value // 2 + 2) * cols
+    d_segs, d_labs = ctx.malloc(16 * cap), ctx.malloc(4 * cap)
+    n_turns = C.c_int64()
+    min_frames = float(np.ceil(F * 640 / (WORKLOAD["window_s"] * 16000)))
+
+    def timed(fn):
+        fn()
+        ctx.timer_start(5)
+        for _ in range(reps):
+            fn()
+        ctx.timer_stop(5)
+        return ctx.timer_ms(5) / reps
+
+    out = {
+        "ingest_pcm16": timed(lambda: ctx._check(ctx.L.sd_ingest_pcm16_dev(ctx.h, vp(d_pcm), n, vp(d_wave)))),
+        "select_masks": timed(lambda: ctx._check(ctx.L.sd_select_masks_dev(ctx.h, vp(d_bin), C_, F, S, min_frames,
+                                                                          vp(d_masks)))),
+        "mask_compact_file": timed(lambda: ctx._check(ctx.L.sd_mask_compact_file_dev(
+            ctx.h, vp(d_wave), n, C_, S, L, step, vp(d_masks), F, 32, 640, vp(d_sig), vp(d_lens), vp(d_ts), vp(d_inv)))),
+        "reconstruct": timed(lambda: ctx._check(ctx.L.sd_reconstruct_dev(
+            ctx.h, vp(d_seg), C_, F, S, C.byref(chunks), vp(d_hard), cols, vp(d_cnt), n_cnt.value, C.byref(cf), vp(d_rec),
+            max(rows.value, 1) * cols, C.byref(rows), C.byref(fr)))),
+        "to_annotation": timed(lambda: ctx._check(ctx.L.sd_to_annotation_dev(
+            ctx.h, vp(d_rec), rows.value, cols, C.byref(fr), 0.5, 0.5, 0.0, 0.5817029476165771, vp(d_segs), vp(d_labs), cap,
+            C.byref(n_turns)))),
+    }
+    out["mask_compact_gbs"] = (2 * 4 * R * L) / (out["mask_compact_file"] / 1e3) / 1e9
+    out["speech_turns"] = int(n_turns.value)
+    for p_ in (d_pcm, d_wave, d_masks, d_sig, d_lens, d_ts, d_inv, d_cnt, d_rec, d_segs, d_labs):
+        ctx.free(p_)
+    return out
 
 
 def cpu_baseline(geo, wav_items, seg, emb, diar, stft_sample_items=2):

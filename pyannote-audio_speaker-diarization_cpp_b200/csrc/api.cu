@@ -262,9 +262,12 @@ int sd_ctx_set_option(sd_ctx* ctx, int option, int value) {
         case SD_OPT_STFT_VARIANT:
             ctx->stft_variant = value;
             return SD_OK;
+        case SD_OPT_LINKAGE_CLUSTER:
+            ctx->linkage_cluster = value != 0;
+            return SD_OK;
         case SD_OPT_LINKAGE_THREADS:
-            if (value != 0 && value != 512 && value != 1024)
-                return ctx->fail(SD_ERR_INVALID, "SD_OPT_LINKAGE_THREADS must be 0, 512 or 1024");
+            if (value != 0 && value != 128 && value != 256 && value != 512 && value != 1024)
+                return ctx->fail(SD_ERR_INVALID, "SD_OPT_LINKAGE_THREADS must be 0, 128, 256, 512 or 1024");
             ctx->linkage_threads = value;
             return SD_OK;
         default:

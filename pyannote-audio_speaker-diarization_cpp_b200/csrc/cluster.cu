@@ -17,6 +17,8 @@
 // nearest-neighbour rescans; the merged cluster's column is patched with strided 8-byte stores.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+
 #include <cfloat>
 #include <cmath>
 
@@ -977,6 +979,483 @@ __global__ void __launch_bounds__(T)
     }
 }
 
+// ---- cluster path: the heap-free merge loop spread over a thread-block cluster ---------------------------
+//
+// Same algorithm and the same uniqueness proof as linkage_fast_kernel, but the rows are dealt out group by
+// group (32 rows) to the 8 CTAs of a cluster and, inside a CTA, to its warps; a row's state (bound, candidate,
+// cluster size and id, size and id of the candidate) is only ever touched by the one thread that owns the row,
+// so there is no block barrier anywhere.  Every request (merge sweep or row rescan) ends with each warp
+// publishing its partial results -- the smallest bound among its rows and its share of the new nearest
+// neighbour of the row being recomputed -- into the shared memory of all 8 CTAs with st.async (DSMEM stores
+// that complete a transaction count on the destination's mbarrier), so a request costs one DSMEM flight and
+// one mbarrier wake-up instead of a cluster barrier with a GPU-scope fence.  After the wait every warp of every
+// CTA reduces the same 8*NW entries and reaches the same decision: nothing has to be broadcast.
+// The distance matrix stays in global memory (L2-resident).  Entries written by one CTA and read by another
+// are ordered by a __threadfence() between the sweep's stores and the publish (merge requests only) and are
+// read with ld.global.cg.
+constexpr int kLcCtas = 8;
+
+__host__ __device__ inline size_t linkcluster_smem_bytes(int n) {
+    const size_t ng = (size_t)(n + 31) / 32;
+    const size_t ngl = (ng + kLcCtas - 1) / kLcCtas;
+    return ngl * 32 * (8 + 8 + 5 * 4) + 64;
+}
+
+namespace lc {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async16(uint32_t raddr, uint32_t rbar, uint4 v) {
+    asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(raddr),
+                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(rbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LC_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LC_DONE_%=;\n"
+        "bra LC_WAIT_%=;\n"
+        "LC_DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_barrier_relaxed() {
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;\nbarrier.cluster.wait.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint4 pack(double a, int b, int c) {
+    uint4 r;
+    r.x = (unsigned)__double2loint(a);
+    r.y = (unsigned)__double2hiint(a);
+    r.z = (unsigned)b;
+    r.w = (unsigned)c;
+    return r;
+}
+__device__ __forceinline__ double unpack_d(const uint4& v) { return __hiloint2double((int)v.y, (int)v.x); }
+}  // namespace lc
+
+// One exchange buffer: four 16-byte pieces per publishing warp + the state of the row being recomputed.
+//   A = (top value, top row, multiplicity)            B = (partial value, partial row, size of that row)
+//   C = (cur[top], nbr[top], size[top])               D = (cid[top], nbs[top], nbc[top], cid of the partial row)
+//   P0 = (lb, cur) P1 = (nbr, nbs, nbc, size) P2 = (cid, -, -, -) of the pending row
+template <int E>
+struct __align__(16) ClusterXch {
+    uint4 A[E], B[E], C[E], D[E], P[3];
+};
+
+template <int T>
+__global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
+    linkage_cluster_kernel(const LinkWork* __restrict__ works, const int* ns, int* __restrict__ need_exact) {
+    constexpr int NW = T / 32;
+    constexpr int E = kLcCtas * NW;
+    constexpr int EPL = (E + 31) / 32;  // exchange entries per lane
+    constexpr int PF = 4;
+    constexpr uint32_t kTxBytes = E * 64 + 48;
+    const int prob = blockIdx.x / kLcCtas;
+    int rank;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    const LinkWork w = works[prob];
+    const int n = ns[prob];
+    extern __shared__ __align__(16) unsigned char lc_smem[];
+    __shared__ ClusterXch<E> xch[2];
+    __shared__ __align__(8) unsigned long long mbar[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool scribe = rank == 0 && tid == 0;  // writes Z / flags / counters
+    if (scribe) need_exact[prob] = 0;
+    if (n < 2) return;
+
+    const int NG = (n + 31) / 32;
+    const int NGl = NG > rank ? (NG - rank + kLcCtas - 1) / kLcCtas : 0;  // groups of this CTA: g = lg * 8 + rank
+    const int NGmax = (NG + kLcCtas - 1) / kLcCtas;
+    double* lb = reinterpret_cast<double*>(lc_smem);
+    double* cur = lb + (size_t)NGmax * 32;
+    int* nbr = reinterpret_cast<int*>(cur + (size_t)NGmax * 32);
+    int* nbs = nbr + (size_t)NGmax * 32;
+    int* nbc = nbs + (size_t)NGmax * 32;
+    int* size = nbc + (size_t)NGmax * 32;
+    int* cid = size + (size_t)NGmax * 32;
+
+    const uint32_t bar_local[2] = {lc::smem_u32(&mbar[0]), lc::smem_u32(&mbar[1])};
+    if (tid == 0) {
+        lc::mbar_init(bar_local[0], 1);
+        lc::mbar_init(bar_local[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        lc::mbar_expect_tx(bar_local[0], kTxBytes);
+        lc::mbar_expect_tx(bar_local[1], kTxBytes);
+    }
+    // this lane's st.async destination: CTA (lane & 7), piece (lane >> 3)
+    const uint32_t dst_rank = (uint32_t)(lane & 7);
+    const int piece = lane >> 3;
+    uint32_t dst_piece[2], dst_pend[2], dst_bar[2];
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        const uint4* base = piece == 0 ? xch[b].A : piece == 1 ? xch[b].B : piece == 2 ? xch[b].C : xch[b].D;
+        dst_piece[b] = lc::mapa(lc::smem_u32(base + (rank * NW + warp)), dst_rank);
+        dst_pend[b] = lc::mapa(lc::smem_u32(&xch[b].P[piece < 3 ? piece : 0]), dst_rank);
+        dst_bar[b] = lc::mapa(bar_local[b], dst_rank);
+    }
+
+    auto row_of = [&](int lg) { return ((lg * kLcCtas + rank) << 5) + lane; };
+    auto owner_rank = [&](int z) { return (z >> 5) % kLcCtas; };
+    auto owner_lg = [&](int z) { return (z >> 5) / kLcCtas; };
+    auto entry_of = [&](int z) { return owner_rank(z) * NW + owner_lg(z) % NW; };
+    auto mine = [&](int z) { return z >= 0 && owner_rank(z) == rank && owner_lg(z) % NW == warp && (z & 31) == lane; };
+
+    for (int lg = warp; lg < NGl; lg += NW) {
+        const int z = row_of(lg), s = lg * 32 + lane;
+        size[s] = z < n ? 1 : 0;
+        cid[s] = z;
+        const int nb = z < n - 1 ? w.nbr[z] : -1;
+        nbr[s] = nb;
+        nbs[s] = 1;
+        nbc[s] = nb;
+        lb[s] = z < n - 1 ? w.lb[z] : INFINITY;
+        cur[s] = lb[s];
+    }
+    lc::cluster_barrier_relaxed();  // every mbarrier of the cluster is initialised before the first st.async
+
+    // smallest bound among this warp's live heap rows, `skip` left out
+    auto warp_rows_top = [&](int skip) -> Top {
+        Top m;
+        m.v = INFINITY;
+        m.i = -1;
+        m.c = 0;
+        for (int lg = warp; lg < NGl; lg += NW) {
+            const int z = row_of(lg), s = lg * 32 + lane;
+            if (z < n - 1 && z != skip && size[s] != 0) {
+                const double v = lb[s];
+                if (m.c == 0 || v < m.v) {
+                    m.v = v;
+                    m.i = z;
+                    m.c = 1;
+                } else if (v == m.v)
+                    ++m.c;  // rows ascend within a lane: the stored row stays the lowest
+            }
+        }
+        return warp_top(m.c ? m.v : INFINITY, m.i, m.c);
+    };
+
+    // publish this warp's entry (top of its rows + partial nearest neighbour) and, from the warp that owns it,
+    // the state of the pending row, to every CTA of the cluster: one 16-byte st.async per lane
+    auto publish = [&](int b, const Top& t, double pv, int pi, int pend, bool dummy_pend) {
+        double d_cur = 0.0;
+        int d_nbr = 0, d_size = 0, d_cid = 0, d_nbs = 0, d_nbc = 0, p_size = 0, p_cid = 0;
+        if (t.i >= 0) {
+            const int src = t.i & 31, s = owner_lg(t.i) * 32 + src;
+            const bool me = lane == src;
+            d_cur = __shfl_sync(0xffffffffu, me ? cur[s] : 0.0, src);
+            d_nbr = __shfl_sync(0xffffffffu, me ? nbr[s] : 0, src);
+            d_size = __shfl_sync(0xffffffffu, me ? size[s] : 0, src);
+            d_cid = __shfl_sync(0xffffffffu, me ? cid[s] : 0, src);
+            d_nbs = __shfl_sync(0xffffffffu, me ? nbs[s] : 0, src);
+            d_nbc = __shfl_sync(0xffffffffu, me ? nbc[s] : 0, src);
+        }
+        if (pi >= 0) {
+            const int src = pi & 31, s = owner_lg(pi) * 32 + src;
+            const bool me = lane == src;
+            p_size = __shfl_sync(0xffffffffu, me ? size[s] : 0, src);
+            p_cid = __shfl_sync(0xffffffffu, me ? cid[s] : 0, src);
+        }
+        uint4 v;
+        if (piece == 0)
+            v = lc::pack(t.v, t.i, t.c);
+        else if (piece == 1)
+            v = lc::pack(pv, pi, p_size);
+        else if (piece == 2)
+            v = lc::pack(d_cur, d_nbr, d_size);
+        else {
+            v.x = (unsigned)d_cid;
+            v.y = (unsigned)d_nbs;
+            v.z = (unsigned)d_nbc;
+            v.w = (unsigned)p_cid;
+        }
+        lc::st_async16(dst_piece[b], dst_bar[b], v);
+        const bool own_pend = pend >= 0 ? (owner_rank(pend) == rank && owner_lg(pend) % NW == warp) : dummy_pend;
+        if (own_pend) {
+            uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0;
+            if (pend >= 0) {
+                const int src = pend & 31, s = owner_lg(pend) * 32 + src;
+                const bool me = lane == src;
+                const double q_lb = __shfl_sync(0xffffffffu, me ? lb[s] : 0.0, src);
+                const double q_cur = __shfl_sync(0xffffffffu, me ? cur[s] : 0.0, src);
+                q0.x = (unsigned)__double2loint(q_lb);
+                q0.y = (unsigned)__double2hiint(q_lb);
+                q0.z = (unsigned)__double2loint(q_cur);
+                q0.w = (unsigned)__double2hiint(q_cur);
+                q1.x = (unsigned)__shfl_sync(0xffffffffu, me ? nbr[s] : 0, src);
+                q1.y = (unsigned)__shfl_sync(0xffffffffu, me ? nbs[s] : 0, src);
+                q1.z = (unsigned)__shfl_sync(0xffffffffu, me ? nbc[s] : 0, src);
+                q1.w = (unsigned)__shfl_sync(0xffffffffu, me ? size[s] : 0, src);
+                q2.x = (unsigned)__shfl_sync(0xffffffffu, me ? cid[s] : 0, src);
+            }
+            if (piece < 3) lc::st_async16(dst_pend[b], dst_bar[b], piece == 0 ? q0 : piece == 1 ? q1 : q2);
+        }
+    };
+
+    int par = 0;
+    unsigned phase[2] = {0u, 0u};
+    int pending = -1;  // row whose bound is being recomputed by the request in flight
+    bool pend_merge = false;
+    {
+        const Top t = warp_rows_top(-1);
+        publish(par, t, INFINITY, -1, -1, rank == 0 && warp == 0);
+    }
+
+    int k = 0, tries = 0;
+    unsigned long long rescans = 0;
+    long long c_dec = 0, c_work = 0, c_pub = 0, c_bar = 0, t0, t1;
+    t1 = clock64();
+    for (;;) {
+        lc::mbar_wait(bar_local[par], phase[par] & 1u);
+        ++phase[par];
+        if (tid == 0) lc::mbar_expect_tx(bar_local[par], kTxBytes);  // re-arm for the round after next
+        t0 = clock64();
+        c_bar += t0 - t1;
+        const ClusterXch<E>& X = xch[par];
+        // ---------------- every warp: reduce the exchange, finish the pending row, pick the request ----------
+        Top m;
+        m.v = INFINITY;
+        m.i = -1;
+        m.c = 0;
+        double pv = INFINITY;
+        int pi = -1;
+#pragma unroll
+        for (int u = 0; u < EPL; ++u) {
+            const int e = lane + 32 * u;
+            if (e < E) {
+                const uint4 a = X.A[e], bq = X.B[e];
+                const int c = (int)a.w;
+                if (c > 0) {
+                    const double v = lc::unpack_d(a);
+                    const int i = (int)a.z;
+                    if (m.c == 0 || v < m.v) {
+                        m.v = v;
+                        m.i = i;
+                        m.c = c;
+                    } else if (v == m.v) {
+                        m.c += c;
+                        m.i = i < m.i ? i : m.i;
+                    }
+                }
+                const int qi = (int)bq.z;
+                if (qi >= 0) {
+                    const double qv = lc::unpack_d(bq);
+                    if (pi < 0 || qv < pv || (qv == pv && qi < pi)) {
+                        pv = qv;
+                        pi = qi;
+                    }
+                }
+            }
+        }
+        Top top = warp_top(m.c ? m.v : INFINITY, m.i, m.c);
+        double td_cur = 0.0;
+        int td_nbr = -1, td_size = 0, td_cid = 0, td_nbs = 0, td_nbc = 0;
+        if (top.i >= 0) {
+            const int e = entry_of(top.i);
+            const uint4 c4 = X.C[e], d4 = X.D[e];
+            td_cur = lc::unpack_d(c4);
+            td_nbr = (int)c4.z;
+            td_size = (int)c4.w;
+            td_cid = (int)d4.x;
+            td_nbs = (int)d4.y;
+            td_nbc = (int)d4.z;
+        }
+        if (pending >= 0) {
+            const Top pt = warp_top(pi >= 0 ? pv : INFINITY, pi, pi >= 0 ? 1 : 0);
+            const uint4 p0 = X.P[0], p1 = X.P[1], p2 = X.P[2];
+            double q_lb = __hiloint2double((int)p0.y, (int)p0.x), q_cur = __hiloint2double((int)p0.w, (int)p0.z);
+            int q_nbr = (int)p1.x, q_nbs = (int)p1.y, q_nbc = (int)p1.z;
+            const int q_size = (int)p1.w, q_cid = (int)p2.x;
+            if (pt.i >= 0) {  // new nearest neighbour (clustering.cpp:395-404 / 259-276)
+                const int e = entry_of(pt.i);
+                q_lb = pt.v;
+                q_cur = pt.v;
+                q_nbr = pt.i;
+                q_nbs = (int)X.B[e].w;
+                q_nbc = (int)X.D[e].w;
+            } else if (!pend_merge) {  // rescan found no live row above x
+                q_lb = INFINITY;
+                q_cur = INFINITY;
+                q_nbr = -1;
+            }
+            if (mine(pending)) {
+                const int s = owner_lg(pending) * 32 + lane;
+                lb[s] = q_lb;
+                cur[s] = q_cur;
+                nbr[s] = q_nbr;
+                nbs[s] = q_nbs;
+                nbc[s] = q_nbc;
+            }
+            if (pending < n - 1) {  // the row re-enters the competition
+                if (top.c == 0 || q_lb < top.v) {
+                    top.v = q_lb;
+                    top.i = pending;
+                    top.c = 1;
+                    td_cur = q_cur;
+                    td_nbr = q_nbr;
+                    td_size = q_size;
+                    td_cid = q_cid;
+                    td_nbs = q_nbs;
+                    td_nbc = q_nbc;
+                } else if (q_lb == top.v) {
+                    top.c += 1;  // tied: the request below aborts, the details no longer matter
+                }
+            }
+        }
+        if (k >= n - 1) break;  // all merges done
+        const int x = top.i;
+        const double dist = top.v;
+        if (top.c != 1 || x < 0 || tries >= n - k) {  // tied minimum: the heap order would matter
+            if (scribe) need_exact[prob] = 1;
+            break;
+        }
+        const int y = td_nbr;
+        par ^= 1;
+        t1 = clock64();
+        c_dec += t1 - t0;
+        if (!(y >= 0 && dist == td_cur)) {
+            // ---------------- rescan row x: first minimum in index order over live i > x ----------------
+            const double* r = w.D + (size_t)x * w.ld;
+            double bv = INFINITY;
+            int bi = -1;
+            for (int lg0 = warp; lg0 < NGl; lg0 += NW * PF) {
+                double d[PF];
+                bool ok[PF];
+#pragma unroll
+                for (int u = 0; u < PF; ++u) {
+                    const int lg = lg0 + u * NW;
+                    const int i = row_of(lg);
+                    ok[u] = lg < NGl && i > x && i < n && size[lg * 32 + lane] != 0;
+                    d[u] = ok[u] ? __ldcg(r + i) : INFINITY;
+                }
+#pragma unroll
+                for (int u = 0; u < PF; ++u)
+                    if (ok[u] && d[u] < bv) {
+                        bv = d[u];
+                        bi = row_of(lg0 + u * NW);
+                    }
+            }
+            const Top part = warp_top(bi >= 0 ? bv : INFINITY, bi, bi >= 0 ? 1 : 0);
+            const Top t = warp_rows_top(x);
+            t0 = clock64();
+            c_work += t0 - t1;
+            publish(par, t, part.i >= 0 ? part.v : INFINITY, part.i, x, false);
+            pending = x;
+            pend_merge = false;
+            ++tries;
+            ++rescans;
+            t1 = clock64();
+            c_pub += t1 - t0;
+            continue;
+        }
+        // ---------------- merge x into y (clustering.cpp:347-404) ----------------
+        const int nx = td_size, ny = td_nbs, ix = td_cid, iy = td_nbc;
+        if (scribe) {
+            double* z = w.Z + 4 * (size_t)k;
+            z[0] = ix < iy ? ix : iy;
+            z[1] = ix < iy ? iy : ix;
+            z[2] = dist;
+            z[3] = nx + ny;
+        }
+        const double* rowx = w.D + (size_t)x * w.ld;
+        double* rowy = w.D + (size_t)y * w.ld;
+        double fx = 0.0, fy = 0.0, fs = 1.0, t3 = 0.0, rs = 1.0;
+        bool have_terms = false;
+        double ymv = INFINITY;
+        int ymi = -1;
+        for (int lg0 = warp; lg0 < NGl; lg0 += NW * PF) {
+            double dx[PF], dy[PF];
+            bool live[PF];
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int lg = lg0 + u * NW;
+                const int z = row_of(lg);
+                live[u] = lg < NGl && z < n && z != x && z != y && size[lg * 32 + lane] != 0;
+                dx[u] = live[u] ? __ldcg(rowx + z) : 0.0;
+                dy[u] = live[u] ? __ldcg(rowy + z) : 0.0;
+            }
+            if (!have_terms) {
+                // centroid update, clustering.cpp:250-256: the third term and the divisor do not depend on z;
+                // computed under the shadow of the loads just issued
+                fx = (double)nx;
+                fy = (double)ny;
+                fs = (double)(nx + ny);
+                t3 = __ddiv_rn(__dmul_rn(__dmul_rn((double)(nx * ny), dist), dist), fs);
+                rs = __drcp_rn(fs);
+                have_terms = true;
+            }
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int lg = lg0 + u * NW;
+                if (lg >= NGl) break;
+                const int z = row_of(lg), s = lg * 32 + lane;
+                if (z == x) size[s] = 0;
+                if (z == y) {
+                    size[s] = nx + ny;
+                    cid[s] = n + k;
+                }
+                if (!live[u]) continue;
+                const double t1q = __dmul_rn(__dmul_rn(fx, dx[u]), dx[u]);
+                const double t2q = __dmul_rn(__dmul_rn(fy, dy[u]), dy[u]);
+                const double nd = __dsqrt_rn(div_by(__dsub_rn(__dadd_rn(t1q, t2q), t3), fs, rs));
+                __stcg(rowy + z, nd);
+                __stcg(w.D + (size_t)z * w.ld + y, nd);
+                if (z < y) {
+                    int nb = nbr[s];
+                    const double lbz = lb[s];
+                    if (z < x && nb == x) nb = y;  // clustering.cpp:374-378
+                    if (nd < lbz) {                // clustering.cpp:381-392
+                        nb = y;
+                        lb[s] = nd;
+                    }
+                    if (nb == y) {  // cur mirrors D[z][nbr[z]]; so do the cached size / id of the candidate
+                        cur[s] = nd;
+                        nbs[s] = nx + ny;
+                        nbc[s] = n + k;
+                    }
+                    nbr[s] = nb;
+                } else if (nd < ymv) {  // rows ascend within a lane: first strict minimum
+                    ymv = nd;
+                    ymi = z;
+                }
+            }
+        }
+        const Top part = warp_top(ymi >= 0 ? ymv : INFINITY, ymi, ymi >= 0 ? 1 : 0);
+        const Top t = warp_rows_top(y);
+        __threadfence();  // the sweep's stores are visible device-wide before any peer can see this publish
+        t0 = clock64();
+        c_work += t0 - t1;
+        publish(par, t, part.i >= 0 ? part.v : INFINITY, part.i, y, false);
+        pending = y;
+        pend_merge = true;
+        ++k;
+        tries = 0;
+        t1 = clock64();
+        c_pub += t1 - t0;
+    }
+    if (scribe && w.stats) {
+        w.stats[0] += rescans;
+        w.stats[3] += c_dec;   // reduce the exchange + decide
+        w.stats[4] += c_work;  // sweep / rescan (+ fence)
+        w.stats[5] += c_pub;   // DSMEM publish
+        w.stats[6] += c_bar;   // mbarrier wait
+        w.stats[7] += (unsigned long long)(n - 1);
+    }
+    lc::cluster_barrier_relaxed();  // no CTA may exit while a peer can still write into its shared memory
+}
+
 // ------------------------------------------------------------------------------------------------
 // fcluster (criterion "distance")
 // ------------------------------------------------------------------------------------------------
@@ -1614,8 +2093,28 @@ static int linkage_fast_launch_mode(sd_ctx* ctx, const LinkWork* d_works, const 
     return SD_OK;
 }
 
+template <int T>
+static int linkage_cluster_launch(sd_ctx* ctx, const LinkWork* d_works, const int* d_ns, int problems, int max_n,
+                                  int* d_need_exact) {
+    const size_t smem = linkcluster_smem_bytes(max_n);
+    static bool configured = false;
+    if (!configured) {
+        SD_CUDA(ctx, cudaFuncSetAttribute(linkage_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+    }
+    linkage_cluster_kernel<T><<<problems * kLcCtas, T, smem, ctx->stream>>>(d_works, d_ns, d_need_exact);
+    SD_LAUNCH_CHECK(ctx);
+    return SD_OK;
+}
+
 static int linkage_fast_dispatch(sd_ctx* ctx, const LinkWork* d_works, const int* d_ns, int problems, int max_n,
                                  int* d_need_exact) {
+    if (ctx->linkage_cluster && linkcluster_smem_bytes(max_n) <= (size_t)190 * 1024) {
+        const int t = ctx->linkage_threads ? ctx->linkage_threads : (max_n <= 4096 ? 128 : max_n <= 12288 ? 256 : 512);
+        if (t <= 128) return linkage_cluster_launch<128>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
+        if (t <= 256) return linkage_cluster_launch<256>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
+        return linkage_cluster_launch<512>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
+    }
     const bool fits = linkfast_smem_bytes(max_n) <= (size_t)220 * 1024;
     const int threads = ctx->linkage_threads ? ctx->linkage_threads : (max_n <= 4096 ? 512 : 1024);
     if (fits && threads == 512) return linkage_fast_launch_mode<LF_SMEM, 512>(ctx, d_works, d_ns, problems, max_n, d_need_exact);

@@ -86,6 +86,7 @@ struct sd_ctx {
     unsigned long long* d_stats = nullptr;  // diagnostic counters (sd_debug_counters)
     int force_exact_linkage = 0;            // test hook: skip the heap-free fast path
     int linkage_threads = 0;                // tuning hook: 0 = auto, 512 or 1024
+    int linkage_cluster = 1;                // 1 = spread the merge loop over an 8-CTA cluster when the state fits
     int stft_variant = 0;                   // tuning hook: 0 = 4 CTAs/SM (<=102 regs), 1 = 3 CTAs/SM
 
     int fail(int code, const char* fmt, ...) {

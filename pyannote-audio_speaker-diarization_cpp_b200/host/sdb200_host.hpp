@@ -18,6 +18,9 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <utility>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -448,6 +451,64 @@ std::vector<Result> to_annotation(const vec2d& scores, const SW& frames, double 
     out.reserve(static_cast<size_t>(n));
     for (int64_t i = 0; i < n; ++i) out.emplace_back(seg[2 * i], seg[2 * i + 1], static_cast<int>(lab[i]));
     return out;
+}
+
+// Ingest: wav::WavReader (frontend/wav.h:62-126) + the /32768 scaling at SD:2948-2951 in one call.  Only the RIFF
+// chunk walk runs on the host; the sample conversion is the device kernel.  16-bit PCM, mono (the reference reads
+// the first num_samples interleaved values of a multi-channel file, i.e. it does not support them either).
+inline std::vector<float> read_wav(const std::string& path, int* sample_rate = nullptr) {
+    FILE* fp = std::fopen(path.c_str(), "rb");
+    if (!fp) throw std::runtime_error("sdb200: cannot open " + path);
+    auto fail = [&](const char* why) {
+        std::fclose(fp);
+        throw std::runtime_error("sdb200: " + path + ": " + why);
+    };
+    unsigned char h[12];
+    if (std::fread(h, 1, 12, fp) != 12 || std::memcmp(h, "RIFF", 4) || std::memcmp(h + 8, "WAVE", 4)) fail("not a RIFF/WAVE file");
+    uint16_t channels = 0, bits = 0;
+    uint32_t rate = 0, data_size = 0;
+    bool have_fmt = false;
+    for (;;) {  // walk sub-chunks until "data" (LIST / fact chunks are skipped, wav.h:84-91)
+        unsigned char ck[8];
+        if (std::fread(ck, 1, 8, fp) != 8) fail("no data chunk");
+        const uint32_t size = ck[4] | (ck[5] << 8) | (ck[6] << 16) | ((uint32_t)ck[7] << 24);
+        if (!std::memcmp(ck, "fmt ", 4)) {
+            unsigned char f[16];
+            if (size < 16 || std::fread(f, 1, 16, fp) != 16) fail("fmt chunk shorter than 16 bytes");
+            channels = f[2] | (f[3] << 8);
+            rate = f[4] | (f[5] << 8) | (f[6] << 16) | ((uint32_t)f[7] << 24);
+            bits = f[14] | (f[15] << 8);
+            std::fseek(fp, size - 16, SEEK_CUR);
+            have_fmt = true;
+        } else if (!std::memcmp(ck, "data", 4)) {
+            data_size = size;
+            break;
+        } else {
+            std::fseek(fp, size, SEEK_CUR);
+        }
+    }
+    if (!have_fmt || bits != 16 || channels != 1) fail("only 16-bit mono PCM is supported");
+    std::vector<int16_t> pcm(data_size / 2);
+    if (std::fread(pcm.data(), 2, pcm.size(), fp) != pcm.size()) fail("truncated data chunk");
+    std::fclose(fp);
+    if (sample_rate) *sample_rate = static_cast<int>(rate);
+    std::vector<float> out(pcm.size());
+    Context& c = context();
+    if (!pcm.empty()) c.check(sd_ingest_pcm16(c.get(), pcm.data(), static_cast<int64_t>(pcm.size()), out.data()));
+    return out;
+}
+
+// SegmentModel::crop (SD:1641-1662) for a batch of windows: one zero-padded chunk per segment start.
+inline vec2f crop(const std::vector<float>& waveform, const std::vector<std::pair<double, double>>& segments,
+                  double duration = 5.0, int sample_rate = 16000) {
+    Context& c = context();
+    std::vector<double> starts;
+    for (const auto& s : segments) starts.push_back(s.first);
+    const size_t L = static_cast<size_t>(std::floor(duration * sample_rate));
+    std::vector<float> flat(L * starts.size());
+    c.check(sd_crop_chunks(c.get(), waveform.data(), static_cast<int64_t>(waveform.size()), starts.data(),
+                           static_cast<int>(starts.size()), duration, sample_rate, flat.data()));
+    return detail::unflatten2<float, float>(flat, starts.size(), L);
 }
 
 }  // namespace sdb200

@@ -44,7 +44,10 @@ static bool same_nan(const std::vector<std::vector<double>>& a, const std::vecto
     return true;
 }
 
-int main() {
+static const char* g_wav_path = nullptr;
+
+int main(int argc, char** argv) {
+    if (argc > 1) g_wav_path = argv[1];
     std::mt19937 rng(7);
     std::uniform_real_distribution<float> U(0.f, 1.f);
     std::normal_distribution<double> G(0.0, 1.0);
@@ -210,6 +213,23 @@ int main() {
         bool lens_ok = true;
         for (int b = 0; b < B; ++b) lens_ok = lens_ok && (cnt[b] < 640 ? (wl[b] == 1.0f && ts[b]) : (wl[b] == cnt[b] / mx && !ts[b]));
         CHECK(ok && same(sig_ref, sig_got) && lens_ok, "masked_signals (interpolate + padSequence + wav_lens)");
+    }
+
+    // ingest: WavReader + scaling, SegmentModel::crop.  The fixture path comes from argv[1] (tests/golden/tiny_list.wav).
+    if (g_wav_path) {
+        wav::WavReader rd(g_wav_path);
+        std::vector<float> ref_w(rd.data(), rd.data() + rd.num_samples());
+        for (auto& v : ref_w) v = v * 1.0f / 32768.0;
+        int sr = 0;
+        auto got_w = sdb200::read_wav(g_wav_path, &sr);
+        CHECK(same(ref_w, got_w) && sr == rd.sample_rate() && !got_w.empty(), "read_wav (WavReader + /32768)");
+        std::vector<float> longw(16000 * 7 + 333);
+        for (auto& v : longw) v = U(rng) - 0.5f;
+        std::vector<std::pair<double, double>> segs = {{0.0, 5.0}, {0.5, 5.5}, {2.25, 7.25}, {6.99, 11.99}};
+        auto got_c = sdb200::crop(longw, segs);
+        bool ok = got_c.size() == segs.size();
+        for (size_t i = 0; ok && i < segs.size(); ++i) ok = same(mm.crop(longw, segs[i]), got_c[i]);
+        CHECK(ok, "crop (SegmentModel::crop)");
     }
 
     // STFT front-end: what reaches emd4.onnx (captured by the ORT stub) vs the shim
