@@ -998,7 +998,7 @@ constexpr int kLcCtas = 8;
 __host__ __device__ inline size_t linkcluster_smem_bytes(int n) {
     const size_t ng = (size_t)(n + 31) / 32;
     const size_t ngl = (ng + kLcCtas - 1) / kLcCtas;
-    return ngl * 32 * (8 + 8 + 5 * 4) + 64;
+    return ngl * 32 * (8 + 8 + 4) + ng * 32 * 8 + 64;  // own rows (lb, cur, nbr) + replicas (size, id)
 }
 
 namespace lc {
@@ -1047,22 +1047,30 @@ __device__ __forceinline__ double unpack_d(const uint4& v) { return __hiloint2do
 }  // namespace lc
 
 // One exchange buffer: four 16-byte pieces per publishing warp + the state of the row being recomputed.
-//   A = (top value, top row, multiplicity)            B = (partial value, partial row, size of that row)
-//   C = (cur[top], nbr[top], size[top])               D = (cid[top], nbs[top], nbc[top], cid of the partial row)
-//   P0 = (lb, cur) P1 = (nbr, nbs, nbc, size) P2 = (cid, -, -, -) of the pending row
+//   A = (smallest bound v1, its row i1, multiplicity c1)      B = (cur[i1], nbr[i1], -)
+//   C = (second smallest bound v2 of the warp, -, -)          D = (partial value, partial row, -)
+//   P0 = (lb, cur) P1 = (nbr, -, -, -) of the pending row (the survivor of the merge just swept)
 template <int E>
 struct __align__(16) ClusterXch {
-    uint4 A[E], B[E], C[E], D[E], P[3];
+    uint4 A[E], B[E], C[E], D[E], P[2];
 };
 
+// Requests that need the whole cluster (a merge sweep, or a refill of the candidate lists) end with an exchange;
+// revalidations of stale candidates (clustering.cpp:329-337) do not: every CTA keeps a replica of the cluster
+// sizes / ids, rescans the row redundantly from the L2-resident matrix and reaches the same result, so a
+// revalidation costs one L2 round trip and one block barrier instead of a DSMEM round.  To keep deciding after
+// a row of some warp has been revalidated, every warp also publishes the value of its second smallest bound:
+// as long as the running minimum stays strictly below it, the rows that warp did not publish cannot matter.
 template <int T>
 __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
     linkage_cluster_kernel(const LinkWork* __restrict__ works, const int* ns, int* __restrict__ need_exact) {
     constexpr int NW = T / 32;
     constexpr int E = kLcCtas * NW;
     constexpr int EPL = (E + 31) / 32;  // exchange entries per lane
-    constexpr int PF = 4;
-    constexpr uint32_t kTxBytes = E * 64 + 48;
+    constexpr int PF = 4;               // sweep groups in flight per warp
+    constexpr int PFR = 8;              // rescan loads in flight per thread
+    constexpr int LOOSE = 4;            // rows revalidated since the last exchange that every warp tracks
+    constexpr uint32_t kTxBytes = E * 64 + 32;
     const int prob = blockIdx.x / kLcCtas;
     int rank;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
@@ -1071,6 +1079,8 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
     extern __shared__ __align__(16) unsigned char lc_smem[];
     __shared__ ClusterXch<E> xch[2];
     __shared__ __align__(8) unsigned long long mbar[2];
+    __shared__ double rs_v[2][NW];
+    __shared__ int rs_i[2][NW];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool scribe = rank == 0 && tid == 0;  // writes Z / flags / counters
     if (scribe) need_exact[prob] = 0;
@@ -1079,13 +1089,13 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
     const int NG = (n + 31) / 32;
     const int NGl = NG > rank ? (NG - rank + kLcCtas - 1) / kLcCtas : 0;  // groups of this CTA: g = lg * 8 + rank
     const int NGmax = (NG + kLcCtas - 1) / kLcCtas;
+    // own rows (private to the owning thread)
     double* lb = reinterpret_cast<double*>(lc_smem);
     double* cur = lb + (size_t)NGmax * 32;
     int* nbr = reinterpret_cast<int*>(cur + (size_t)NGmax * 32);
-    int* nbs = nbr + (size_t)NGmax * 32;
-    int* nbc = nbs + (size_t)NGmax * 32;
-    int* size = nbc + (size_t)NGmax * 32;
-    int* cid = size + (size_t)NGmax * 32;
+    // replicas, all rows: cluster size (0 = dead) and id
+    int* rsize = nbr + (size_t)NGmax * 32;
+    int* rcid = rsize + (size_t)NG * 32;
 
     const uint32_t bar_local[2] = {lc::smem_u32(&mbar[0]), lc::smem_u32(&mbar[1])};
     if (tid == 0) {
@@ -1103,7 +1113,7 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
     for (int b = 0; b < 2; ++b) {
         const uint4* base = piece == 0 ? xch[b].A : piece == 1 ? xch[b].B : piece == 2 ? xch[b].C : xch[b].D;
         dst_piece[b] = lc::mapa(lc::smem_u32(base + (rank * NW + warp)), dst_rank);
-        dst_pend[b] = lc::mapa(lc::smem_u32(&xch[b].P[piece < 3 ? piece : 0]), dst_rank);
+        dst_pend[b] = lc::mapa(lc::smem_u32(&xch[b].P[piece & 1]), dst_rank);
         dst_bar[b] = lc::mapa(bar_local[b], dst_rank);
     }
 
@@ -1115,76 +1125,75 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
 
     for (int lg = warp; lg < NGl; lg += NW) {
         const int z = row_of(lg), s = lg * 32 + lane;
-        size[s] = z < n ? 1 : 0;
-        cid[s] = z;
-        const int nb = z < n - 1 ? w.nbr[z] : -1;
-        nbr[s] = nb;
-        nbs[s] = 1;
-        nbc[s] = nb;
+        nbr[s] = z < n - 1 ? w.nbr[z] : -1;
         lb[s] = z < n - 1 ? w.lb[z] : INFINITY;
         cur[s] = lb[s];
     }
+    for (int i = tid; i < NG * 32; i += T) {
+        rsize[i] = i < n ? 1 : 0;
+        rcid[i] = i;
+    }
+    __syncthreads();
     lc::cluster_barrier_relaxed();  // every mbarrier of the cluster is initialised before the first st.async
 
-    // smallest bound among this warp's live heap rows, `skip` left out
-    auto warp_rows_top = [&](int skip) -> Top {
+    // the two smallest bounds among this warp's live heap rows (skip_a / skip_b left out): (v1, i1, c1) and v2
+    auto warp_rows_top2 = [&](int skip_a, int skip_b, double& v2) -> Top {
         Top m;
         m.v = INFINITY;
         m.i = -1;
         m.c = 0;
+        double second = INFINITY;  // smallest value of this lane not counted in m
         for (int lg = warp; lg < NGl; lg += NW) {
             const int z = row_of(lg), s = lg * 32 + lane;
-            if (z < n - 1 && z != skip && size[s] != 0) {
+            if (z < n - 1 && z != skip_a && z != skip_b && rsize[z] != 0) {
                 const double v = lb[s];
                 if (m.c == 0 || v < m.v) {
+                    if (m.c) second = m.v;  // the old best (and anything tied with it) is now second
                     m.v = v;
                     m.i = z;
                     m.c = 1;
-                } else if (v == m.v)
-                    ++m.c;  // rows ascend within a lane: the stored row stays the lowest
+                } else if (v == m.v) {
+                    ++m.c;
+                } else if (v < second)
+                    second = v;
             }
         }
-        return warp_top(m.c ? m.v : INFINITY, m.i, m.c);
+        const Top t = warp_top(m.c ? m.v : INFINITY, m.i, m.c);
+        // second smallest of the warp: lanes that lost contribute their best, the winner (or lanes tied with it:
+        // a tie aborts the fast path anyway) its own second
+        const bool at_min = m.c > 0 && m.v == t.v;
+        double cand = at_min ? second : (m.c ? m.v : INFINITY);
+        const unsigned hi = (unsigned)__double2hiint(cand);
+        const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? (unsigned)__double2loint(cand) : 0xffffffffu);
+        v2 = __hiloint2double((int)mh, (int)ml);
+        return t;
     };
 
-    // publish this warp's entry (top of its rows + partial nearest neighbour) and, from the warp that owns it,
-    // the state of the pending row, to every CTA of the cluster: one 16-byte st.async per lane
-    auto publish = [&](int b, const Top& t, double pv, int pi, int pend, bool dummy_pend) {
+    // publish this warp's entry and, from the warp that owns it, the state of the pending row, to every CTA of
+    // the cluster: one 16-byte st.async per lane
+    auto publish = [&](int b, const Top& t, double v2, double pv, int pi, int pend, bool dummy_pend) {
         double d_cur = 0.0;
-        int d_nbr = 0, d_size = 0, d_cid = 0, d_nbs = 0, d_nbc = 0, p_size = 0, p_cid = 0;
+        int d_nbr = -1;
         if (t.i >= 0) {
             const int src = t.i & 31, s = owner_lg(t.i) * 32 + src;
             const bool me = lane == src;
             d_cur = __shfl_sync(0xffffffffu, me ? cur[s] : 0.0, src);
             d_nbr = __shfl_sync(0xffffffffu, me ? nbr[s] : 0, src);
-            d_size = __shfl_sync(0xffffffffu, me ? size[s] : 0, src);
-            d_cid = __shfl_sync(0xffffffffu, me ? cid[s] : 0, src);
-            d_nbs = __shfl_sync(0xffffffffu, me ? nbs[s] : 0, src);
-            d_nbc = __shfl_sync(0xffffffffu, me ? nbc[s] : 0, src);
-        }
-        if (pi >= 0) {
-            const int src = pi & 31, s = owner_lg(pi) * 32 + src;
-            const bool me = lane == src;
-            p_size = __shfl_sync(0xffffffffu, me ? size[s] : 0, src);
-            p_cid = __shfl_sync(0xffffffffu, me ? cid[s] : 0, src);
         }
         uint4 v;
         if (piece == 0)
             v = lc::pack(t.v, t.i, t.c);
         else if (piece == 1)
-            v = lc::pack(pv, pi, p_size);
+            v = lc::pack(d_cur, d_nbr, 0);
         else if (piece == 2)
-            v = lc::pack(d_cur, d_nbr, d_size);
-        else {
-            v.x = (unsigned)d_cid;
-            v.y = (unsigned)d_nbs;
-            v.z = (unsigned)d_nbc;
-            v.w = (unsigned)p_cid;
-        }
+            v = lc::pack(v2, 0, 0);
+        else
+            v = lc::pack(pv, pi, 0);
         lc::st_async16(dst_piece[b], dst_bar[b], v);
         const bool own_pend = pend >= 0 ? (owner_rank(pend) == rank && owner_lg(pend) % NW == warp) : dummy_pend;
         if (own_pend) {
-            uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0, q2 = q0;
+            uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
             if (pend >= 0) {
                 const int src = pend & 31, s = owner_lg(pend) * 32 + src;
                 const bool me = lane == src;
@@ -1195,51 +1204,120 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
                 q0.z = (unsigned)__double2loint(q_cur);
                 q0.w = (unsigned)__double2hiint(q_cur);
                 q1.x = (unsigned)__shfl_sync(0xffffffffu, me ? nbr[s] : 0, src);
-                q1.y = (unsigned)__shfl_sync(0xffffffffu, me ? nbs[s] : 0, src);
-                q1.z = (unsigned)__shfl_sync(0xffffffffu, me ? nbc[s] : 0, src);
-                q1.w = (unsigned)__shfl_sync(0xffffffffu, me ? size[s] : 0, src);
-                q2.x = (unsigned)__shfl_sync(0xffffffffu, me ? cid[s] : 0, src);
             }
-            if (piece < 3) lc::st_async16(dst_pend[b], dst_bar[b], piece == 0 ? q0 : piece == 1 ? q1 : q2);
+            if (piece < 2) lc::st_async16(dst_pend[b], dst_bar[b], piece == 0 ? q0 : q1);
         }
     };
 
     int par = 0;
     unsigned phase[2] = {0u, 0u};
-    int pending = -1;  // row whose bound is being recomputed by the request in flight
-    bool pend_merge = false;
+    int pending = -1;        // survivor of the merge whose sweep preceded the exchange in flight
+    int dead = -1;           // the row that merge removed
+    int pend_size = 0, pend_cid = 0;
     {
-        const Top t = warp_rows_top(-1);
-        publish(par, t, INFINITY, -1, -1, rank == 0 && warp == 0);
+        double v2;
+        const Top t = warp_rows_top2(-1, -1, v2);
+        publish(par, t, v2, INFINITY, -1, -1, rank == 0 && warp == 0);
     }
 
-    int k = 0, tries = 0;
-    unsigned long long rescans = 0;
-    long long c_dec = 0, c_work = 0, c_pub = 0, c_bar = 0, t0, t1;
+    int k = 0, tries = 0, rs_par = 0;
+    unsigned long long rescans = 0, refills = 0;
+    long long c_dec = 0, c_work = 0, c_res = 0, c_bar = 0, t0, t1;
     t1 = clock64();
     for (;;) {
         lc::mbar_wait(bar_local[par], phase[par] & 1u);
         ++phase[par];
-        if (tid == 0) lc::mbar_expect_tx(bar_local[par], kTxBytes);  // re-arm for the round after next
+        if (tid == 0) {
+            lc::mbar_expect_tx(bar_local[par], kTxBytes);  // re-arm for the round after next
+            if (pending >= 0) {                            // replicas follow the merge (clustering.cpp:347-358)
+                rsize[dead] = 0;
+                rsize[pending] = pend_size;
+                rcid[pending] = pend_cid;
+            }
+        }
+        __syncthreads();
         t0 = clock64();
         c_bar += t0 - t1;
         const ClusterXch<E>& X = xch[par];
-        // ---------------- every warp: reduce the exchange, finish the pending row, pick the request ----------
-        Top m;
-        m.v = INFINITY;
-        m.i = -1;
-        m.c = 0;
+        // ---------------- every warp: load its share of the exchange ----------------
+        double a_v[EPL], b_cur[EPL], c_v2[EPL];
+        int a_i[EPL], a_c[EPL], b_nbr[EPL];
+        bool used[EPL];
         double pv = INFINITY;
         int pi = -1;
 #pragma unroll
         for (int u = 0; u < EPL; ++u) {
             const int e = lane + 32 * u;
+            a_v[u] = INFINITY;
+            a_i[u] = -1;
+            a_c[u] = 0;
+            b_cur[u] = 0.0;
+            b_nbr[u] = -1;
+            c_v2[u] = INFINITY;
+            used[u] = false;
             if (e < E) {
-                const uint4 a = X.A[e], bq = X.B[e];
-                const int c = (int)a.w;
+                const uint4 a = X.A[e], bq = X.B[e], cq = X.C[e], dq = X.D[e];
+                a_v[u] = lc::unpack_d(a);
+                a_i[u] = (int)a.z;
+                a_c[u] = (int)a.w;
+                b_cur[u] = lc::unpack_d(bq);
+                b_nbr[u] = (int)bq.z;
+                c_v2[u] = lc::unpack_d(cq);
+                const int qi = (int)dq.z;
+                if (qi >= 0) {
+                    const double qv = lc::unpack_d(dq);
+                    if (pi < 0 || qv < pv || (qv == pv && qi < pi)) {
+                        pv = qv;
+                        pi = qi;
+                    }
+                }
+            }
+        }
+        // rows whose bound changed since the exchange was published (same in every warp of the cluster)
+        double l_v[LOOSE], l_cur[LOOSE];
+        int l_i[LOOSE], l_nbr[LOOSE];
+        int nl = 0;
+        if (pending >= 0) {
+            const Top pt = warp_top(pi >= 0 ? pv : INFINITY, pi, pi >= 0 ? 1 : 0);
+            const uint4 p0 = X.P[0], p1 = X.P[1];
+            double q_lb = __hiloint2double((int)p0.y, (int)p0.x), q_cur = __hiloint2double((int)p0.w, (int)p0.z);
+            int q_nbr = (int)p1.x;
+            if (pt.i >= 0) {  // new nearest neighbour of the survivor (clustering.cpp:395-404)
+                q_lb = pt.v;
+                q_cur = pt.v;
+                q_nbr = pt.i;
+            }
+            if (mine(pending)) {
+                const int s = owner_lg(pending) * 32 + lane;
+                lb[s] = q_lb;
+                cur[s] = q_cur;
+                nbr[s] = q_nbr;
+            }
+            if (pending < n - 1) {
+                l_v[0] = q_lb;
+                l_cur[0] = q_cur;
+                l_i[0] = pending;
+                l_nbr[0] = q_nbr;
+                nl = 1;
+            }
+            pending = -1;
+        }
+        // ---------------- pop until a valid candidate, a tie, or a list runs dry ----------------
+        int op = 0;  // 0 merge, 1 refill, 2 abort (need the exact kernel)
+        int x = -1, y = -1;
+        double dist = 0.0;
+        for (;;) {
+            Top m;
+            m.v = INFINITY;
+            m.i = -1;
+            m.c = 0;
+#pragma unroll
+            for (int u = 0; u < EPL; ++u) {
+                // a list whose head was consumed stands in with the value of its second entry (row unknown: -2)
+                const double v = used[u] ? c_v2[u] : a_v[u];
+                const int i = used[u] ? -2 : a_i[u];
+                const int c = used[u] ? (c_v2[u] < INFINITY ? 1 : 0) : a_c[u];
                 if (c > 0) {
-                    const double v = lc::unpack_d(a);
-                    const int i = (int)a.z;
                     if (m.c == 0 || v < m.v) {
                         m.v = v;
                         m.i = i;
@@ -1249,119 +1327,151 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
                         m.i = i < m.i ? i : m.i;
                     }
                 }
-                const int qi = (int)bq.z;
-                if (qi >= 0) {
-                    const double qv = lc::unpack_d(bq);
-                    if (pi < 0 || qv < pv || (qv == pv && qi < pi)) {
-                        pv = qv;
-                        pi = qi;
+            }
+            Top top = warp_top(m.c ? m.v : INFINITY, m.i, m.c);
+            int loose_src = -1;
+#pragma unroll
+            for (int j = 0; j < LOOSE; ++j)
+                if (j < nl) {
+                    if (top.c == 0 || l_v[j] < top.v) {
+                        top.v = l_v[j];
+                        top.i = l_i[j];
+                        top.c = 1;
+                        loose_src = j;
+                    } else if (l_v[j] == top.v)
+                        top.c += 1;
+                }
+            x = top.i;
+            dist = top.v;
+            if (top.c != 1 || x == -1 || tries >= n - k) {  // tied minimum: the heap order would matter
+                op = 2;
+                break;
+            }
+            if (x == -2) {  // the minimum may be a row nobody published: refill the lists
+                op = 1;
+                break;
+            }
+            double x_cur;
+            int x_nbr;
+            if (loose_src >= 0) {
+                x_cur = l_cur[0];
+                x_nbr = l_nbr[0];
+#pragma unroll
+                for (int j = 1; j < LOOSE; ++j)
+                    if (j == loose_src) {
+                        x_cur = l_cur[j];
+                        x_nbr = l_nbr[j];
+                    }
+            } else {
+                const int e = entry_of(x), src = e & 31, uu = e >> 5;
+                double sc = b_cur[0];
+                int sn = b_nbr[0];
+#pragma unroll
+                for (int u = 1; u < EPL; ++u)
+                    if (u == uu) {
+                        sc = b_cur[u];
+                        sn = b_nbr[u];
+                    }
+                x_cur = __shfl_sync(0xffffffffu, sc, src);
+                x_nbr = __shfl_sync(0xffffffffu, sn, src);
+            }
+            y = x_nbr;
+            if (y >= 0 && dist == x_cur) {  // valid candidate (clustering.cpp:329)
+                op = 0;
+                break;
+            }
+            // ---- stale: find_min_dist(x) (clustering.cpp:259-276), redundantly in every CTA ----
+            long long tr0 = clock64();
+            {
+                const double* r = w.D + (size_t)x * w.ld;
+                double bv = INFINITY;
+                int bi = -1;
+                for (int i0 = x + 1 + tid; i0 < n; i0 += T * PFR) {
+                    double d[PFR];
+#pragma unroll
+                    for (int u = 0; u < PFR; ++u) {
+                        const int i = i0 + u * T;
+                        d[u] = i < n ? __ldcg(r + i) : INFINITY;
+                    }
+#pragma unroll
+                    for (int u = 0; u < PFR; ++u) {
+                        const int i = i0 + u * T;
+                        if (i < n && rsize[i] != 0 && d[u] < bv) {
+                            bv = d[u];
+                            bi = i;
+                        }
                     }
                 }
-            }
-        }
-        Top top = warp_top(m.c ? m.v : INFINITY, m.i, m.c);
-        double td_cur = 0.0;
-        int td_nbr = -1, td_size = 0, td_cid = 0, td_nbs = 0, td_nbc = 0;
-        if (top.i >= 0) {
-            const int e = entry_of(top.i);
-            const uint4 c4 = X.C[e], d4 = X.D[e];
-            td_cur = lc::unpack_d(c4);
-            td_nbr = (int)c4.z;
-            td_size = (int)c4.w;
-            td_cid = (int)d4.x;
-            td_nbs = (int)d4.y;
-            td_nbc = (int)d4.z;
-        }
-        if (pending >= 0) {
-            const Top pt = warp_top(pi >= 0 ? pv : INFINITY, pi, pi >= 0 ? 1 : 0);
-            const uint4 p0 = X.P[0], p1 = X.P[1], p2 = X.P[2];
-            double q_lb = __hiloint2double((int)p0.y, (int)p0.x), q_cur = __hiloint2double((int)p0.w, (int)p0.z);
-            int q_nbr = (int)p1.x, q_nbs = (int)p1.y, q_nbc = (int)p1.z;
-            const int q_size = (int)p1.w, q_cid = (int)p2.x;
-            if (pt.i >= 0) {  // new nearest neighbour (clustering.cpp:395-404 / 259-276)
-                const int e = entry_of(pt.i);
-                q_lb = pt.v;
-                q_cur = pt.v;
-                q_nbr = pt.i;
-                q_nbs = (int)X.B[e].w;
-                q_nbc = (int)X.D[e].w;
-            } else if (!pend_merge) {  // rescan found no live row above x
-                q_lb = INFINITY;
-                q_cur = INFINITY;
-                q_nbr = -1;
-            }
-            if (mine(pending)) {
-                const int s = owner_lg(pending) * 32 + lane;
-                lb[s] = q_lb;
-                cur[s] = q_cur;
-                nbr[s] = q_nbr;
-                nbs[s] = q_nbs;
-                nbc[s] = q_nbc;
-            }
-            if (pending < n - 1) {  // the row re-enters the competition
-                if (top.c == 0 || q_lb < top.v) {
-                    top.v = q_lb;
-                    top.i = pending;
-                    top.c = 1;
-                    td_cur = q_cur;
-                    td_nbr = q_nbr;
-                    td_size = q_size;
-                    td_cid = q_cid;
-                    td_nbs = q_nbs;
-                    td_nbc = q_nbc;
-                } else if (q_lb == top.v) {
-                    top.c += 1;  // tied: the request below aborts, the details no longer matter
+                const Top part = warp_top(bi >= 0 ? bv : INFINITY, bi, bi >= 0 ? 1 : 0);
+                if (lane == 0) {
+                    rs_v[rs_par][warp] = part.v;
+                    rs_i[rs_par][warp] = part.i;
+                }
+                __syncthreads();
+                const bool has = lane < NW && rs_i[rs_par][lane < NW ? lane : 0] >= 0;
+                const Top res = warp_top(has ? rs_v[rs_par][lane] : INFINITY, has ? rs_i[rs_par][lane] : -1, has ? 1 : 0);
+                rs_par ^= 1;
+                const double nv = res.i >= 0 ? res.v : INFINITY;
+                if (mine(x)) {
+                    const int s = owner_lg(x) * 32 + lane;
+                    lb[s] = nv;
+                    cur[s] = nv;
+                    nbr[s] = res.i;
+                }
+                ++tries;
+                ++rescans;
+                if (loose_src >= 0) {
+#pragma unroll
+                    for (int j = 0; j < LOOSE; ++j)
+                        if (j == loose_src) {
+                            l_v[j] = nv;
+                            l_cur[j] = nv;
+                            l_nbr[j] = res.i;
+                        }
+                } else {
+                    const int e = entry_of(x);
+                    if (lane == (e & 31)) {
+#pragma unroll
+                        for (int u = 0; u < EPL; ++u)
+                            if (u == (e >> 5)) used[u] = true;
+                    }
+                    if (nl == LOOSE) {  // no room to track another row: republish everything
+                        op = 1;
+                        c_res += clock64() - tr0;
+                        break;
+                    }
+#pragma unroll
+                    for (int j = 0; j < LOOSE; ++j)
+                        if (j == nl) {
+                            l_v[j] = nv;
+                            l_cur[j] = nv;
+                            l_i[j] = x;
+                            l_nbr[j] = res.i;
+                        }
+                    ++nl;
                 }
             }
+            c_res += clock64() - tr0;
         }
-        if (k >= n - 1) break;  // all merges done
-        const int x = top.i;
-        const double dist = top.v;
-        if (top.c != 1 || x < 0 || tries >= n - k) {  // tied minimum: the heap order would matter
+        if (op == 2) {
             if (scribe) need_exact[prob] = 1;
             break;
         }
-        const int y = td_nbr;
         par ^= 1;
         t1 = clock64();
         c_dec += t1 - t0;
-        if (!(y >= 0 && dist == td_cur)) {
-            // ---------------- rescan row x: first minimum in index order over live i > x ----------------
-            const double* r = w.D + (size_t)x * w.ld;
-            double bv = INFINITY;
-            int bi = -1;
-            for (int lg0 = warp; lg0 < NGl; lg0 += NW * PF) {
-                double d[PF];
-                bool ok[PF];
-#pragma unroll
-                for (int u = 0; u < PF; ++u) {
-                    const int lg = lg0 + u * NW;
-                    const int i = row_of(lg);
-                    ok[u] = lg < NGl && i > x && i < n && size[lg * 32 + lane] != 0;
-                    d[u] = ok[u] ? __ldcg(r + i) : INFINITY;
-                }
-#pragma unroll
-                for (int u = 0; u < PF; ++u)
-                    if (ok[u] && d[u] < bv) {
-                        bv = d[u];
-                        bi = row_of(lg0 + u * NW);
-                    }
-            }
-            const Top part = warp_top(bi >= 0 ? bv : INFINITY, bi, bi >= 0 ? 1 : 0);
-            const Top t = warp_rows_top(x);
+        if (op == 1) {  // refill: every warp republishes its two smallest bounds
+            double v2;
+            const Top t = warp_rows_top2(-1, -1, v2);
+            publish(par, t, v2, INFINITY, -1, -1, rank == 0 && warp == 0);
+            ++refills;
             t0 = clock64();
             c_work += t0 - t1;
-            publish(par, t, part.i >= 0 ? part.v : INFINITY, part.i, x, false);
-            pending = x;
-            pend_merge = false;
-            ++tries;
-            ++rescans;
-            t1 = clock64();
-            c_pub += t1 - t0;
+            t1 = t0;
             continue;
         }
         // ---------------- merge x into y (clustering.cpp:347-404) ----------------
-        const int nx = td_size, ny = td_nbs, ix = td_cid, iy = td_nbc;
+        const int nx = rsize[x], ny = rsize[y], ix = rcid[x], iy = rcid[y];
         if (scribe) {
             double* z = w.Z + 4 * (size_t)k;
             z[0] = ix < iy ? ix : iy;
@@ -1382,7 +1492,7 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
             for (int u = 0; u < PF; ++u) {
                 const int lg = lg0 + u * NW;
                 const int z = row_of(lg);
-                live[u] = lg < NGl && z < n && z != x && z != y && size[lg * 32 + lane] != 0;
+                live[u] = lg < NGl && z < n && z != x && z != y && rsize[z] != 0;
                 dx[u] = live[u] ? __ldcg(rowx + z) : 0.0;
                 dy[u] = live[u] ? __ldcg(rowy + z) : 0.0;
             }
@@ -1400,13 +1510,8 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
             for (int u = 0; u < PF; ++u) {
                 const int lg = lg0 + u * NW;
                 if (lg >= NGl) break;
-                const int z = row_of(lg), s = lg * 32 + lane;
-                if (z == x) size[s] = 0;
-                if (z == y) {
-                    size[s] = nx + ny;
-                    cid[s] = n + k;
-                }
                 if (!live[u]) continue;
+                const int z = row_of(lg), s = lg * 32 + lane;
                 const double t1q = __dmul_rn(__dmul_rn(fx, dx[u]), dx[u]);
                 const double t2q = __dmul_rn(__dmul_rn(fy, dy[u]), dy[u]);
                 const double nd = __dsqrt_rn(div_by(__dsub_rn(__dadd_rn(t1q, t2q), t3), fs, rs));
@@ -1420,11 +1525,7 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
                         nb = y;
                         lb[s] = nd;
                     }
-                    if (nb == y) {  // cur mirrors D[z][nbr[z]]; so do the cached size / id of the candidate
-                        cur[s] = nd;
-                        nbs[s] = nx + ny;
-                        nbc[s] = n + k;
-                    }
+                    if (nb == y) cur[s] = nd;  // cur mirrors D[z][nbr[z]]
                     nbr[s] = nb;
                 } else if (nd < ymv) {  // rows ascend within a lane: first strict minimum
                     ymv = nd;
@@ -1432,25 +1533,30 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
                 }
             }
         }
-        const Top part = warp_top(ymi >= 0 ? ymv : INFINITY, ymi, ymi >= 0 ? 1 : 0);
-        const Top t = warp_rows_top(y);
-        __threadfence();  // the sweep's stores are visible device-wide before any peer can see this publish
-        t0 = clock64();
-        c_work += t0 - t1;
-        publish(par, t, part.i >= 0 ? part.v : INFINITY, part.i, y, false);
         pending = y;
-        pend_merge = true;
+        dead = x;
+        pend_size = nx + ny;
+        pend_cid = n + k;
         ++k;
         tries = 0;
-        t1 = clock64();
-        c_pub += t1 - t0;
+        if (k >= n - 1) break;  // that was the last merge: nothing left to exchange
+        const Top part = warp_top(ymi >= 0 ? ymv : INFINITY, ymi, ymi >= 0 ? 1 : 0);
+        double v2;
+        const Top t = warp_rows_top2(x, y, v2);
+        // the sweep's stores are visible device-wide before any peer can see this publish
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        publish(par, t, v2, part.i >= 0 ? part.v : INFINITY, part.i, y, false);
+        t0 = clock64();
+        c_work += t0 - t1;
+        t1 = t0;
     }
     if (scribe && w.stats) {
         w.stats[0] += rescans;
-        w.stats[3] += c_dec;   // reduce the exchange + decide
-        w.stats[4] += c_work;  // sweep / rescan (+ fence)
-        w.stats[5] += c_pub;   // DSMEM publish
-        w.stats[6] += c_bar;   // mbarrier wait
+        w.stats[1] += refills;
+        w.stats[3] += c_dec - c_res;  // reduce the exchange + decide
+        w.stats[4] += c_res;          // revalidation (local row rescans)
+        w.stats[5] += c_work;         // sweep + fence + publish
+        w.stats[6] += c_bar;          // mbarrier wait
         w.stats[7] += (unsigned long long)(n - 1);
     }
     lc::cluster_barrier_relaxed();  // no CTA may exit while a peer can still write into its shared memory
@@ -2110,7 +2216,7 @@ static int linkage_cluster_launch(sd_ctx* ctx, const LinkWork* d_works, const in
 static int linkage_fast_dispatch(sd_ctx* ctx, const LinkWork* d_works, const int* d_ns, int problems, int max_n,
                                  int* d_need_exact) {
     if (ctx->linkage_cluster && linkcluster_smem_bytes(max_n) <= (size_t)190 * 1024) {
-        const int t = ctx->linkage_threads ? ctx->linkage_threads : (max_n <= 4096 ? 128 : max_n <= 12288 ? 256 : 512);
+        const int t = ctx->linkage_threads ? ctx->linkage_threads : (max_n <= 4096 ? 128 : 256);
         if (t <= 128) return linkage_cluster_launch<128>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
         if (t <= 256) return linkage_cluster_launch<256>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
         return linkage_cluster_launch<512>(ctx, d_works, d_ns, problems, max_n, d_need_exact);

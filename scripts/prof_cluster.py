@@ -28,6 +28,6 @@ dt = (time.perf_counter() - t0) / reps
 c = ctx.debug_counters().astype(float)
 N = int((~np.isnan(emb[:, :, 0])).sum())
 m = max(c[7], 1.0)
-print("N=%d clusters=%d: %.2f ms per clustering; per merge: %.2f stale revalidations, cycles pop %.0f / revalidate %.0f / "
-      "sweep %.0f / barrier %.0f; fallbacks to heap kernel %d"
-      % (N, k, dt * 1e3, c[0] / m, c[3] / m, c[4] / m, c[5] / m, c[6] / m, int(c[2])))
+print("N=%d clusters=%d: %.2f ms per clustering; per merge: %.2f stale revalidations, cycles decide %.0f / revalidate %.0f / "
+      "sweep+publish %.0f / wait %.0f; refills %d; fallbacks to heap kernel %d"
+      % (N, k, dt * 1e3, c[0] / m, c[3] / m, c[4] / m, c[5] / m, c[6] / m, int(c[1]), int(c[2])))
