@@ -992,7 +992,8 @@ __global__ void __launch_bounds__(T)
 // CTA reduces the same 8*NW entries and reaches the same decision: nothing has to be broadcast.
 // The distance matrix stays in global memory (L2-resident).  Entries written by one CTA and read by another
 // are ordered by a __threadfence() between the sweep's stores and the publish (merge requests only) and are
-// read with ld.global.cg.
+// read with ld.global.cg after a cluster-scope acquire on the mbarrier (measured: the weaker CTA-scope wait,
+// which drops the CCTL.IVALL the compiler adds, does not change the run time).
 constexpr int kLcCtas = 8;
 
 __host__ __device__ inline size_t linkcluster_smem_bytes(int n) {
@@ -1543,8 +1544,7 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
         const Top part = warp_top(ymi >= 0 ? ymv : INFINITY, ymi, ymi >= 0 ? 1 : 0);
         double v2;
         const Top t = warp_rows_top2(x, y, v2);
-        // the sweep's stores are visible device-wide before any peer can see this publish
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        __threadfence();  // the sweep's stores are visible device-wide before any peer can see this publish
         publish(par, t, v2, part.i >= 0 ? part.v : INFINITY, part.i, y, false);
         t0 = clock64();
         c_work += t0 - t1;
