@@ -254,6 +254,45 @@ def test_linkage_fast_and_exact_paths_agree(ctx, oracle, pkg, synth):
     assert np.array_equal(Zg, oracle.linkage(grid)) and c[2] == 1  # tied minimum -> handed to the heap kernel
 
 
+@pytest.mark.parametrize("N,D,seed", [(2, 3, 1), (3, 5, 2), (33, 8, 3), (257, 16, 4), (1000, 24, 5), (2049, 12, 6),
+                                      (4100, 8, 7)])
+def test_linkage_cluster_one_cta_and_heap_kernels_agree(ctx, oracle, pkg, N, D, seed):
+    """The three merge-loop kernels (8-CTA cluster at 128/256/512 threads, one CTA, heap) give the reference's Z."""
+    rng = np.random.default_rng(seed)
+    cen = rng.standard_normal((5, D)) * 2.5
+    x = cen[rng.integers(0, 5, N)] + rng.standard_normal((N, D)) * 0.7
+    Zo = oracle.linkage(x)
+    SD_OPT_LINKAGE_THREADS, SD_OPT_LINKAGE_CLUSTER = 2, 4
+    try:
+        for threads in (0, 128, 256, 512):
+            ctx.set_option(SD_OPT_LINKAGE_THREADS, threads)
+            ctx.debug_counters()
+            assert np.array_equal(ctx.linkage(x), Zo), ("cluster", threads)
+            assert ctx.debug_counters()[2] == 0
+        ctx.set_option(SD_OPT_LINKAGE_CLUSTER, 0)
+        for threads in (512, 1024):
+            ctx.set_option(SD_OPT_LINKAGE_THREADS, threads)
+            assert np.array_equal(ctx.linkage(x), Zo), ("one CTA", threads)
+        ctx.set_option(pkg.SD_OPT_FORCE_EXACT_LINKAGE, 1)
+        assert np.array_equal(ctx.linkage(x), Zo), "heap"
+    finally:
+        ctx.set_option(pkg.SD_OPT_FORCE_EXACT_LINKAGE, 0)
+        ctx.set_option(SD_OPT_LINKAGE_CLUSTER, 1)
+        ctx.set_option(SD_OPT_LINKAGE_THREADS, 0)
+
+
+def test_linkage_cluster_kernel_hands_ties_to_heap_kernel(ctx, oracle):
+    """Duplicate rows and lattices tie the minimum: the cluster kernel must raise the flag, never guess."""
+    rng = np.random.default_rng(11)
+    base = rng.standard_normal((40, 6))
+    x = np.concatenate([base, base[:17], base[5:9], np.zeros((3, 6)) + 0.5])
+    ctx.debug_counters()
+    assert np.array_equal(ctx.linkage(x), oracle.linkage(x))
+    assert ctx.debug_counters()[2] == 1
+    lat = np.stack(np.meshgrid(np.arange(9.0), np.arange(8.0), np.arange(3.0)), -1).reshape(-1, 3)
+    assert np.array_equal(ctx.linkage(lat), oracle.linkage(lat))
+
+
 def test_linkage_golden_toy_and_ties(ctx, golden_dir):
     d = g(golden_dir, "linkage_small.npz")
     assert np.array_equal(ctx.linkage(d["toy"]), d["toy_Z"])
