@@ -112,15 +112,24 @@ SD_HD void stft_phase1(const float* sig, int fa_off, int fb_off, const float (&w
     }
 }
 
-// Padded staging: PAD extra floats are inserted after every kHop samples of the tile, so frame f starts at
-// f * (kHop + PAD) and sample 20*n1 + r of a frame sits kSigPad(n1) floats further.  With PAD = 10 the frame-pair
-// bases of consecutive 20-thread groups differ by 340 = 20 (mod 32) banks: the lanes of the two groups that share
-// a warp then cover all 32 banks exactly once -> conflict-free 4-byte reads.  PAD = 12 is used instead: the segment
-// stride (172 floats = 688 B) stays 16-byte aligned, which the bulk (TMA) copies need, at the price of a 2-way
-// conflict on 4 of the 32 lanes.
-constexpr int kPad = 12;
-constexpr int kHopP = kHop + kPad;
-SD_HD constexpr int sig_pad(int n1) { return kPad * ((20 * n1) / kHop); }
+// Padded staging: extra floats are inserted after every kHop samples of the tile, alternately kPadEven and kPadOdd,
+// so frame pair g starts at g * (2*kHop + kPadEven + kPadOdd) = 340 g = 20 g (mod 32) banks: the lanes of the two or
+// three 20-thread groups that share a warp then cover distinct banks -> conflict-free 4-byte reads (a uniform pad
+// would have to be 10 = 2 (mod 4) floats, which breaks the 16-byte alignment the bulk (TMA) copies need; 8 and 12
+// keep every segment 16-byte aligned).  Tiles start at an even frame, so segment parity == frame parity.
+constexpr int kPadEven = 8;    // after an even hop segment
+constexpr int kPadOdd = 12;    // after an odd hop segment
+constexpr int kPairStride = 2 * kHop + kPadEven + kPadOdd;  // floats between the first frames of consecutive pairs
+// padded position of sample j of the tile
+SD_HD constexpr int sig_pos(int j) {
+    return j + (kPadEven + kPadOdd) * ((j / kHop) / 2) + kPadEven * ((j / kHop) & 1);
+}
+SD_HD constexpr int sig_frame_off(int f) { return sig_pos(f * kHop); }  // padded position of frame f's first sample
+// extra offset of sample 20*n1 + r of an even / odd frame (the frame crosses two segment boundaries)
+SD_HD constexpr int sig_pad_even(int n1) { return (20 * n1) / kHop == 0 ? 0 : (20 * n1) / kHop == 1 ? kPadEven : kPadEven + kPadOdd; }
+SD_HD constexpr int sig_pad_odd(int n1) { return (20 * n1) / kHop == 0 ? 0 : (20 * n1) / kHop == 1 ? kPadOdd : kPadEven + kPadOdd; }
+// floats needed to stage n samples
+SD_HD constexpr int sig_padded_size(int n) { return sig_pos(n - 1) + 1; }
 
 // Twiddle table layout.  A row of 20 float2 does not fit the 16 eight-byte banks: in a half-warp that holds
 // lanes r = a..19 of one group and r' = 0..a-5 of the next, roles 16..19 would alias roles 0..3.  So roles 0..15
@@ -151,7 +160,7 @@ SD_HD void stft_phase1_tab(const float* sig, int fa_off, int fb_off, const float
     for (int n1 = 0; n1 < 20; ++n1) {
         const int o = 20 * n1 + r;
         const float w = wtab[o];
-        v[n1] = make_float2(sig[fa_off + o + sig_pad(n1)] * w, sig[fb_off + o + sig_pad(n1)] * w);
+        v[n1] = make_float2(sig[fa_off + o + sig_pad_even(n1)] * w, sig[fb_off + o + sig_pad_odd(n1)] * w);
     }
     dft20(v);
     float2* dst = xchg + g * kGroupStride + r;
@@ -243,8 +252,8 @@ SD_HD void stft_phase3_fast(const float2* zbuf, int g, int r, float* outA, float
 // (and Z[0] for the k = 0 bin) into a 201-entry buffer indexed by j - 200.
 constexpr int kZStride = 212;  // float2 units per group (201 used); 212 - 20 = 12 * 16 keeps the stores conflict-free
 
-SD_HD void stft_publish_upper(const float2 (&v)[20], int g, int r, float2* zup) {
-    float2* dst = zup + g * kZStride + r;
+SD_HD void stft_publish_upper(const float2 (&v)[20], int g, int r, float2* zup, int zstride = kZStride) {
+    float2* dst = zup + g * zstride + r;
 #pragma unroll
     for (int k2 = 10; k2 < 20; ++k2) dst[20 * (k2 - 10)] = v[dft20_slot(k2)];  // Z[200 + r + 20 (k2 - 10)]
     if (r == 0) dst[200] = v[dft20_slot(0)];                                   // Z[400] == Z[0] (periodicity)
@@ -252,8 +261,9 @@ SD_HD void stft_publish_upper(const float2 (&v)[20], int g, int r, float2* zup) 
 
 // Spectrum scaled by 1/2 (folded into the window): A[k] = Z[k] + conj Z[400-k], B[k] = -i (Z[k] - conj Z[400-k]).
 template <bool HAS_A, bool HAS_B>
-SD_HD void stft_split_store(const float2 (&v)[20], const float2* zup, int g, int r, float* outA, float* outB) {
-    const float2* zu = zup + g * kZStride;  // zu[j - 200] = Z[j]
+SD_HD void stft_split_store(const float2 (&v)[20], const float2* zup, int g, int r, float* outA, float* outB,
+                            int zstride = kZStride) {
+    const float2* zu = zup + g * zstride;  // zu[j - 200] = Z[j]
     float2* oa = reinterpret_cast<float2*>(outA);
     float2* ob = reinterpret_cast<float2*>(outB);
     const float2* zm = zu + 200 - r;  // Z[400 - (r + 20 m)] = zu[200 - r - 20 m]

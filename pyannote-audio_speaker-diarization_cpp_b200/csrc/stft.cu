@@ -24,14 +24,15 @@ struct StftCfg {
     static constexpr int kThreads = GROUPS * kRadix;
     static constexpr int kTileFrames = GROUPS * 2;
     static constexpr int kSigFloats = (kTileFrames - 1) * kHop + kNfft;  // samples covered by one tile
-    static constexpr int kSigHops = (kSigFloats + kHop - 1) / kHop;      // hop-sized segments, each padded
-    static constexpr int kSigPadded = kSigFloats + kPad * kSigHops + 4;  // staged floats
+    static constexpr int kSigPadded = sig_padded_size(kSigFloats) + 4;   // staged floats (hop segments padded 8 / 12)
     static constexpr size_t kSigBytes = (size_t)((kSigPadded + 3) / 4 * 4) * sizeof(float);
     static constexpr size_t kZBytes = (size_t)GROUPS * kZStride * sizeof(float2);
-    // the upper-spectrum buffer shares storage with the staged samples (dead after phase 1)
-    static constexpr size_t kSmemBytes = (kSigBytes > kZBytes ? kSigBytes : kZBytes) +
-                                         (size_t)GROUPS * kGroupStride * sizeof(float2) + kNfft * sizeof(float) +
-                                         kTwTableUnits * sizeof(float2);
+    static constexpr size_t kTablesBytes = (size_t)GROUPS * kGroupStride * sizeof(float2) + kNfft * sizeof(float) +
+                                           kTwTableUnits * sizeof(float2);
+    // fbank kernel: the upper-spectrum buffer shares storage with the staged samples (dead after phase 1)
+    static constexpr size_t kSmemBytes = (kSigBytes > kZBytes ? kSigBytes : kZBytes) + kTablesBytes;
+    // STFT kernel: the upper spectrum goes into the (dead) transpose buffer, the sample buffer is not aliased
+    static constexpr size_t kSmemBytesStft = kSigBytes + kTablesBytes;
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -49,7 +50,7 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 // Stage the samples of an edge tile (item b, frames [t0, t0 + kTileFrames)) into the padded buffer: sample j of
-// the tile (item index t0*hop - n_fft/2 + j) goes to sig[j + kPad * (j / kHop)].  Out-of-range samples are the
+// the tile (item index t0*hop - n_fft/2 + j) goes to sig[sig_pos(j)].  Out-of-range samples are the
 // zeros of torch::stft's centre padding (pad_mode "constant").  16-byte pieces never straddle a hop boundary.
 template <int GROUPS>
 __device__ __forceinline__ void stage_tile(float* sig, const float* __restrict__ wav, int L, long tile,
@@ -63,7 +64,7 @@ __device__ __forceinline__ void stage_tile(float* sig, const float* __restrict__
         for (int c = threadIdx.x; c < Cfg::kSigFloats / 4; c += Cfg::kThreads) {
             const int j = 4 * c;
             const long s = s0 + j;
-            float* dst = sig + j + kPad * (j / kHop);
+            float* dst = sig + sig_pos(j);
             if (s >= 0 && s + 3 < L)
                 cp_async16(dst, src + s);
             else {
@@ -78,7 +79,7 @@ __device__ __forceinline__ void stage_tile(float* sig, const float* __restrict__
     } else {
         for (int j = threadIdx.x; j < Cfg::kSigFloats; j += Cfg::kThreads) {
             const long s = s0 + j;
-            float* dst = sig + j + kPad * (j / kHop);
+            float* dst = sig + sig_pos(j);
             if (s >= 0 && s < L)
                 cp_async4(dst, src + s);
             else
@@ -100,13 +101,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
+        "WAIT_LOOP_%=:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_LOOP_%=;\n"
+        "DONE_%=:\n"
         "}\n" ::"r"(a),
-        "r"(parity));
+        "r"(parity)
+        : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
@@ -126,7 +128,7 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     float2* twT = xbuf + GROUPS * kGroupStride;                         // twiddle table (see tw_thread_offset)
     float* wtab = reinterpret_cast<float*>(twT + kTwTableUnits);        // window, pre-scaled by 1/2
     float* sig = wtab + kNfft;                                          // padded samples of the tile
-    float2* zup = reinterpret_cast<float2*>(sig);                       // upper half of the spectrum (aliases sig)
+    float2* zup = xbuf;  // upper half of the spectrum: reuses the transpose buffer once phase 2 has loaded it
     __shared__ __align__(8) uint64_t bar;
 
     const int g = threadIdx.x / kRadix;
@@ -158,46 +160,57 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
 #pragma unroll 1
         for (int j = 0; j < Cfg::kSigFloats; j += kHop) {
             const int n = (Cfg::kSigFloats - j) < kHop ? (Cfg::kSigFloats - j) : kHop;
-            bulk_g2s(sig + j + kPad * (j / kHop), src + j, n * sizeof(float), &bar);
+            bulk_g2s(sig + sig_pos(j), src + j, n * sizeof(float), &bar);
         }
     };
 
+    // Only thread 0 polls the mbarrier (a polling warp burns issue slots: with every warp polling, 16 % of the
+    // kernel's issued instructions were try_wait / branch / yield); the others learn about the arrival through the
+    // block barrier that follows, which is the barrier the tile loop needs anyway.
     unsigned parity = 0;
     long tile = blockIdx.x;
     bool fetched = false;
     if (tile < total_tiles && interior(tile)) {
-        if (threadIdx.x == 0) issue_bulk(tile);
+        if (threadIdx.x == 0) {
+            issue_bulk(tile);
+            mbar_wait(&bar, parity);
+        }
+        parity ^= 1;
         fetched = true;
+        __syncthreads();
     }
     for (; tile < total_tiles; tile += gridDim.x) {
-        if (fetched) {
-            mbar_wait(&bar, parity);
-            parity ^= 1;
-        } else {
+        if (!fetched) {
             stage_tile<GROUPS>(sig, wav, L, tile, tiles_per_item, aligned16 != 0);
             cp_async_commit();
             cp_async_wait<0>();
             __syncthreads();
         }
-        stft_phase1_tab(sig, (2 * g) * kHopP, (2 * g + 1) * kHopP, wtab, twp, g, r, xbuf);
-        __syncthreads();  // sig is free again, the transpose is complete
+        stft_phase1_tab(sig, sig_frame_off(2 * g), sig_frame_off(2 * g + 1), wtab, twp, g, r, xbuf);
+        __syncthreads();  // the transpose is complete and sig is free: the next tile's samples may land already,
+                          // under the shadow of phase 2 and the stores
+        const long next = tile + gridDim.x;
+        fetched = next < total_tiles && interior(next);
+        if (fetched && threadIdx.x == 0) issue_bulk(next);
         float2 v[20];
         stft_phase2_load(xbuf, g, r, v);
-        stft_publish_upper(v, g, r, zup);
-        __syncthreads();  // upper halves are visible; xbuf may be overwritten by the next tile's phase 1
+        __syncthreads();  // every row of the transpose buffer is in registers: it now receives the upper halves
+        stft_publish_upper(v, g, r, zup, kGroupStride);
+        __syncthreads();  // upper halves are visible
 
         const int b = (int)(tile / tiles_per_item);
         const int ti = (int)(tile - (long)b * tiles_per_item);
         const int tA = ti * Cfg::kTileFrames + 2 * g;
         float* rowA = out + ((size_t)b * T + tA) * (kBins * 2);
         if (tA + 1 < T)
-            stft_split_store<true, true>(v, zup, g, r, rowA, rowA + kBins * 2);
+            stft_split_store<true, true>(v, zup, g, r, rowA, rowA + kBins * 2, kGroupStride);
         else if (tA < T)
-            stft_split_store<true, false>(v, zup, g, r, rowA, nullptr);
-        __syncthreads();  // zup (which aliases sig) is consumed: the next tile's samples may land
-        const long next = tile + gridDim.x;
-        fetched = next < total_tiles && interior(next);
-        if (fetched && threadIdx.x == 0) issue_bulk(next);
+            stft_split_store<true, false>(v, zup, g, r, rowA, nullptr, kGroupStride);
+        if (fetched) {
+            if (threadIdx.x == 0) mbar_wait(&bar, parity);  // the next tile's samples have landed
+            parity ^= 1;
+        }
+        __syncthreads();  // zup (the transpose buffer) is consumed: the next tile's phase 1 may overwrite it
     }
 }
 
@@ -274,7 +287,7 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
 #pragma unroll 1
         for (int j = 0; j < Cfg::kSigFloats; j += kHop) {
             const int n = (Cfg::kSigFloats - j) < kHop ? (Cfg::kSigFloats - j) : kHop;
-            bulk_g2s(sig + j + kPad * (j / kHop), src + j, n * sizeof(float), &bar);
+            bulk_g2s(sig + sig_pos(j), src + j, n * sizeof(float), &bar);
         }
     };
 
@@ -295,7 +308,7 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
             cp_async_wait<0>();
             __syncthreads();
         }
-        stft_phase1_tab(sig, (2 * g) * kHopP, (2 * g + 1) * kHopP, wtab, twp, g, r, xbuf);
+        stft_phase1_tab(sig, sig_frame_off(2 * g), sig_frame_off(2 * g + 1), wtab, twp, g, r, xbuf);
         __syncthreads();
         float2 v[20];
         stft_phase2_load(xbuf, g, r, v);
@@ -480,9 +493,9 @@ static int launch_cfg(sd_ctx* ctx, const float* d_wav, int B, int L, int T, floa
     static int blocks_per_sm = 0;
     if (!blocks_per_sm) {
         SD_CUDA(ctx, cudaFuncSetAttribute(stft400_kernel<GROUPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)Cfg::kSmemBytes));
+                                          (int)Cfg::kSmemBytesStft));
         SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, stft400_kernel<GROUPS, MINB>,
-                                                                   Cfg::kThreads, Cfg::kSmemBytes));
+                                                                   Cfg::kThreads, Cfg::kSmemBytesStft));
         if (blocks_per_sm < 1) blocks_per_sm = 1;
     }
     const int tiles_per_item = (T + Cfg::kTileFrames - 1) / Cfg::kTileFrames;
@@ -490,7 +503,7 @@ static int launch_cfg(sd_ctx* ctx, const float* d_wav, int B, int L, int T, floa
     long grid = (long)ctx->num_sms * blocks_per_sm;
     if (grid > total) grid = total;
     const int aligned = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_wav) & 15) == 0);
-    stft400_kernel<GROUPS, MINB><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream>>>(
+    stft400_kernel<GROUPS, MINB><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytesStft, ctx->stream>>>(
         d_wav, d_out, L, T, tiles_per_item, total, ctx->d_window, reinterpret_cast<const float2*>(ctx->d_twiddle),
         aligned);
     SD_LAUNCH_CHECK(ctx);

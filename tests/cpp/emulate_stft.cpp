@@ -37,9 +37,9 @@ int main() {
         stft_phase3(zbuf.data(), g, t % kRadix, &out[(2 * g) * kBins * 2], &out[(2 * g + 1) * kBins * 2]);
     }
     // variant B (the kernel's): padded staging, shared window / twiddle tables, one exchange buffer
-    std::vector<float> sigp(nsig + kPad * (nsig / kHop + 1) + 8, 0.f), out2(frames * kBins * 2, 0.f), wtab(w);
+    std::vector<float> sigp(sig_padded_size(nsig) + 8, 0.f), out2(frames * kBins * 2, 0.f), wtab(w);
     for (auto& v : wtab) v *= 0.5f;  // the kernel folds the 1/2 of the real-pair split into the window
-    for (int j = 0; j < nsig; ++j) sigp[j + kPad * (j / kHop)] = sig[j];
+    for (int j = 0; j < nsig; ++j) sigp[sig_pos(j)] = sig[j];
     std::vector<float2> twT(kTwTableUnits), xb(groups * kGroupStride);
     for (int e = 0; e < kTwTableUnits; ++e) {
         const int src = tw_table_source(e), r = src / 20, k1 = src % 20;
@@ -56,27 +56,42 @@ int main() {
             owner[bank] = u;
         }
     }
+    // bank check of the padded sample layout: every warp must hit 32 distinct 4-byte banks
+    for (int wp = 0; wp < nthreads / 32; ++wp)
+        for (int n1 = 0; n1 < 20; ++n1)
+            for (int fr = 0; fr < 2; ++fr) {
+                int owner[32];
+                for (int b = 0; b < 32; ++b) owner[b] = -1;
+                for (int t = 32 * wp; t < 32 * wp + 32; ++t) {
+                    const int g = t / kRadix, r = t % kRadix;
+                    const int a = sig_frame_off(2 * g + fr) + 20 * n1 + r + (fr ? sig_pad_odd(n1) : sig_pad_even(n1));
+                    if (a != sig_pos((2 * g + fr) * kHop + 20 * n1 + r)) { printf("sig_pos mismatch\n"); return 4; }
+                    if (owner[a % 32] != -1 && owner[a % 32] != a) { printf("sample bank conflict in warp %d\n", wp); return 4; }
+                    owner[a % 32] = a;
+                }
+            }
     std::vector<std::vector<float2>> regs(nthreads, std::vector<float2>(20));
     for (int t = 0; t < nthreads; ++t) {
         int g = t / kRadix, r = t % kRadix;
-        stft_phase1_tab(sigp.data(), (2 * g) * kHopP, (2 * g + 1) * kHopP, wtab.data(), twT.data() + tw_thread_offset(t), g, r, xb.data());
+        stft_phase1_tab(sigp.data(), sig_frame_off(2 * g), sig_frame_off(2 * g + 1), wtab.data(), twT.data() + tw_thread_offset(t), g, r, xb.data());
     }
     for (int t = 0; t < nthreads; ++t) {
         float2 v[20];
         stft_phase2_load(xb.data(), t / kRadix, t % kRadix, v);
         for (int i = 0; i < 20; ++i) regs[t][i] = v[i];
     }
-    std::vector<float2> zup(groups * kZStride);
+    std::vector<float2> zup(groups * kGroupStride);  // the kernel reuses the transpose buffer (stride kGroupStride)
     for (int t = 0; t < nthreads; ++t) {  // compact second exchange: only Z[200..400] crosses threads
         float2 v[20];
         for (int i = 0; i < 20; ++i) v[i] = regs[t][i];
-        stft_publish_upper(v, t / kRadix, t % kRadix, zup.data());
+        stft_publish_upper(v, t / kRadix, t % kRadix, zup.data(), kGroupStride);
     }
     for (int t = 0; t < nthreads; ++t) {
         int g = t / kRadix;
         float2 v[20];
         for (int i = 0; i < 20; ++i) v[i] = regs[t][i];
-        stft_split_store<true, true>(v, zup.data(), g, t % kRadix, &out2[(2 * g) * kBins * 2], &out2[(2 * g + 1) * kBins * 2]);
+        stft_split_store<true, true>(v, zup.data(), g, t % kRadix, &out2[(2 * g) * kBins * 2], &out2[(2 * g + 1) * kBins * 2],
+                                     kGroupStride);
     }
     for (size_t i = 0; i < out.size(); ++i)
         if (out[i] != out2[i] && !(out[i] == 0.f && out2[i] == 0.f)) {
