@@ -19,6 +19,7 @@
 
 #include <cooperative_groups.h>
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 
@@ -996,10 +997,14 @@ __global__ void __launch_bounds__(T)
 // which drops the CCTL.IVALL the compiler adds, does not change the run time).
 constexpr int kLcCtas = 8;
 
-__host__ __device__ inline size_t linkcluster_smem_bytes(int n) {
+// own rows (lb, cur, nbr, alive) + -- unless they live in global memory -- the replicas of cluster size / id
+__host__ __device__ inline size_t linkcluster_smem_bytes(int n, bool global_replicas) {
     const size_t ng = (size_t)(n + 31) / 32;
     const size_t ngl = (ng + kLcCtas - 1) / kLcCtas;
-    return ngl * 32 * (8 + 8 + 4) + ng * 32 * 8 + 64;  // own rows (lb, cur, nbr) + replicas (size, id)
+    return ngl * 32 * (8 + 8 + 4 + 4) + (global_replicas ? 0 : ng * 32 * 8) + 64;
+}
+__host__ __device__ inline size_t linkcluster_global_bytes(int n) {  // replicas of all 8 CTAs
+    return (size_t)kLcCtas * ((size_t)(n + 31) / 32 * 32) * 8 + 256;
 }
 
 namespace lc {
@@ -1062,14 +1067,13 @@ struct __align__(16) ClusterXch {
 // revalidation costs one L2 round trip and one block barrier instead of a DSMEM round.  To keep deciding after
 // a row of some warp has been revalidated, every warp also publishes the value of its second smallest bound:
 // as long as the running minimum stays strictly below it, the rows that warp did not publish cannot matter.
-template <int T>
+template <int T, bool GREPL>
 __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
     linkage_cluster_kernel(const LinkWork* __restrict__ works, const int* ns, int* __restrict__ need_exact) {
     constexpr int NW = T / 32;
     constexpr int E = kLcCtas * NW;
     constexpr int EPL = (E + 31) / 32;  // exchange entries per lane
-    constexpr int PF = 4;               // sweep groups in flight per warp
-    constexpr int PFR = 8;              // rescan loads in flight per thread
+    constexpr int PF = 4;               // sweep / rescan groups in flight per warp
     constexpr int LOOSE = 4;            // rows revalidated since the last exchange that every warp tracks
     constexpr uint32_t kTxBytes = E * 64 + 32;
     const int prob = blockIdx.x / kLcCtas;
@@ -1079,9 +1083,8 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
     const int n = ns[prob];
     extern __shared__ __align__(16) unsigned char lc_smem[];
     __shared__ ClusterXch<E> xch[2];
-    __shared__ __align__(8) unsigned long long mbar[2];
-    __shared__ double rs_v[2][NW];
-    __shared__ int rs_i[2][NW];
+    __shared__ __align__(16) uint4 rx[2][E];  // revalidation exchange: (partial value, partial row) per warp
+    __shared__ __align__(8) unsigned long long mbar[2], rbar[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool scribe = rank == 0 && tid == 0;  // writes Z / flags / counters
     if (scribe) need_exact[prob] = 0;
@@ -1094,28 +1097,39 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
     double* lb = reinterpret_cast<double*>(lc_smem);
     double* cur = lb + (size_t)NGmax * 32;
     int* nbr = reinterpret_cast<int*>(cur + (size_t)NGmax * 32);
-    // replicas, all rows: cluster size (0 = dead) and id
-    int* rsize = nbr + (size_t)NGmax * 32;
+    int* alive = nbr + (size_t)NGmax * 32;
+    // replicas, all rows: cluster size and id -- in shared memory, or (large N) this CTA's copy in global memory
+    int* rsize = GREPL ? reinterpret_cast<int*>(w.fast_scratch) + (size_t)rank * 2 * NG * 32 : alive + (size_t)NGmax * 32;
     int* rcid = rsize + (size_t)NG * 32;
 
+    constexpr uint32_t kRxBytes = E * 16;
     const uint32_t bar_local[2] = {lc::smem_u32(&mbar[0]), lc::smem_u32(&mbar[1])};
+    const uint32_t rbar_local[2] = {lc::smem_u32(&rbar[0]), lc::smem_u32(&rbar[1])};
     if (tid == 0) {
-        lc::mbar_init(bar_local[0], 1);
-        lc::mbar_init(bar_local[1], 1);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            lc::mbar_init(bar_local[b], 1);
+            lc::mbar_init(rbar_local[b], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        lc::mbar_expect_tx(bar_local[0], kTxBytes);
-        lc::mbar_expect_tx(bar_local[1], kTxBytes);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            lc::mbar_expect_tx(bar_local[b], kTxBytes);
+            lc::mbar_expect_tx(rbar_local[b], kRxBytes);
+        }
     }
     // this lane's st.async destination: CTA (lane & 7), piece (lane >> 3)
     const uint32_t dst_rank = (uint32_t)(lane & 7);
     const int piece = lane >> 3;
-    uint32_t dst_piece[2], dst_pend[2], dst_bar[2];
+    uint32_t dst_piece[2], dst_pend[2], dst_bar[2], dst_rx[2], dst_rbar[2];
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
         const uint4* base = piece == 0 ? xch[b].A : piece == 1 ? xch[b].B : piece == 2 ? xch[b].C : xch[b].D;
         dst_piece[b] = lc::mapa(lc::smem_u32(base + (rank * NW + warp)), dst_rank);
         dst_pend[b] = lc::mapa(lc::smem_u32(&xch[b].P[piece & 1]), dst_rank);
         dst_bar[b] = lc::mapa(bar_local[b], dst_rank);
+        dst_rx[b] = lc::mapa(lc::smem_u32(&rx[b][rank * NW + warp]), dst_rank);
+        dst_rbar[b] = lc::mapa(rbar_local[b], dst_rank);
     }
 
     auto row_of = [&](int lg) { return ((lg * kLcCtas + rank) << 5) + lane; };
@@ -1129,6 +1143,7 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
         nbr[s] = z < n - 1 ? w.nbr[z] : -1;
         lb[s] = z < n - 1 ? w.lb[z] : INFINITY;
         cur[s] = lb[s];
+        alive[s] = z < n ? 1 : 0;
     }
     for (int i = tid; i < NG * 32; i += T) {
         rsize[i] = i < n ? 1 : 0;
@@ -1146,7 +1161,7 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
         double second = INFINITY;  // smallest value of this lane not counted in m
         for (int lg = warp; lg < NGl; lg += NW) {
             const int z = row_of(lg), s = lg * 32 + lane;
-            if (z < n - 1 && z != skip_a && z != skip_b && rsize[z] != 0) {
+            if (z < n - 1 && z != skip_a && z != skip_b && alive[s] != 0) {
                 const double v = lb[s];
                 if (m.c == 0 || v < m.v) {
                     if (m.c) second = m.v;  // the old best (and anything tied with it) is now second
@@ -1221,7 +1236,8 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
         publish(par, t, v2, INFINITY, -1, -1, rank == 0 && warp == 0);
     }
 
-    int k = 0, tries = 0, rs_par = 0;
+    int k = 0, tries = 0, rpar = 0;
+    unsigned rphase[2] = {0u, 0u};
     unsigned long long rescans = 0, refills = 0;
     long long c_dec = 0, c_work = 0, c_res = 0, c_bar = 0, t0, t1;
     t1 = clock64();
@@ -1381,37 +1397,52 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
                 op = 0;
                 break;
             }
-            // ---- stale: find_min_dist(x) (clustering.cpp:259-276), redundantly in every CTA ----
+            // ---- stale: find_min_dist(x) (clustering.cpp:259-276).  Every warp scans its own rows i > x, the 8*NW
+            // partial minima are exchanged (one 16-byte st.async per destination CTA) and reduced by everyone ----
             long long tr0 = clock64();
             {
                 const double* r = w.D + (size_t)x * w.ld;
                 double bv = INFINITY;
                 int bi = -1;
-                for (int i0 = x + 1 + tid; i0 < n; i0 += T * PFR) {
-                    double d[PFR];
+                for (int lg0 = warp; lg0 < NGl; lg0 += NW * PF) {
+                    double d[PF];
+                    bool ok[PF];
 #pragma unroll
-                    for (int u = 0; u < PFR; ++u) {
-                        const int i = i0 + u * T;
-                        d[u] = i < n ? __ldcg(r + i) : INFINITY;
+                    for (int u = 0; u < PF; ++u) {
+                        const int lg = lg0 + u * NW;
+                        const int i = row_of(lg);
+                        ok[u] = lg < NGl && i > x && i < n && alive[lg * 32 + lane] != 0;
+                        d[u] = ok[u] ? __ldcg(r + i) : INFINITY;
                     }
 #pragma unroll
-                    for (int u = 0; u < PFR; ++u) {
-                        const int i = i0 + u * T;
-                        if (i < n && rsize[i] != 0 && d[u] < bv) {
+                    for (int u = 0; u < PF; ++u)
+                        if (ok[u] && d[u] < bv) {  // rows ascend within a lane: first minimum in index order
                             bv = d[u];
-                            bi = i;
+                            bi = row_of(lg0 + u * NW);
+                        }
+                }
+                const Top part = warp_top(bi >= 0 ? bv : INFINITY, bi, bi >= 0 ? 1 : 0);
+                if (lane < kLcCtas) lc::st_async16(dst_rx[rpar], dst_rbar[rpar], lc::pack(part.i >= 0 ? part.v : INFINITY, part.i, 0));
+                lc::mbar_wait(rbar_local[rpar], rphase[rpar] & 1u);
+                ++rphase[rpar];
+                if (tid == 0) lc::mbar_expect_tx(rbar_local[rpar], kRxBytes);  // re-arm for the revalidation after next
+                double qv = INFINITY;
+                int qi = -1;
+#pragma unroll
+                for (int u = 0; u < EPL; ++u) {
+                    const int e = lane + 32 * u;
+                    if (e < E) {
+                        const uint4 q = rx[rpar][e];
+                        const int ci = (int)q.z;
+                        const double cv = lc::unpack_d(q);
+                        if (ci >= 0 && (qi < 0 || cv < qv || (cv == qv && ci < qi))) {
+                            qv = cv;
+                            qi = ci;
                         }
                     }
                 }
-                const Top part = warp_top(bi >= 0 ? bv : INFINITY, bi, bi >= 0 ? 1 : 0);
-                if (lane == 0) {
-                    rs_v[rs_par][warp] = part.v;
-                    rs_i[rs_par][warp] = part.i;
-                }
-                __syncthreads();
-                const bool has = lane < NW && rs_i[rs_par][lane < NW ? lane : 0] >= 0;
-                const Top res = warp_top(has ? rs_v[rs_par][lane] : INFINITY, has ? rs_i[rs_par][lane] : -1, has ? 1 : 0);
-                rs_par ^= 1;
+                const Top res = warp_top(qi >= 0 ? qv : INFINITY, qi, qi >= 0 ? 1 : 0);
+                rpar ^= 1;
                 const double nv = res.i >= 0 ? res.v : INFINITY;
                 if (mine(x)) {
                     const int s = owner_lg(x) * 32 + lane;
@@ -1493,7 +1524,8 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
             for (int u = 0; u < PF; ++u) {
                 const int lg = lg0 + u * NW;
                 const int z = row_of(lg);
-                live[u] = lg < NGl && z < n && z != x && z != y && rsize[z] != 0;
+                live[u] = lg < NGl && z < n && z != x && z != y && alive[lg * 32 + lane] != 0;
+                if (lg < NGl && z == x) alive[lg * 32 + lane] = 0;
                 dx[u] = live[u] ? __ldcg(rowx + z) : 0.0;
                 dy[u] = live[u] ? __ldcg(rowy + z) : 0.0;
             }
@@ -2128,7 +2160,7 @@ static LinkLayout link_layout(int N) {
     L.off_n = o;
     o += 256;
     L.off_fast = o;
-    o += align_up(linkfast_smem_bytes(N), 256);
+    o += align_up(std::max(linkfast_smem_bytes(N), linkcluster_global_bytes(N)), 256);
     L.total = o;
     return L;
 }
@@ -2199,28 +2231,32 @@ static int linkage_fast_launch_mode(sd_ctx* ctx, const LinkWork* d_works, const 
     return SD_OK;
 }
 
-template <int T>
+template <int T, bool GREPL>
 static int linkage_cluster_launch(sd_ctx* ctx, const LinkWork* d_works, const int* d_ns, int problems, int max_n,
                                   int* d_need_exact) {
-    const size_t smem = linkcluster_smem_bytes(max_n);
+    const size_t smem = linkcluster_smem_bytes(max_n, GREPL);
     static bool configured = false;
     if (!configured) {
-        SD_CUDA(ctx, cudaFuncSetAttribute(linkage_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SD_CUDA(ctx, cudaFuncSetAttribute(linkage_cluster_kernel<T, GREPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          200 * 1024));
         configured = true;
     }
-    linkage_cluster_kernel<T><<<problems * kLcCtas, T, smem, ctx->stream>>>(d_works, d_ns, d_need_exact);
+    linkage_cluster_kernel<T, GREPL><<<problems * kLcCtas, T, smem, ctx->stream>>>(d_works, d_ns, d_need_exact);
     SD_LAUNCH_CHECK(ctx);
     return SD_OK;
 }
 
 static int linkage_fast_dispatch(sd_ctx* ctx, const LinkWork* d_works, const int* d_ns, int problems, int max_n,
                                  int* d_need_exact) {
-    if (ctx->linkage_cluster && linkcluster_smem_bytes(max_n) <= (size_t)190 * 1024) {
+    constexpr size_t kClusterSmem = (size_t)180 * 1024;
+    if (ctx->linkage_cluster && linkcluster_smem_bytes(max_n, false) <= kClusterSmem) {
         const int t = ctx->linkage_threads ? ctx->linkage_threads : (max_n <= 4096 ? 128 : 256);
-        if (t <= 128) return linkage_cluster_launch<128>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
-        if (t <= 256) return linkage_cluster_launch<256>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
-        return linkage_cluster_launch<512>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
+        if (t <= 128) return linkage_cluster_launch<128, false>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
+        if (t <= 256) return linkage_cluster_launch<256, false>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
+        return linkage_cluster_launch<512, false>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
     }
+    if (ctx->linkage_cluster && linkcluster_smem_bytes(max_n, true) <= kClusterSmem)  // replicas in global memory
+        return linkage_cluster_launch<512, true>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
     const bool fits = linkfast_smem_bytes(max_n) <= (size_t)220 * 1024;
     const int threads = ctx->linkage_threads ? ctx->linkage_threads : (max_n <= 4096 ? 512 : 1024);
     if (fits && threads == 512) return linkage_fast_launch_mode<LF_SMEM, 512>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
