@@ -194,20 +194,48 @@ __device__ __forceinline__ unsigned compose_fn(unsigned f, unsigned g) {
 
 constexpr int kAnThreads = 1024;
 
+// inclusive block scan of ints (1024 threads): warp shuffles + one pass over the 32 warp totals
+__device__ __forceinline__ int an_scan_incl(int v, int* warp_tot, int* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    if (lane == 31) warp_tot[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        int t = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, t, o);
+            if (lane >= o) t += u;
+        }
+        warp_tot[lane] = t;
+    }
+    __syncthreads();
+    if (warp > 0) v += warp_tot[warp - 1];
+    if (total) *total = warp_tot[31];
+    __syncthreads();  // warp_tot may be reused
+    return v;
+}
+
 // One CTA per class.  Every thread owns a contiguous slice of frames: (1) compose the slice's transition
 // function, block-scan the functions to get the state entering each slice, (2) count segment starts / ends,
-// block-scan the counts, (3) emit (start, end) pairs in time order, then thread 0 applies support() and
-// removeShort() in place (they are sequential merges over a list that is tiny compared with the frame count).
+// block-scan the counts, (3) emit (start, end) pairs in time order into list A, (4) support(): consecutive
+// segments are disjoint and ordered, so "gap to the running segment < min_duration_off" only involves neighbours:
+// chain heads are flagged, ranked with a block scan and the merged segments go to list B, (5) removeShort(): the
+// kept segments are ranked and copied back to A.  (4) and (5) degenerate to copies when disabled.
 __global__ void __launch_bounds__(kAnThreads)
     annot_runs_kernel(const unsigned char* __restrict__ flags, long rows, int cols, double f_start, double f_step,
-                      double f_duration, double min_on, double min_off, double* __restrict__ lists, long maxseg,
-                      int* __restrict__ nseg) {
+                      double f_duration, double min_on, double min_off, double* __restrict__ lists,
+                      double* __restrict__ lists_b, long maxseg, int* __restrict__ nseg) {
     __shared__ unsigned s_fn[kAnThreads];
-    __shared__ int s_cnt[kAnThreads];
-    __shared__ int s_total;
+    __shared__ int warp_tot[32];
     const int k = blockIdx.x, tid = threadIdx.x;
     const unsigned char* fl = flags + (size_t)k * rows;
     double* segs = lists + (size_t)k * maxseg * 2;
+    double* segb = lists_b + (size_t)k * maxseg * 2;
     // frame 0 only sets the initial state (v > onset); slices cover frames 1..rows-1
     const long n = rows - 1;
     const long per = n > 0 ? (n + kAnThreads - 1) / kAnThreads : 1;
@@ -224,113 +252,87 @@ __global__ void __launch_bounds__(kAnThreads)
         __syncthreads();
     }
     const unsigned init = rows > 0 ? (fl[0] & 1u) : 0u;
-    unsigned state = tid == 0 ? init : apply_fn(s_fn[tid - 1], init);
-    // a segment is counted where it ends (deactivation, or the last frame while active)
-    int ends = 0;
+    const unsigned state = tid == 0 ? init : apply_fn(s_fn[tid - 1], init);
+    // a segment is counted where it ends (deactivation, or the last frame while active) and where it starts
+    int ends = 0, starts = 0;
     {
         unsigned s = state;
         for (long t = lo; t < hi; ++t) {
             const unsigned ns = apply_fn(step_fn(fl[t]), s);
             ends += (s == 1u && ns == 0u);
-            s = ns;
-        }
-        if (owns_last && s == 1u) ++ends;  // still active at the last frame
-    }
-    if (n <= 0 && tid == 0) ends = init ? 1 : 0;  // a single frame: active -> (TS(0), TS(0))
-    s_cnt[tid] = ends;
-    __syncthreads();
-    for (int o = 1; o < kAnThreads; o <<= 1) {
-        int mine = s_cnt[tid], prev = tid >= o ? s_cnt[tid - o] : 0;
-        __syncthreads();
-        s_cnt[tid] = mine + prev;
-        __syncthreads();
-    }
-    int w = s_cnt[tid] - ends;  // exclusive
-    if (tid == kAnThreads - 1) s_total = s_cnt[tid];
-    // emit ends from this slice; the matching start is the most recent activation, possibly in an earlier slice:
-    // every slice also records the start of the run that is open when it begins (walk back is avoided by
-    // writing starts separately: the j-th start of the class pairs with the j-th end).
-    {
-        unsigned s = state;
-        for (long t = lo; t < hi; ++t) {
-            const unsigned ns = apply_fn(step_fn(fl[t]), s);
-            if (s == 1u && ns == 0u) segs[2 * (size_t)w++ + 1] = frame_middle(f_start, f_step, f_duration, t);
-            s = ns;
-        }
-        if (owns_last && s == 1u)
-            segs[2 * (size_t)w++ + 1] = frame_middle(f_start, f_step, f_duration, rows - 1);
-    }
-    if (n <= 0 && tid == 0 && init) segs[1] = frame_middle(f_start, f_step, f_duration, 0);
-    // starts: activation at t (0 -> 1), plus frame 0 when the class starts active
-    int starts = 0;
-    {
-        unsigned s = state;
-        for (long t = lo; t < hi; ++t) {
-            const unsigned ns = apply_fn(step_fn(fl[t]), s);
             starts += (s == 0u && ns == 1u);
             s = ns;
         }
+        if (owns_last && s == 1u) ++ends;  // still active at the last frame
         if (tid == 0 && init) ++starts;
     }
-    __syncthreads();
-    s_cnt[tid] = starts;
-    __syncthreads();
-    for (int o = 1; o < kAnThreads; o <<= 1) {
-        int mine = s_cnt[tid], prev = tid >= o ? s_cnt[tid - o] : 0;
-        __syncthreads();
-        s_cnt[tid] = mine + prev;
-        __syncthreads();
-    }
+    if (n <= 0 && tid == 0) ends = init ? 1 : 0;  // a single frame: active -> (TS(0), TS(0))
+    int total = 0;
+    int w = an_scan_incl(ends, warp_tot, &total) - ends;
+    int ws = an_scan_incl(starts, warp_tot, nullptr) - starts;
     {
-        int ws = s_cnt[tid] - starts;
+        // the j-th start of the class pairs with the j-th end
         if (tid == 0 && init) segs[2 * (size_t)ws++] = frame_middle(f_start, f_step, f_duration, 0);
         unsigned s = state;
         for (long t = lo; t < hi; ++t) {
             const unsigned ns = apply_fn(step_fn(fl[t]), s);
+            if (s == 1u && ns == 0u) segs[2 * (size_t)w++ + 1] = frame_middle(f_start, f_step, f_duration, t);
             if (s == 0u && ns == 1u) segs[2 * (size_t)ws++] = frame_middle(f_start, f_step, f_duration, t);
             s = ns;
         }
+        if (owns_last && s == 1u) segs[2 * (size_t)w++ + 1] = frame_middle(f_start, f_step, f_duration, rows - 1);
+    }
+    if (n <= 0 && tid == 0 && init) segs[1] = frame_middle(f_start, f_step, f_duration, 0);
+    __syncthreads();
+    // ---- Track::support (SD:911-941): A -> B
+    int cnt = total;
+    {
+        int carry = 0;
+        for (int base = 0; base < cnt; base += kAnThreads) {
+            const int i = base + tid;
+            bool head = false, tail = false;
+            if (i < cnt) {
+                auto chained = [&](int a) {  // does raw segment a+1 extend the chain that contains raw segment a?
+                    if (!(min_off > 0.0)) return false;
+                    const double ce = segs[2 * a + 1], ns = segs[2 * (a + 1)];
+                    const double gap = ce >= ns ? 0.0 : __dsub_rn(ns, ce);  // cur.start < next.start always holds
+                    return gap < min_off;
+                };
+                head = i == 0 || !chained(i - 1);
+                tail = i == cnt - 1 || !chained(i);
+            }
+            int chunk_total = 0;
+            const int rank = carry + an_scan_incl(head ? 1 : 0, warp_tot, &chunk_total) - 1;  // chain index of i
+            if (head) segb[2 * (size_t)rank] = segs[2 * i];
+            if (tail) segb[2 * (size_t)rank + 1] = segs[2 * i + 1];
+            carry += chunk_total;
+        }
+        cnt = carry;
     }
     __syncthreads();
-    if (tid != 0) return;
-    __threadfence_block();
-    long cnt = s_total;
-    if (min_off > 0.0 && cnt > 0) {  // Track::support (SD:911-941)
-        long wr = 0;
-        double cs = segs[0], ce = segs[1];
-        for (long i = 1; i < cnt; ++i) {
-            const double ns = segs[2 * i], ne = segs[2 * i + 1];
-            double gap;
-            if (cs < ns)
-                gap = ce >= ns ? 0.0 : __dsub_rn(ns, ce);
-            else
-                gap = cs <= ne ? 0.0 : __dsub_rn(cs, ne);
-            if (gap < min_off) {
-                if (ns < cs) cs = ns;
-                if (ne > ce) ce = ne;
-            } else {
-                segs[2 * wr] = cs;
-                segs[2 * wr + 1] = ce;
-                ++wr;
-                cs = ns;
-                ce = ne;
+    // ---- Track::removeShort never examines the first segment (SD:943-953): B -> A
+    {
+        int carry = 0;
+        for (int base = 0; base < cnt; base += kAnThreads) {
+            const int i = base + tid;
+            bool keep = false;
+            double s0 = 0.0, e0 = 0.0;
+            if (i < cnt) {
+                s0 = segb[2 * i];
+                e0 = segb[2 * i + 1];
+                keep = i == 0 || !(min_on > 0.0) || !(__dsub_rn(e0, s0) < min_on);
             }
+            int chunk_total = 0;
+            const int rank = carry + an_scan_incl(keep ? 1 : 0, warp_tot, &chunk_total) - 1;
+            if (keep) {
+                segs[2 * (size_t)rank] = s0;
+                segs[2 * (size_t)rank + 1] = e0;
+            }
+            carry += chunk_total;
         }
-        segs[2 * wr] = cs;
-        segs[2 * wr + 1] = ce;
-        cnt = wr + 1;
+        cnt = carry;
     }
-    if (min_on > 0.0) {  // Track::removeShort never examines the first segment (SD:943-953)
-        long wr = cnt > 0 ? 1 : 0;
-        for (long i = 1; i < cnt; ++i)
-            if (!(__dsub_rn(segs[2 * i + 1], segs[2 * i]) < min_on)) {
-                segs[2 * wr] = segs[2 * i];
-                segs[2 * wr + 1] = segs[2 * i + 1];
-                ++wr;
-            }
-        cnt = wr;
-    }
-    nseg[k] = (int)cnt;
+    if (tid == 0) nseg[k] = cnt;
 }
 
 // finalResult (SD:962-978): all segments ordered by start.  Every class list is already sorted, so the final
@@ -375,7 +377,8 @@ int to_annotation_launch(sd_ctx* ctx, const double* d_scores, int64_t rows, int 
                          int64_t cap, long* d_n) {
     const long maxseg = rows / 2 + 2;
     unsigned char* d_flags = (unsigned char*)ctx->scratch(BUF_AN_FLAGS, (size_t)rows * cols);
-    double* d_lists = (double*)ctx->scratch(BUF_AN_LISTS, sizeof(double) * 2 * (size_t)maxseg * cols);
+    double* d_lists = (double*)ctx->scratch(BUF_AN_LISTS, sizeof(double) * 4 * (size_t)maxseg * cols);  // lists A and B
+    double* d_lists_b = d_lists ? d_lists + 2 * (size_t)maxseg * cols : nullptr;
     int* d_nseg = (int*)ctx->scratch(BUF_AN_META, sizeof(int) * (size_t)cols);
     if (!d_flags || !d_lists || !d_nseg) return SD_ERR_NOMEM;
     const long total = (long)rows * cols;
@@ -383,7 +386,8 @@ int to_annotation_launch(sd_ctx* ctx, const double* d_scores, int64_t rows, int 
                                                                                d_flags);
     SD_LAUNCH_CHECK(ctx);
     annot_runs_kernel<<<cols, kAnThreads, 0, ctx->stream>>>(d_flags, (long)rows, cols, frames->start, frames->step,
-                                                            frames->duration, min_on, min_off, d_lists, maxseg, d_nseg);
+                                                            frames->duration, min_on, min_off, d_lists, d_lists_b, maxseg,
+                                                            d_nseg);
     SD_LAUNCH_CHECK(ctx);
     annot_merge_kernel<<<32, 256, 0, ctx->stream>>>(d_lists, maxseg, d_nseg, cols, d_seg, d_label, (long)cap, d_n);
     SD_LAUNCH_CHECK(ctx);

@@ -15,21 +15,27 @@ __host__ __device__ inline int frame_first_sample(int f, int F, int L) { return 
 
 // One CTA per item.  wav_base[b] = offset of the item's first sample inside `wav` (samples beyond wav_limit are
 // the zero padding of SegmentModel::crop, speakerDiarizer.cpp:1641-1662).
+// Shared memory: first[f] = first sample of frame f (f = 0..F, first[F] = L) and off[f] = destination of the run of
+// frame f, so the per-sample work has no division: a thread takes 8 consecutive samples (two 16-byte loads when the
+// source is aligned), looks its frame up once and only compares against the next boundary.
 __global__ void __launch_bounds__(512)
     mask_compact_kernel(const float* __restrict__ wav, const long* __restrict__ wav_base, long item_stride,
                         long wav_limit, const float* __restrict__ masks, int L, int F, float* __restrict__ signals,
                         float* __restrict__ counts) {
-    extern __shared__ int sm[];  // off[F+1]
+    extern __shared__ int sm[];
+    int* first = sm;          // [F + 1]
+    int* off = sm + (F + 1);  // [F]: destination offset of frame f's run, -1 when the frame is masked out
     __shared__ int warp_tot[16];
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* m = masks + (size_t)b * F;
+    for (int f = tid; f <= F; f += 512) first[f] = f < F ? frame_first_sample(f, F, L) : L;
     // exclusive prefix of the run lengths of the active frames
     int carry = 0;
     for (int f0 = 0; f0 < F; f0 += 512) {
         const int f = f0 + tid;
-        int n = 0;
-        if (f < F && m[f] > 0.5f) n = frame_first_sample(f + 1, F, L) - frame_first_sample(f, F, L);
+        const bool on = f < F && m[f] > 0.5f;
+        const int n = on ? frame_first_sample(f + 1, F, L) - frame_first_sample(f, F, L) : 0;
         int inc = n;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -40,7 +46,7 @@ __global__ void __launch_bounds__(512)
         __syncthreads();
         int before = carry;
         for (int w2 = 0; w2 < warp; ++w2) before += warp_tot[w2];
-        if (f < F) sm[f] = before + inc - n;
+        if (f < F) off[f] = on ? before + inc - n : -1;
         int tot = 0;
         for (int w2 = 0; w2 < 16; ++w2) tot += warp_tot[w2];
         carry += tot;
@@ -48,13 +54,45 @@ __global__ void __launch_bounds__(512)
     }
     const int count = carry;
     const long base = wav_base ? wav_base[b] : (long)b * item_stride;
+    const float* src = wav + base;
     float* out = signals + (size_t)b * L;
-    for (int j = tid; j < L; j += 512) {
-        const int f = (int)((long)j * F / L);
-        if (m[f] > 0.5f) {
-            const long s = base + j;
-            out[sm[f] + (j - frame_first_sample(f, F, L))] = s < wav_limit ? wav[s] : 0.f;
+    // A warp takes 256 consecutive samples per step: lane l handles samples l, l + 32, ... so that both the loads and
+    // the (shifted) stores of one instruction cover whole 128-byte lines.  The frame of a sample is estimated in
+    // fp32 and corrected against the exact boundaries in shared memory.
+    const float scale = (float)F / (float)L;
+    for (int j0 = warp * 256; j0 < L; j0 += 16 * 256) {
+        // frame of this lane's first sample (fp32 estimate corrected against the exact boundaries), then only
+        // boundary comparisons (samples ascend with u); masked-out samples are never loaded
+        const int jfirst = j0 + lane;
+        int f = min(F - 1, (int)((float)jfirst * scale));
+        if (jfirst < L) {
+            while (jfirst < first[f]) --f;
+            while (jfirst >= first[f + 1]) ++f;
         }
+        int fb = first[f], nextb = first[f + 1], o = off[f];
+        int dst[8];
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + 32 * u + lane;
+            dst[u] = -1;
+            v[u] = 0.f;
+            if (j < L) {
+                if (j >= nextb) {
+                    do ++f; while (j >= first[f + 1]);
+                    fb = first[f];
+                    nextb = first[f + 1];
+                    o = off[f];
+                }
+                if (o >= 0) {
+                    dst[u] = o + (j - fb);
+                    if (base + j < wav_limit) v[u] = src[j];
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (dst[u] >= 0) out[dst[u]] = v[u];
     }
     for (int j = count + tid; j < L; j += 512) out[j] = 0.f;  // padSequence's zero tail
     if (tid == 0) counts[b] = (float)count;
@@ -125,7 +163,7 @@ int mask_compact_launch(sd_ctx* ctx, const float* d_wav, const long* d_wav_base,
                         float* d_wav_lens, unsigned char* d_too_short, unsigned char* d_batch_invalid) {
     float* d_counts = (float*)ctx->scratch(BUF_GENERIC_A, sizeof(float) * (size_t)R);
     if (!d_counts) return SD_ERR_NOMEM;
-    mask_compact_kernel<<<R, 512, sizeof(int) * (size_t)(F + 1), ctx->stream>>>(d_wav, d_wav_base, item_stride, wav_limit,
+    mask_compact_kernel<<<R, 512, sizeof(int) * (size_t)(2 * F + 2), ctx->stream>>>(d_wav, d_wav_base, item_stride, wav_limit,
                                                                                 d_masks, L, F, d_signals, d_counts);
     SD_LAUNCH_CHECK(ctx);
     const int ngroups = (R + batch - 1) / batch;
