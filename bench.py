@@ -206,6 +206,19 @@ def run_product(args, rank, world):
     synth = ge.load_synth()
     geo = geometry()
     local = int(os.environ.get("LOCAL_RANK", rank))
+    # Host threads waiting for the GPU spin by default, which is the fastest (1 GPU: 235.7 k audio-s/s, yield
+    # 202.6 k, blocking 158.8 k) until the ranks' worker threads outnumber the host cores (8 GPUs x 8 files on 32
+    # cores: spin 1.20 M, yield 1.36 M): then they yield.  SDB_SCHED=spin|yield|blocking overrides.
+    sched = os.environ.get("SDB_SCHED", "")
+    if not sched and world * max(1, args.files) > (os.cpu_count() or 1):
+        sched = "yield"
+    if sched:
+        from cuda import cudart
+        cudart.cudaSetDevice(local)
+        flag = {"yield": cudart.cudaDeviceScheduleYield, "blocking": cudart.cudaDeviceScheduleBlockingSync,
+                "spin": cudart.cudaDeviceScheduleSpin}[sched]
+        err, = cudart.cudaSetDeviceFlags(flag)
+        print("cudaSetDeviceFlags(%s): %s" % (sched, err), file=sys.stderr)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -247,7 +260,7 @@ def run_product(args, rank, world):
     # leaving 140 SMs idle.  Lock-step per step (measured better than free-running threads: 20-21 ms vs 23-25 ms per
     # 8 files); the labels of the step's files are gathered over the ranks with one NCCL all_gather per step -- the
     # only collective on the path (KBs).
-    pool = ThreadPoolExecutor(max_workers=nfiles)
+    pool = ThreadPoolExecutor(max_workers=nfiles, initializer=torch.cuda.set_device, initargs=(local,))
 
     def run_batch(nsteps):
         for s_ in range(nsteps):
@@ -345,6 +358,7 @@ def run_product(args, rank, world):
                    "l2_policy": "inputs larger than L2 (STFT streams 3.99 GB per file)",
                    "files_per_step_per_gpu": nfiles,
                    "concurrency": "one host thread + sd_ctx + CUDA stream per file of the batch, joined every step",
+                   "host_wait": sched or "spin (driver default)",
                    "parallelism": "file-sharded x%d" % world},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "files_per_step_per_gpu": 1},

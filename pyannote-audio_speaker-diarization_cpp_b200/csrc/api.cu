@@ -181,6 +181,7 @@ const char* sd_last_error(const sd_ctx* ctx) { return ctx ? ctx->err.c_str() : "
 
 int sd_ctx_set_stream(sd_ctx* ctx, void* cuda_stream) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     cudaStreamSynchronize(ctx->stream);
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return SD_OK;
@@ -189,6 +190,7 @@ void* sd_ctx_stream(sd_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 int sd_sync(sd_ctx* ctx) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SD_OK;
 }
@@ -203,6 +205,7 @@ int sd_malloc(sd_ctx* ctx, size_t bytes, void** dptr) {
 }
 int sd_free(sd_ctx* ctx, void* dptr) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_CUDA(ctx, cudaFree(dptr));
     return SD_OK;
 }
@@ -217,21 +220,25 @@ int sd_host_alloc(sd_ctx* ctx, size_t bytes, void** hptr) {
 }
 int sd_host_free(sd_ctx* ctx, void* hptr) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_CUDA(ctx, cudaFreeHost(hptr));
     return SD_OK;
 }
 int sd_memcpy_h2d(sd_ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return SD_OK;
 }
 int sd_memcpy_d2h(sd_ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return SD_OK;
 }
 int sd_memset(sd_ctx* ctx, void* dst, int value, size_t bytes) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_CUDA(ctx, cudaMemsetAsync(dst, value, bytes, ctx->stream));
     return SD_OK;
 }
@@ -255,6 +262,7 @@ int64_t sd_launch_count(const sd_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int sd_ctx_set_option(sd_ctx* ctx, int option, int value) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     switch (option) {
         case SD_OPT_FORCE_EXACT_LINKAGE:
             ctx->force_exact_linkage = value != 0;
@@ -285,6 +293,7 @@ int sd_debug_counters(sd_ctx* ctx, int64_t* out8, int reset) {
 
 int sd_flush_l2(sd_ctx* ctx) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     if (!ctx->flush_buf) {
         ctx->flush_bytes = std::max<size_t>(2 * ctx->l2_bytes, (size_t)256 << 20);
         SD_CUDA(ctx, cudaMalloc(&ctx->flush_buf, ctx->flush_bytes));
@@ -309,6 +318,7 @@ int64_t sd_stft_num_frames(int L, int hop) { return hop > 0 ? 1 + L / hop : 0; }
 
 int sd_stft_dev(sd_ctx* ctx, const float* d_wav, int B, int L, const sd_stft_params* p, float* d_out) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, d_wav && d_out && p, "sd_stft_dev: null pointer");
     SD_REQUIRE(ctx, B > 0 && L > 0, "sd_stft_dev: B and L must be positive");
     return stft_launch(ctx, d_wav, B, L, p, d_out);
@@ -320,6 +330,7 @@ int sd_stft_dev(sd_ctx* ctx, const float* d_wav, int B, int L, const sd_stft_par
 // for the copies to be truly asynchronous; pageable ones still work, just serialised by the driver.)
 int sd_stft(sd_ctx* ctx, const float* wav, int B, int L, const sd_stft_params* p, float* out) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, wav && out && p, "sd_stft: null pointer");
     SD_REQUIRE(ctx, B > 0 && L > 0, "sd_stft: B and L must be positive");
     const int64_t T = sd_stft_num_frames(L, p->hop);
@@ -394,6 +405,7 @@ void sd_fbank_default_params(sd_fbank_params* p) {
 int sd_fbank_dev(sd_ctx* ctx, const float* d_wav, int B, int L, const float* d_wav_lens, const sd_fbank_params* p,
                  float* d_out) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, d_wav && d_out && p && d_wav_lens, "sd_fbank_dev: null pointer");
     SD_REQUIRE(ctx, B > 0 && L > 0, "sd_fbank_dev: B and L must be positive");
     return fbank_launch(ctx, d_wav, B, L, d_wav_lens, p, d_out);
@@ -402,6 +414,7 @@ int sd_fbank_dev(sd_ctx* ctx, const float* d_wav, int B, int L, const float* d_w
 int sd_fbank(sd_ctx* ctx, const float* wav, int B, int L, const float* wav_lens, const sd_fbank_params* p,
              float* out) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, wav && out && p && wav_lens, "sd_fbank: null pointer");
     SD_REQUIRE(ctx, B > 0 && L > 0, "sd_fbank: B and L must be positive");
     const int64_t T = sd_stft_num_frames(L, p->stft.hop);
@@ -447,6 +460,7 @@ int sd_aggregate_dev(sd_ctx* ctx, const double* d_scores, int C, int F, int K, c
                      double* d_out, int64_t cap_rows, int64_t* num_frames, sd_window* post_frames, double* d_count_out,
                      double* d_mask_out) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, d_scores && d_out && chunks && frames, "sd_aggregate_dev: null pointer");
     SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0, "sd_aggregate_dev: C, F, K must be positive");
     SD_REQUIRE(ctx, chunks->num_samples > 0, "sd_aggregate: scores_frames.num_samples must be > 0 (SD:1181)");
@@ -463,6 +477,7 @@ int sd_aggregate(sd_ctx* ctx, const double* scores, int C, int F, int K, const s
                  const sd_window* frames, int hamming, double missing, int skip_average, double epsilon, double* out,
                  int64_t cap_rows, int64_t* num_frames, sd_window* post_frames, double* count_out, double* mask_out) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, scores && out && chunks && frames, "sd_aggregate: null pointer");
     SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0, "sd_aggregate: C, F, K must be positive");
     const int64_t NF = sd_aggregate_num_frames(C, chunks, frames);
@@ -492,6 +507,7 @@ int sd_aggregate(sd_ctx* ctx, const double* scores, int C, int F, int K, const s
 int sd_binarize_dev(sd_ctx* ctx, const float* d_scores, int C, int F, int K, double onset, int initial_state,
                     double* d_out) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, d_scores && d_out, "sd_binarize_dev: null pointer");
     SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0, "sd_binarize_dev: C, F, K must be positive");
     return binarize_launch(ctx, d_scores, C, F, K, onset, initial_state, d_out);
@@ -499,6 +515,7 @@ int sd_binarize_dev(sd_ctx* ctx, const float* d_scores, int C, int F, int K, dou
 
 int sd_binarize(sd_ctx* ctx, const float* scores, int C, int F, int K, double onset, int initial_state, double* out) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, scores && out, "sd_binarize: null pointer");
     SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0, "sd_binarize: C, F, K must be positive");
     const size_t n = (size_t)C * F * K;
@@ -515,6 +532,7 @@ int sd_binarize(sd_ctx* ctx, const float* scores, int C, int F, int K, double on
 
 int sd_binarize_rows(sd_ctx* ctx, const double* scores, int R, int F, double onset, int initial_state, uint8_t* out) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, scores && out, "sd_binarize_rows: null pointer");
     SD_REQUIRE(ctx, R > 0 && F > 0, "sd_binarize_rows: R, F must be positive");
     const size_t n = (size_t)R * F;
@@ -544,6 +562,7 @@ static void trimmed_window(int F, double left, double right, const sd_window* be
 int sd_trim(sd_ctx* ctx, const double* binarized, int C, int F, int K, double left, double right,
             const sd_window* before, double* out, sd_window* trimmed_frames) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, binarized && out && before, "sd_trim: null pointer");
     SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0, "sd_trim: C, F, K must be positive");
     const int nl = (int)std::floor((double)F * left);
@@ -565,6 +584,7 @@ int sd_trim(sd_ctx* ctx, const double* binarized, int C, int F, int K, double le
 int sd_speaker_count_dev(sd_ctx* ctx, const double* d_binarized, int C, int F, int K, const sd_window* chunks,
                          const sd_window* frames, int32_t* d_out, int64_t cap, int64_t* n_out, sd_window* count_frames) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, d_binarized && d_out && chunks && frames, "sd_speaker_count_dev: null pointer");
     SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0, "sd_speaker_count_dev: C, F, K must be positive");
     // trim 10% / 10% of the chunk window (speakerDiarizer.cpp:1691-1693; the reference anchors it at 0.0)
@@ -595,6 +615,7 @@ int sd_speaker_count_dev(sd_ctx* ctx, const double* d_binarized, int C, int F, i
 int sd_speaker_count(sd_ctx* ctx, const double* binarized, int C, int F, int K, const sd_window* chunks,
                      const sd_window* frames, int32_t* out, int64_t cap, int64_t* n_out, sd_window* count_frames) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, binarized && out && chunks && frames, "sd_speaker_count: null pointer");
     SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0, "sd_speaker_count: C, F, K must be positive");
     const size_t in_bytes = sizeof(double) * (size_t)C * F * K;
@@ -613,6 +634,7 @@ int sd_speaker_count(sd_ctx* ctx, const double* binarized, int C, int F, int K, 
 
 int sd_clean_segmentations(sd_ctx* ctx, const double* binarized, int C, int F, int K, double* out) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, binarized && out, "sd_clean_segmentations: null pointer");
     SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0, "sd_clean_segmentations: C, F, K must be positive");
     const size_t bytes = sizeof(double) * (size_t)C * F * K;
@@ -645,6 +667,7 @@ static int reset_status(sd_ctx* ctx) {
 
 int sd_normalize(sd_ctx* ctx, double* x, int N, int D) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, x, "sd_normalize: null pointer");
     SD_REQUIRE(ctx, N > 0 && D > 0, "sd_normalize: N, D must be positive");
     const size_t bytes = sizeof(double) * (size_t)N * D;
@@ -661,6 +684,7 @@ int sd_normalize(sd_ctx* ctx, double* x, int N, int D) {
 
 int sd_pdist(sd_ctx* ctx, const double* x, int N, int D, int mode, double* condensed) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, x && condensed, "sd_pdist: null pointer");
     SD_REQUIRE(ctx, N > 1 && D > 0, "sd_pdist: need N > 1, D > 0");
     const size_t bytes = sizeof(double) * (size_t)N * D;
@@ -678,6 +702,7 @@ int sd_pdist(sd_ctx* ctx, const double* x, int N, int D, int mode, double* conde
 
 int sd_linkage_dev(sd_ctx* ctx, const double* d_x, int N, int D, double* d_Z) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, d_x && d_Z, "sd_linkage_dev: null pointer");
     SD_REQUIRE(ctx, N > 1 && D > 0, "sd_linkage_dev: need N > 1, D > 0");
     int rc = reset_status(ctx);
@@ -687,6 +712,7 @@ int sd_linkage_dev(sd_ctx* ctx, const double* d_x, int N, int D, double* d_Z) {
 
 int sd_linkage(sd_ctx* ctx, const double* x, int N, int D, double* Z) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, x && Z, "sd_linkage: null pointer");
     SD_REQUIRE(ctx, N > 1 && D > 0, "sd_linkage: need N > 1, D > 0");
     const size_t bytes = sizeof(double) * (size_t)N * D;
@@ -702,6 +728,7 @@ int sd_linkage(sd_ctx* ctx, const double* x, int N, int D, double* Z) {
 
 int sd_fcluster(sd_ctx* ctx, const double* Z, int N, double cutoff, int32_t* T) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, Z && T, "sd_fcluster: null pointer");
     SD_REQUIRE(ctx, N > 1, "sd_fcluster: need N > 1");
     double* d_Z = (double*)ctx->scratch(BUF_CL_Z, sizeof(double) * 4 * (size_t)N);
@@ -717,6 +744,7 @@ int sd_fcluster(sd_ctx* ctx, const double* Z, int N, double cutoff, int32_t* T) 
 
 int sd_cluster(sd_ctx* ctx, const double* x, int N, int D, double cutoff, int32_t* T) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, x && T, "sd_cluster: null pointer");
     SD_REQUIRE(ctx, N > 1 && D > 0, "sd_cluster: need N > 1, D > 0");
     const size_t bytes = sizeof(double) * (size_t)N * D;
@@ -737,6 +765,7 @@ int sd_cluster(sd_ctx* ctx, const double* x, int N, int D, double cutoff, int32_
 
 int sd_cosine_cdist(sd_ctx* ctx, const double* a, int na, const double* b, int nb, int D, double* out) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, a && b && out, "sd_cosine_cdist: null pointer");
     SD_REQUIRE(ctx, na > 0 && nb > 0 && D > 0, "sd_cosine_cdist: sizes must be positive");
     double* d_a = (double*)ctx->scratch(BUF_CL_X, sizeof(double) * (size_t)na * D);
@@ -767,6 +796,7 @@ void sd_cluster_default_params(sd_cluster_params* p) {
 
 int sd_cluster_labels(sd_ctx* ctx, const double* x, int N, int D, const sd_cluster_params* p, int32_t* labels) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, x && labels && p, "sd_cluster_labels: null pointer");
     SD_REQUIRE(ctx, N > 0 && D > 0, "sd_cluster_labels: N, D must be positive");
     if (N == 1) {
@@ -790,6 +820,7 @@ int sd_clustering_dev(sd_ctx* ctx, const double* d_embeddings, int C, int S, int
                       const double* d_binarized, int F, int32_t* d_hard, double* d_soft, int soft_k_cap,
                       int* num_clusters) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, d_embeddings && d_hard && p, "sd_clustering_dev: null pointer");
     SD_REQUIRE(ctx, C > 0 && S > 0 && D > 0, "sd_clustering_dev: C, S, D must be positive");
     const int R = C * S;
@@ -815,6 +846,7 @@ int sd_clustering_dev(sd_ctx* ctx, const double* d_embeddings, int C, int S, int
 int sd_clustering(sd_ctx* ctx, const double* embeddings, int C, int S, int D, const sd_cluster_params* p,
                   const double* binarized, int F, int32_t* hard, double* soft, int soft_k_cap, int* num_clusters) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, embeddings && hard && p, "sd_clustering: null pointer");
     SD_REQUIRE(ctx, C > 0 && S > 0 && D > 0, "sd_clustering: C, S, D must be positive");
     SD_REQUIRE(ctx, !binarized || F > 0, "sd_clustering: F must be positive when binarized is given");
@@ -859,6 +891,7 @@ int sd_clustering(sd_ctx* ctx, const double* embeddings, int C, int S, int D, co
 int sd_mask_compact(sd_ctx* ctx, const float* wav, const float* masks, int B, int L, int F, int min_num_samples,
                     float* signals, float* wav_lens, uint8_t* too_short, int* all_too_short) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, wav && masks && signals && wav_lens && too_short, "sd_mask_compact: null pointer");
     SD_REQUIRE(ctx, B > 0 && L > 0 && F > 0 && L > F, "sd_mask_compact: need B > 0 and L > F > 0 (SD:753)");
     const size_t wb = sizeof(float) * (size_t)B * L, mb = sizeof(float) * (size_t)B * F;
@@ -888,6 +921,7 @@ int sd_mask_compact(sd_ctx* ctx, const float* wav, const float* masks, int B, in
 int sd_select_masks_dev(sd_ctx* ctx, const double* d_binarized, int C, int F, int K, double min_num_frames,
                         float* d_masks) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, d_binarized && d_masks, "sd_select_masks_dev: null pointer");
     SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0, "sd_select_masks_dev: C, F, K must be positive");
     return select_masks_launch(ctx, d_binarized, C, F, K, min_num_frames, d_masks);
@@ -897,6 +931,7 @@ int sd_mask_compact_file_dev(sd_ctx* ctx, const float* d_wave, int64_t num_sampl
                              int step_samples, const float* d_masks, int F, int batch, int min_num_samples,
                              float* d_signals, float* d_wav_lens, uint8_t* d_too_short, uint8_t* d_batch_invalid) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, d_wave && d_masks && d_signals && d_wav_lens && d_too_short, "sd_mask_compact_file_dev: null pointer");
     SD_REQUIRE(ctx, C > 0 && K > 0 && L > F && F > 0 && batch > 0 && step_samples > 0, "sd_mask_compact_file_dev: bad sizes");
     const int R = C * K;
@@ -924,6 +959,7 @@ int sd_reconstruct_dev(sd_ctx* ctx, const float* d_seg, int C, int F, int K, con
                        const sd_window* count_frames, double* d_out, int64_t cap_elems, int64_t* rows_out,
                        sd_window* frames_out) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, d_seg && d_hard && d_count && d_out && chunks && count_frames, "sd_reconstruct_dev: null pointer");
     SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0 && cols > 0 && n_count > 0, "sd_reconstruct_dev: sizes must be positive");
     SD_REQUIRE(ctx, chunks->num_samples > 0, "sd_reconstruct: chunk window num_samples must be > 0 (SD:1181)");
@@ -936,6 +972,7 @@ int sd_reconstruct(sd_ctx* ctx, const float* segmentations, int C, int F, int K,
                    const sd_window* count_frames, double* out, int64_t cap_elems, int64_t* rows_out, int* cols_out,
                    sd_window* frames_out) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, segmentations && hard_clusters && count && out && chunks && count_frames,
                "sd_reconstruct: null pointer");
     SD_REQUIRE(ctx, C > 0 && F > 0 && K > 0 && n_count > 0, "sd_reconstruct: sizes must be positive");
@@ -973,6 +1010,7 @@ int sd_to_annotation_dev(sd_ctx* ctx, const double* d_scores, int64_t rows, int 
                          double onset, double offset, double min_duration_on, double min_duration_off,
                          double* d_segments, int32_t* d_labels, int64_t cap, int64_t* n_out) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, d_scores && frames && d_segments && d_labels && n_out, "sd_to_annotation_dev: null pointer");
     SD_REQUIRE(ctx, rows > 0 && cols > 0 && cap >= 0, "sd_to_annotation_dev: rows and cols must be positive");
     long* d_n = (long*)ctx->scratch(BUF_GENERIC_A, sizeof(long));
@@ -992,6 +1030,7 @@ int sd_to_annotation(sd_ctx* ctx, const double* scores, int64_t rows, int cols, 
                      double offset, double min_duration_on, double min_duration_off, double* segments,
                      int32_t* labels, int64_t cap, int64_t* n_out) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, scores && frames && segments && labels && n_out, "sd_to_annotation: null pointer");
     SD_REQUIRE(ctx, rows > 0 && cols > 0 && cap >= 0, "sd_to_annotation: rows and cols must be positive");
     const size_t in_b = sizeof(double) * (size_t)rows * cols;
@@ -1017,12 +1056,14 @@ int sd_to_annotation(sd_ctx* ctx, const double* scores, int64_t rows, int cols, 
 
 int sd_ingest_pcm16_dev(sd_ctx* ctx, const int16_t* d_pcm, int64_t n, float* d_out) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, d_pcm && d_out && n > 0, "sd_ingest_pcm16_dev: null pointer or empty input");
     return ingest_pcm16_launch(ctx, d_pcm, (long)n, d_out);
 }
 
 int sd_ingest_pcm16(sd_ctx* ctx, const int16_t* pcm, int64_t n, float* out) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, pcm && out && n > 0, "sd_ingest_pcm16: null pointer or empty input");
     short* d_in = (short*)ctx->scratch(BUF_GENERIC_A, sizeof(short) * (size_t)n);
     float* d_out = (float*)ctx->scratch(BUF_GENERIC_B, sizeof(float) * (size_t)n);
@@ -1053,6 +1094,7 @@ int sd_slide_geometry(int64_t num_samples, double duration, double step, int64_t
 int sd_crop_chunks_dev(sd_ctx* ctx, const float* d_wave, int64_t num_samples, const double* starts_s, int n_chunks,
                        double duration, int sample_rate, float* d_out) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, d_wave && starts_s && d_out, "sd_crop_chunks_dev: null pointer");
     SD_REQUIRE(ctx, num_samples > 0 && n_chunks > 0 && n_chunks <= 65535 && duration > 0 && sample_rate > 0,
                "sd_crop_chunks_dev: bad sizes (1..65535 chunks per call)");
@@ -1062,6 +1104,7 @@ int sd_crop_chunks_dev(sd_ctx* ctx, const float* d_wave, int64_t num_samples, co
 int sd_crop_chunks(sd_ctx* ctx, const float* wave, int64_t num_samples, const double* starts_s, int n_chunks,
                    double duration, int sample_rate, float* out) {
     if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, wave && starts_s && out, "sd_crop_chunks: null pointer");
     SD_REQUIRE(ctx, num_samples > 0 && n_chunks > 0 && duration > 0 && sample_rate > 0, "sd_crop_chunks: bad sizes");
     const size_t L = (size_t)std::floor(duration * sample_rate);
