@@ -17,8 +17,8 @@ assignment) and the skip-average aggregation of the diarization path.
  * `e2e`     : the same step through the host-pointer C-ABI calls (pinned host buffers, H2D + D2H inside)
  * `roofline`: the STFT kernel (the HBM-bound kernel the metric names) -- algorithmic bytes / event time
  * `cpu_baseline`: the reference's own code (oracle/_ref) on this box's host cores, bounded sample
-With N > 1 every rank processes its own batch of files per step (files shard with no data-path collective; labels are
-gathered with one NCCL all_gather per step) -> weak scaling.
+With N > 1 every rank processes its own batch of files (files shard with no data-path collective; the labels of all
+steps are gathered with one NCCL all_gather at the end of the timed region) -> weak scaling.
 """
 import argparse
 import json
@@ -232,7 +232,7 @@ def run_product(args, rank, world):
     chunks, frames, NFd, cap_cnt = job0.chunks, job0.frames, job0.NFd, job0.cap_cnt
     sp, cp, n_out, cf, post, kc = job0.sp, job0.cp, job0.n_out, job0.cf, job0.post, job0.kc
     d_seg, d_bin, d_hard = job0.d_seg, job0.d_bin, job0.d_hard
-    all_hard = torch.empty((nfiles, C_ * S), dtype=torch.int32, device="cuda")
+    all_hard = torch.empty((max(args.steps, args.warmup), nfiles, C_ * S), dtype=torch.int32, device="cuda")
     gathered = [torch.empty_like(all_hard) for _ in range(world)] if world > 1 else None
 
     def barrier():
@@ -255,20 +255,26 @@ def run_product(args, rank, world):
     single_ms = ctx.timer_ms(0) / args.steps
     barrier()
 
-    # ---- pass 2 (the headline): the batch of files, one host thread + context + stream per file, so that the
-    # latency-bound clustering of one file runs concurrently with the other files' clustering (8 SMs each) instead of
-    # leaving 140 SMs idle.  Lock-step per step (measured better than free-running threads: 20-21 ms vs 23-25 ms per
-    # 8 files); the labels of the step's files are gathered over the ranks with one NCCL all_gather per step -- the
-    # only collective on the path (KBs).
+    # ---- pass 2 (the headline): the batch of files, one host thread + context + stream per file, each running its
+    # file `steps` times without waiting for the others (a per-step join makes every step as slow as its slowest
+    # file: 25-27 ms instead of 21 ms per 8 files), so that the latency-bound clustering of one file runs concurrently
+    # with the other files' work instead of leaving 140 SMs idle.  The labels of every (step, file) stay on the
+    # device and are gathered over the ranks with ONE NCCL all_gather at the end of the timed region -- the only
+    # collective on the path (KBs).
     pool = ThreadPoolExecutor(max_workers=nfiles, initializer=torch.cuda.set_device, initargs=(local,))
 
-    def run_batch(nsteps):
+    def worker(j, idx, nsteps):
         for s_ in range(nsteps):
-            for f_ in [pool.submit(j.step_and_sync) for j in jobs]:
-                f_.result()
-            if world > 1:
-                torch.stack([j.hard_t for j in jobs], out=all_hard)
-                dist.all_gather(gathered, all_hard)
+            j.step()
+            with torch.cuda.stream(j.stream):
+                all_hard[s_, idx].copy_(j.hard_t, non_blocking=True)
+        j.ctx.sync()
+
+    def run_batch(nsteps):
+        for f_ in [pool.submit(worker, j, i, nsteps) for i, j in enumerate(jobs)]:
+            f_.result()
+        if world > 1:
+            dist.all_gather(gathered, all_hard)
 
     run_batch(args.warmup)
     barrier()
@@ -357,7 +363,8 @@ def run_product(args, rank, world):
                    "stft_items": items, "samples_per_item": L, "embeddings": items, "embedding_dim": D,
                    "l2_policy": "inputs larger than L2 (STFT streams 3.99 GB per file)",
                    "files_per_step_per_gpu": nfiles,
-                   "concurrency": "one host thread + sd_ctx + CUDA stream per file of the batch, joined every step",
+                   "concurrency": "one host thread + sd_ctx + CUDA stream per file of the batch, free-running over "
+                                  "the steps; one all_gather of all labels at the end of the timed region",
                    "host_wait": sched or "spin (driver default)",
                    "parallelism": "file-sharded x%d" % world},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

@@ -2461,11 +2461,12 @@ int clustering_launch(sd_ctx* ctx, const double* d_emb, int C, int S, int D, con
     if (rc) return rc;
     int K = 0;
     SD_CUDA(ctx, cudaMemcpyAsync(&K, d_num, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    // on the context stream, not cudaMemcpy: a copy on the legacy default stream would wait for every other
+    // (blocking) stream of the process, i.e. for the other files of a batch
+    if (ctx->h_status)
+        SD_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->h_status) {
-        SD_CUDA(ctx, cudaMemcpy(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost));
-        if (*ctx->h_status) return ctx->fail(*ctx->h_status, "Vectors have zero magnitude.");
-    }
+    if (ctx->h_status && *ctx->h_status) return ctx->fail(*ctx->h_status, "Vectors have zero magnitude.");
     if (K < 1 || K > N) return ctx->fail(SD_ERR_CUDA, "cluster post-processing produced %d clusters", K);
     char* base = (char*)ctx->scratch(BUF_CL_OUT, sizeof(double) * (size_t)K * D);
     if (!base) return SD_ERR_NOMEM;
