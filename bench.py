@@ -160,8 +160,13 @@ class FileJob:
         self.n_out, self.cf, self.post, self.kc = C.c_int64(), pkg.Window(), pkg.Window(), C.c_int()
         self.hard_t = torch.empty(C_ * S, dtype=torch.int32, device="cuda")  # torch-owned so NCCL can gather it
         self.d_hard = self.hard_t.data_ptr()
+        # what the synchronous clustering call reads back at its start: the rows that hold an embedding
+        self.keep = np.flatnonzero(~np.isnan(self.emb.reshape(C_ * S, D)[:, 0])).astype(np.int32)
+        self.d_kc = ctx.malloc(4)
         if index > 0:
             self.wav_items = None  # the host copy of a shifted file is not needed again
+
+    use_async = False
 
     def step(self, timed=False):
         C, ctx, pkg = self.C, self.ctx, self.pkg
@@ -179,8 +184,13 @@ class FileJob:
         if timed:
             ctx.timer_stop(2)
             ctx.timer_start(3)
-        ctx._check(ctx.L.sd_clustering_dev(ctx.h, vp(self.d_emb), C_, S, D, C.byref(self.cp), vp(self.d_bin), F,
-                                           vp(self.d_hard), None, 0, C.byref(self.kc)))
+        if self.use_async:  # nothing is read back: the stream never idles between the kernels of this file
+            ctx._check(ctx.L.sd_clustering_async_dev(ctx.h, vp(self.d_emb), C_, S, D, C.byref(self.cp), pkg._ptr(self.keep),
+                                                     self.keep.size, vp(self.d_bin), F, vp(self.d_hard), None, 0,
+                                                     vp(self.d_kc)))
+        else:
+            ctx._check(ctx.L.sd_clustering_dev(ctx.h, vp(self.d_emb), C_, S, D, C.byref(self.cp), vp(self.d_bin), F,
+                                               vp(self.d_hard), None, 0, C.byref(self.kc)))
         if timed:
             ctx.timer_stop(3)
             ctx.timer_start(4)
@@ -264,11 +274,14 @@ def run_product(args, rank, world):
     pool = ThreadPoolExecutor(max_workers=nfiles, initializer=torch.cuda.set_device, initargs=(local,))
 
     def worker(j, idx, nsteps):
+        j.use_async = args.async_clustering
+        j.ctx._check(j.ctx.L.sd_status_reset(j.ctx.h))
         for s_ in range(nsteps):
             j.step()
             with torch.cuda.stream(j.stream):
                 all_hard[s_, idx].copy_(j.hard_t, non_blocking=True)
-        j.ctx.sync()
+        j.ctx._check(j.ctx.L.sd_status_check(j.ctx.h))  # synchronises; device-side errors of all steps surface here
+        j.use_async = False
 
     def run_batch(nsteps):
         for f_ in [pool.submit(worker, j, i, nsteps) for i, j in enumerate(jobs)]:
@@ -366,6 +379,7 @@ def run_product(args, rank, world):
                    "concurrency": "one host thread + sd_ctx + CUDA stream per file of the batch, free-running over "
                                   "the steps; one all_gather of all labels at the end of the timed region",
                    "host_wait": sched or "spin (driver default)",
+                   "clustering_call": "sd_clustering_async_dev" if args.async_clustering else "sd_clustering_dev",
                    "parallelism": "file-sharded x%d" % world},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "files_per_step_per_gpu": 1},
@@ -540,6 +554,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--files", type=int, default=8, help="files per step per GPU, processed concurrently")
+    ap.add_argument("--async-clustering", action="store_true",
+                    help="batch pass with sd_clustering_async_dev (no read-backs) instead of sd_clustering_dev; "
+                         "measured slower in the batch (25 vs 20.5 ms per 8 files), see DESIGN.md section 5")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", 0))

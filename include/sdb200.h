@@ -201,6 +201,20 @@ int sd_clustering_dev(sd_ctx* ctx, const double* d_embeddings, int C, int S, int
                       const double* d_binarized, int F, int32_t* d_hard, double* d_soft, int soft_k_cap,
                       int* num_clusters);
 
+/* Asynchronous Cluster::clustering: like sd_clustering_dev, but nothing is read back and the call only enqueues, so
+ * that a stream never idles between the kernels of one file (which matters when several files are in flight on
+ * different streams).  The caller supplies what the synchronous call reads back at its start: keep_rows (host array,
+ * ascending) = the rows of d_embeddings[C*S][D] whose first element is not NaN (filter_embeddings, SD:2214-2259 --
+ * in the pipeline these are the items that were not "too short").  The final cluster count is written to
+ * *d_num_clusters on the device.  Errors found on the device (zero-magnitude vectors, more than 1 024 raw clusters)
+ * are latched in the context's status word: sd_status_reset before the first call of a sequence, sd_status_check
+ * (synchronises) after the last. */
+int sd_clustering_async_dev(sd_ctx* ctx, const double* d_embeddings, int C, int S, int D, const sd_cluster_params* p,
+                            const int32_t* keep_rows, int n_keep, const double* d_binarized, int F, int32_t* d_hard,
+                            double* d_soft, int soft_k_cap, int32_t* d_num_clusters);
+int sd_status_reset(sd_ctx* ctx);
+int sd_status_check(sd_ctx* ctx);
+
 /* ---- "next" rows --------------------------------------------------------------------------
  * f1: pre-embedding masking.
  * sd_mask_compact      : Helper::interpolate (SD:746) + Helper::padSequence (SD:770) + the wav_lens / too-short logic

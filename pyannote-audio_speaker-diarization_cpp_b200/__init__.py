@@ -73,7 +73,7 @@ EXPORTS = [
     "sd_cluster_labels", "sd_clustering", "sd_clustering_dev", "sd_mask_compact", "sd_select_masks_dev",
     "sd_mask_compact_file_dev", "sd_reconstruct_rows", "sd_reconstruct", "sd_reconstruct_dev", "sd_to_annotation",
     "sd_to_annotation_dev", "sd_ingest_pcm16", "sd_ingest_pcm16_dev", "sd_slide_geometry", "sd_crop_chunks",
-    "sd_crop_chunks_dev",
+    "sd_crop_chunks_dev", "sd_clustering_async_dev", "sd_status_reset", "sd_status_check",
 ]
 
 _lib = None
@@ -157,6 +157,9 @@ def lib():
         "sd_slide_geometry": (i, [i64, d, d, c_lp, c_lp, c_lp]),
         "sd_crop_chunks": (i, [vp, vp, i64, vp, i, d, i, vp]),
         "sd_crop_chunks_dev": (i, [vp, vp, i64, vp, i, d, i, vp]),
+        "sd_clustering_async_dev": (i, [vp, vp, i, i, i, C.POINTER(ClusterParams), vp, i, vp, i, vp, vp, i, vp]),
+        "sd_status_reset": (i, [vp]),
+        "sd_status_check": (i, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -567,3 +570,30 @@ class Context:
         self._check(self.L.sd_crop_chunks(self.h, _ptr(wave), wave.size, _ptr(starts), starts.size, duration, sample_rate,
                                           _ptr(out)))
         return out
+
+    def clustering_async(self, embeddings, binarized=None, params=None):
+        """sd_clustering_async_dev + sd_status_check: same results as clustering(), nothing read back in between."""
+        emb = np.ascontiguousarray(embeddings, np.float64)
+        Cn, S, D = emb.shape
+        keep = np.flatnonzero(~np.isnan(emb.reshape(Cn * S, D)[:, 0])).astype(np.int32)
+        p = params if params is not None else self.cluster_params()
+        d_e = self.to_device(emb)
+        d_b, F = None, 0
+        if binarized is not None:
+            b = np.ascontiguousarray(binarized, np.float64)
+            F = b.shape[1]
+            d_b = self.to_device(b)
+        d_h, d_k = self.malloc(4 * Cn * S), self.malloc(4)
+        try:
+            self._check(self.L.sd_status_reset(self.h))
+            self._check(self.L.sd_clustering_async_dev(self.h, d_e, Cn, S, D, C.byref(p), _ptr(keep), keep.size, d_b, F,
+                                                       d_h, None, 0, d_k))
+            self._check(self.L.sd_status_check(self.h))
+            hard, k = np.empty((Cn, S), np.int32), np.empty(1, np.int32)
+            self.d2h(hard, d_h)
+            self.d2h(k, d_k)
+        finally:
+            for q in (d_e, d_b, d_h, d_k):
+                if q:
+                    self.free(q)
+        return hard, int(k[0])

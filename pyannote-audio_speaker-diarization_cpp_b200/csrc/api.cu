@@ -14,10 +14,10 @@ int linkage_launch(sd_ctx* ctx, const double* d_x, int N, int D, double* d_Z, in
 int fcluster_launch(sd_ctx* ctx, const double* d_Z, int N, double cutoff, int* d_T, int* d_num);
 int cosine_cdist_launch(sd_ctx* ctx, const double* d_a, int na, const double* d_b, int nb, int D, double* d_out);
 int cluster_labels_launch(sd_ctx* ctx, const double* d_x, int N, int D, const sd_cluster_params* p, int* d_labels,
-                          int* d_num);
-int clustering_launch(sd_ctx* ctx, const double* d_emb, int C, int S, int D, const std::vector<int>& h_keep,
+                          int* d_num, int k_cap);
+int clustering_launch(sd_ctx* ctx, const double* d_emb, int C, int S, int D, const int* h_keep, int n_keep,
                       const sd_cluster_params* p, const double* d_binarized, int F, int* d_hard, double* d_soft,
-                      int soft_k_cap, int* num_clusters_out);
+                      int soft_k_cap, int* num_clusters_out, int* d_num_out);
 int row_valid_launch(sd_ctx* ctx, const double* d_emb, int R, int D, unsigned char* d_valid);
 int mask_compact_launch(sd_ctx* ctx, const float* d_wav, const long* d_wav_base, long item_stride, long wav_limit,
                         const float* d_masks, int R, int L, int F, int batch, int min_num_samples, float* d_signals,
@@ -810,7 +810,7 @@ int sd_cluster_labels(sd_ctx* ctx, const double* x, int N, int D, const sd_clust
     SD_CUDA(ctx, cudaMemcpyAsync(d_x, x, bytes, cudaMemcpyHostToDevice, ctx->stream));
     int rc = reset_status(ctx);
     if (rc) return rc;
-    rc = cluster_labels_launch(ctx, d_x, N, D, p, d_lab, d_lab + N);
+    rc = cluster_labels_launch(ctx, d_x, N, D, p, d_lab, d_lab + N, 0);
     if (rc) return rc;
     SD_CUDA(ctx, cudaMemcpyAsync(labels, d_lab, sizeof(int) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
     return check_status(ctx);
@@ -837,9 +837,37 @@ int sd_clustering_dev(sd_ctx* ctx, const double* d_embeddings, int C, int S, int
         if (valid[r]) keep.push_back(r);
     rc = reset_status(ctx);
     if (rc) return rc;
-    rc = clustering_launch(ctx, d_embeddings, C, S, D, keep, p, d_binarized, F, d_hard, d_soft, soft_k_cap,
-                           num_clusters);
+    rc = clustering_launch(ctx, d_embeddings, C, S, D, keep.data(), (int)keep.size(), p, d_binarized, F, d_hard, d_soft,
+                           soft_k_cap, num_clusters, nullptr);
     if (rc) return rc;
+    return check_status(ctx);
+}
+
+int sd_clustering_async_dev(sd_ctx* ctx, const double* d_embeddings, int C, int S, int D, const sd_cluster_params* p,
+                            const int32_t* keep_rows, int n_keep, const double* d_binarized, int F, int32_t* d_hard,
+                            double* d_soft, int soft_k_cap, int32_t* d_num_clusters) {
+    if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    SD_REQUIRE(ctx, d_embeddings && d_hard && p && d_num_clusters, "sd_clustering_async_dev: null pointer");
+    SD_REQUIRE(ctx, C > 0 && S > 0 && D > 0, "sd_clustering_async_dev: C, S, D must be positive");
+    SD_REQUIRE(ctx, n_keep >= 0 && n_keep <= C * S && (n_keep == 0 || keep_rows),
+               "sd_clustering_async_dev: keep_rows must list 0..C*S valid rows");
+    for (int i = 0; i < n_keep; ++i)
+        SD_REQUIRE(ctx, keep_rows[i] >= 0 && keep_rows[i] < C * S && (i == 0 || keep_rows[i] > keep_rows[i - 1]),
+                   "sd_clustering_async_dev: keep_rows must be ascending row indices");
+    return clustering_launch(ctx, d_embeddings, C, S, D, keep_rows, n_keep, p, d_binarized, F, d_hard, d_soft, soft_k_cap,
+                             nullptr, d_num_clusters);
+}
+
+int sd_status_reset(sd_ctx* ctx) {
+    if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    return reset_status(ctx);
+}
+
+int sd_status_check(sd_ctx* ctx) {
+    if (!ctx) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);
     return check_status(ctx);
 }
 
@@ -877,7 +905,8 @@ int sd_clustering(sd_ctx* ctx, const double* embeddings, int C, int S, int D, co
         if (!std::isnan(embeddings[(size_t)r * D])) keep.push_back(r);
     int rc = reset_status(ctx);
     if (rc) return rc;
-    rc = clustering_launch(ctx, d_emb, C, S, D, keep, p, d_bin, F, d_hard, d_soft, soft_k_cap, num_clusters);
+    rc = clustering_launch(ctx, d_emb, C, S, D, keep.data(), (int)keep.size(), p, d_bin, F, d_hard, d_soft, soft_k_cap,
+                           num_clusters, nullptr);
     if (rc) return rc;
     SD_CUDA(ctx, cudaMemcpyAsync(hard, d_hard, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost, ctx->stream));
     if (d_soft)

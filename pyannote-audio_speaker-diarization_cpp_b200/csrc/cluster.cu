@@ -1901,12 +1901,13 @@ struct PostWork {
 constexpr int CM_TILE = 1024;
 __global__ void __launch_bounds__(512)
     cluster_means_kernel(const double* __restrict__ x, const int* __restrict__ labels, int N, int D, int K,
-                         const int* __restrict__ enable, double* __restrict__ means) {
+                         const int* __restrict__ enable, double* __restrict__ means, const int* __restrict__ d_k) {
     __shared__ int list[CM_TILE];
     __shared__ int wcount[16];
     __shared__ int s_total;
     if (enable && !*enable) return;
     const int k = blockIdx.x;
+    if (d_k && k >= *d_k) return;  // asynchronous path: the grid covers the upper bound of the cluster count
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
     double acc[2] = {0.0, 0.0};  // dimensions tid and tid + blockDim.x (D <= 1024)
     long members = 0;
@@ -1956,9 +1957,18 @@ __global__ void __launch_bounds__(512)
 }
 
 // phase 1 of Cluster::cluster's post-processing: labels - 1, counts, large/small split
-__global__ void __launch_bounds__(1024) cluster_post1_kernel(PostWork w, int N, int K, int min_cluster_size) {
+__global__ void __launch_bounds__(1024)
+    cluster_post1_kernel(PostWork w, int N, int K, int min_cluster_size, const int* __restrict__ d_k, int k_cap) {
     __shared__ int s_nl, s_ns;
     const int tid = threadIdx.x;
+    if (d_k) {  // asynchronous path: the cluster count of fcluster is only known on the device
+        K = *d_k;
+        if (K < 1 || K > k_cap) {
+            if (tid == 0) atomicExch(w.status, SD_ERR_CAPACITY);
+            K = K < 1 ? 1 : k_cap;
+        }
+        __syncthreads();  // everybody has read *d_k before thread 0 may overwrite it (num_clusters aliases it)
+    }
     for (int l = tid; l <= K; l += blockDim.x) {
         w.count[l] = 0;
         w.map[l] = l;
@@ -2002,10 +2012,15 @@ __global__ void __launch_bounds__(1024) cluster_post1_kernel(PostWork w, int N, 
 // phase 2: each small cluster -> nearest large cluster by centroid cosine distance with a float running
 // minimum (speakerDiarizer.cpp:2390-2415; large clusters visited in ascending label order), then the rank of
 // each surviving label among the sorted unique labels (speakerDiarizer.cpp:519-548)
-__global__ void __launch_bounds__(1024) cluster_post2_kernel(PostWork w, int N, int D, int K, int min_cluster_size) {
+__global__ void __launch_bounds__(1024)
+    cluster_post2_kernel(PostWork w, int N, int D, int K, int min_cluster_size, const int* __restrict__ d_k) {
     __shared__ int s_next;
     if (!*w.need_means) return;
     const int tid = threadIdx.x;
+    if (d_k) {
+        K = *d_k;
+        __syncthreads();
+    }
     long mcs = (long)round(0.1 * (double)N);
     if (mcs < 1) mcs = 1;
     if (mcs > min_cluster_size) mcs = min_cluster_size;
@@ -2052,10 +2067,11 @@ struct AssignWork {
 // one thread per (embedding row, centroid): cosine distance in the reference's sequential order
 // (speakerDiarizer.cpp:2180-2203); soft = 2 - d
 __global__ void __launch_bounds__(256) assign_dist_kernel(AssignWork w, int R, int D, int K, double* __restrict__ soft,
-                                                         int ld_soft) {
+                                                         int ld_soft, const int* __restrict__ d_k) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long)R * K) return;
+    if (idx >= (long)R * K) return;  // K is the grid's (upper-bound) cluster count
     const int r = (int)(idx / K), k = (int)(idx - (long)r * K);
+    if (d_k && k >= *d_k) return;
     double d;
     if (!cosine_distance(w.emb + (size_t)r * D, w.cent + (size_t)k * D, D, &d)) {
         atomicExch(w.status, SD_ERR_ZERO_MAGNITUDE);
@@ -2069,10 +2085,11 @@ __global__ void __launch_bounds__(256) assign_dist_kernel(AssignWork w, int R, i
 // activity of the speaker over the chunk's frames in float, which is exact in any order
 __global__ void __launch_bounds__(256) assign_argmax_kernel(AssignWork w, int R, int S, int K, int F,
                                                            const double* __restrict__ soft, int ld_soft,
-                                                           int user_cap) {
+                                                           int user_cap, const int* __restrict__ d_k) {
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (r >= R) return;
+    if (d_k) K = *d_k;
     int arg = 0;
     if (lane == 0) {
         double best = -DBL_MAX;
@@ -2381,8 +2398,11 @@ int cosine_cdist_launch(sd_ctx* ctx, const double* d_a, int na, const double* d_
 
 // Cluster::cluster on filtered device rows.  d_x un-normalised [N][D]; d_labels[N] out; d_num out (device int).
 // Synchronises once (the number of flat clusters sizes the post-processing workspace).
+// k_cap == 0: the cluster count is read back after fcluster (one stream synchronisation) and sizes everything;
+// k_cap > 0 : nothing is read back -- buffers and grids are sized for k_cap clusters, the kernels take the count
+//             from *d_num and flag SD_ERR_CAPACITY in the status word if it does not fit.
 int cluster_labels_launch(sd_ctx* ctx, const double* d_x, int N, int D, const sd_cluster_params* p, int* d_labels,
-                          int* d_num) {
+                          int* d_num, int k_cap) {
     if (p->num_clusters != -1)
         return ctx->fail(SD_ERR_UNSUPPORTED, "num_clusters != -1 is not implemented by the reference (SD:2368-2369)");
     double* d_xn = (double*)ctx->scratch(BUF_CL_XN, sizeof(double) * (size_t)N * D);
@@ -2395,10 +2415,13 @@ int cluster_labels_launch(sd_ctx* ctx, const double* d_x, int N, int D, const sd
     if (rc) return rc;
     rc = fcluster_launch(ctx, d_Z, N, (double)p->threshold, d_labels, d_num);  // float threshold, SD:2049/2323
     if (rc) return rc;
-    int K = 0;
-    SD_CUDA(ctx, cudaMemcpyAsync(&K, d_num, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (K < 1 || K > N) return ctx->fail(SD_ERR_CUDA, "fcluster produced %d clusters for %d points", K, N);
+    int K = k_cap;
+    const int* d_k = k_cap > 0 ? d_num : nullptr;
+    if (k_cap <= 0) {
+        SD_CUDA(ctx, cudaMemcpyAsync(&K, d_num, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (K < 1 || K > N) return ctx->fail(SD_ERR_CUDA, "fcluster produced %d clusters for %d points", K, N);
+    }
     const size_t o_count = 0, o_map = align_up(sizeof(int) * (size_t)(K + 1), 256),
                  o_rank = o_map + align_up(sizeof(int) * (size_t)(K + 1), 256),
                  o_flag = o_rank + align_up(sizeof(int) * (size_t)(K + 1), 256), o_sums = o_flag + 256,
@@ -2415,22 +2438,27 @@ int cluster_labels_launch(sd_ctx* ctx, const double* d_x, int N, int D, const sd
     w.num_clusters = d_num;
     w.status = ctx->d_status;
     w.need_means = reinterpret_cast<int*>(base + o_flag);
-    cluster_post1_kernel<<<1, 1024, 0, ctx->stream>>>(w, N, K, p->min_cluster_size);
+    cluster_post1_kernel<<<1, 1024, 0, ctx->stream>>>(w, N, K, p->min_cluster_size, d_k, k_cap);
     SD_LAUNCH_CHECK(ctx);
     if (D > 1024) return ctx->fail(SD_ERR_UNSUPPORTED, "embedding dimension %d > 1024", D);
-    cluster_means_kernel<<<K, means_threads(D), 0, ctx->stream>>>(d_x, d_labels, N, D, K, w.need_means, w.sums);
+    // after phase 1 *d_num is still fcluster's count whenever phase 2 / the means are needed at all
+    cluster_means_kernel<<<K, means_threads(D), 0, ctx->stream>>>(d_x, d_labels, N, D, K, w.need_means, w.sums, d_k);
     SD_LAUNCH_CHECK(ctx);
-    cluster_post2_kernel<<<1, 1024, 0, ctx->stream>>>(w, N, D, K, p->min_cluster_size);
+    cluster_post2_kernel<<<1, 1024, 0, ctx->stream>>>(w, N, D, K, p->min_cluster_size, d_k);
     SD_LAUNCH_CHECK(ctx);
     return SD_OK;
 }
 
 // Cluster::clustering.  d_emb[C*S][D]; h_keep = rows with a non-NaN first element (chunk-major).
-int clustering_launch(sd_ctx* ctx, const double* d_emb, int C, int S, int D, const std::vector<int>& h_keep,
+// d_num_out == nullptr: synchronous (cluster counts are read back, *num_clusters_out is set);
+// d_num_out != nullptr: nothing is read back, the final cluster count is copied to *d_num_out on the device.
+int clustering_launch(sd_ctx* ctx, const double* d_emb, int C, int S, int D, const int* h_keep, int n_keep,
                       const sd_cluster_params* p, const double* d_binarized, int F, int* d_hard, double* d_soft,
-                      int soft_k_cap, int* num_clusters_out) {
+                      int soft_k_cap, int* num_clusters_out, int* d_num_out) {
     const int R = C * S;
-    const int N = (int)h_keep.size();
+    const int N = n_keep;
+    const bool async = d_num_out != nullptr;
+    const int k_cap = async ? std::min(N, 1024) : 0;
     // set_num_clusters (speakerDiarizer.cpp:2261-2296) with the defaults: min 1, max N
     int min_c = p->min_clusters == -1 ? 1 : p->min_clusters;
     int max_c = p->max_clusters == -1 ? N : p->max_clusters;
@@ -2444,6 +2472,10 @@ int clustering_launch(sd_ctx* ctx, const double* d_emb, int C, int S, int D, con
             SD_LAUNCH_CHECK(ctx);
         }
         if (num_clusters_out) *num_clusters_out = 1;
+        if (async) {
+            fill_int_kernel<<<1, 32, 0, ctx->stream>>>(d_num_out, 1, 1);
+            SD_LAUNCH_CHECK(ctx);
+        }
         return SD_OK;
     }
     int* d_keep = (int*)ctx->scratch(BUF_CL_MISC, sizeof(int) * (size_t)N + 256);
@@ -2452,22 +2484,25 @@ int clustering_launch(sd_ctx* ctx, const double* d_emb, int C, int S, int D, con
     int* d_labels = (int*)ctx->scratch(BUF_CL_LABELS, sizeof(int) * (size_t)N + 256);
     if (!d_keep || !d_x || !d_xn || !d_labels) return SD_ERR_NOMEM;
     int* d_num = d_labels + N;  // spare slot after the labels (scratch is over-allocated by 256 B)
-    int rc = upload_small(ctx, d_keep, h_keep.data(), sizeof(int) * (size_t)N);
+    int rc = upload_small(ctx, d_keep, h_keep, sizeof(int) * (size_t)N);
     if (rc) return rc;
     // filter_embeddings (speakerDiarizer.cpp:2214-2259); x is also what cluster_labels normalises again
     gather_normalize_kernel<<<(unsigned)(((long)N * 32 + 255) / 256), 256, 0, ctx->stream>>>(d_emb, d_keep, N, D, d_x, nullptr);
     SD_LAUNCH_CHECK(ctx);
-    rc = cluster_labels_launch(ctx, d_x, N, D, p, d_labels, d_num);
+    rc = cluster_labels_launch(ctx, d_x, N, D, p, d_labels, d_num, k_cap);
     if (rc) return rc;
-    int K = 0;
-    SD_CUDA(ctx, cudaMemcpyAsync(&K, d_num, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    // on the context stream, not cudaMemcpy: a copy on the legacy default stream would wait for every other
-    // (blocking) stream of the process, i.e. for the other files of a batch
-    if (ctx->h_status)
-        SD_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->h_status && *ctx->h_status) return ctx->fail(*ctx->h_status, "Vectors have zero magnitude.");
-    if (K < 1 || K > N) return ctx->fail(SD_ERR_CUDA, "cluster post-processing produced %d clusters", K);
+    int K = k_cap;
+    const int* d_k = async ? d_num : nullptr;
+    if (!async) {
+        SD_CUDA(ctx, cudaMemcpyAsync(&K, d_num, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        // on the context stream, not cudaMemcpy: a copy on the legacy default stream would wait for every other
+        // (blocking) stream of the process, i.e. for the other files of a batch
+        if (ctx->h_status)
+            SD_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->h_status && *ctx->h_status) return ctx->fail(*ctx->h_status, "Vectors have zero magnitude.");
+        if (K < 1 || K > N) return ctx->fail(SD_ERR_CUDA, "cluster post-processing produced %d clusters", K);
+    }
     char* base = (char*)ctx->scratch(BUF_CL_OUT, sizeof(double) * (size_t)K * D);
     if (!base) return SD_ERR_NOMEM;
     AssignWork w;
@@ -2480,16 +2515,19 @@ int clustering_launch(sd_ctx* ctx, const double* d_emb, int C, int S, int D, con
     w.binarized = d_binarized;
     w.status = ctx->d_status;
     if (D > 1024) return ctx->fail(SD_ERR_UNSUPPORTED, "embedding dimension %d > 1024", D);
-    cluster_means_kernel<<<K, means_threads(D), 0, ctx->stream>>>(d_x, d_labels, N, D, K, nullptr, w.cent);
+    cluster_means_kernel<<<K, means_threads(D), 0, ctx->stream>>>(d_x, d_labels, N, D, K, nullptr, w.cent, d_k);
     SD_LAUNCH_CHECK(ctx);
     double* d_softk = (double*)ctx->scratch(BUF_CL_WORK, sizeof(double) * (size_t)R * K);
     if (!d_softk) return SD_ERR_NOMEM;
-    assign_dist_kernel<<<(unsigned)(((long)R * K + 255) / 256), 256, 0, ctx->stream>>>(w, R, D, K, d_softk, K);
+    assign_dist_kernel<<<(unsigned)(((long)R * K + 255) / 256), 256, 0, ctx->stream>>>(w, R, D, K, d_softk, K, d_k);
     SD_LAUNCH_CHECK(ctx);
     assign_argmax_kernel<<<(unsigned)(((long)R * 32 + 255) / 256), 256, 0, ctx->stream>>>(w, R, S, K, F, d_softk, K,
-                                                                                      soft_k_cap);
+                                                                                      soft_k_cap, d_k);
     SD_LAUNCH_CHECK(ctx);
-    if (num_clusters_out) *num_clusters_out = K;
+    if (async)
+        SD_CUDA(ctx, cudaMemcpyAsync(d_num_out, d_num, sizeof(int), cudaMemcpyDeviceToDevice, ctx->stream));
+    else if (num_clusters_out)
+        *num_clusters_out = K;
     return SD_OK;
 }
 

@@ -19,6 +19,8 @@ pkg, synth, geo = ge.load_package(), ge.load_synth(), bench.geometry()
 torch.cuda.set_device(0)
 base = synth.fbank_items(102, geo["items"], geo["L"])
 jobs = [bench.FileJob(pkg, synth, geo, 0, 17 * i, base, i, torch) for i in range(K)]
+for j in jobs:
+    j.use_async = os.environ.get("ASYNC", "0") == "1"  # sd_clustering_async_dev instead of sd_clustering_dev
 pool = ThreadPoolExecutor(max_workers=K)
 acc = np.zeros((K, 5))
 

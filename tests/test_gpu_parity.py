@@ -417,6 +417,36 @@ def test_clustering_degenerate(ctx, oracle, pkg):
     assert e.value.code == pkg.SD_ERR_UNSUPPORTED
 
 
+@pytest.mark.parametrize("seed,C,nspk,tiny,nan_frac", [(1, 30, 2, (), 0.0), (2, 60, 3, (4,), 0.05), (3, 109, 4, (3, 5), 0.1),
+                                                        (4, 200, 6, (2,), 0.02), (5, 591, 4, (), 0.03)])
+def test_clustering_async_equals_sync(ctx, oracle, synth, seed, C, nspk, tiny, nan_frac):
+    """sd_clustering_async_dev (no read-backs, cluster counts stay on the device) gives the synchronous results."""
+    emb, _ = synth.embeddings(seed, C, 3, 192, n_speakers=nspk, tiny=tiny, nan_frac=nan_frac)
+    seg = synth.segmentations(seed + 50, C, 293, 3)
+    b = oracle.binarize(seg)
+    for binar in (None, b):
+        hs, ks = ctx.clustering(emb, binar)
+        ha, ka = ctx.clustering_async(emb, binar)
+        assert ka == ks and np.array_equal(ha, hs)
+    _, ho, _, ko = oracle.clustering_stage(emb, b)
+    assert np.array_equal(ha, ho) and ka == ko
+
+
+def test_clustering_async_degenerate_and_errors(ctx, pkg, synth):
+    emb, _ = synth.embeddings(9, 4, 3, 16, n_speakers=1, tiny=())
+    one = emb.copy()
+    one[:] = np.nan
+    one[0, 0] = emb[0, 0]                     # a single valid embedding: everything lands in cluster 0
+    hs, ks = ctx.clustering(one)
+    ha, ka = ctx.clustering_async(one)
+    assert ka == ks == 1 and np.array_equal(ha, hs)
+    zero = emb.copy()
+    zero[1, 1] = 0.0                          # zero-magnitude embedding -> latched status, reported by the check
+    with pytest.raises(pkg.SdError) as e:
+        ctx.clustering_async(zero)
+    assert e.value.code == pkg.SD_ERR_ZERO_MAGNITUDE if hasattr(pkg, "SD_ERR_ZERO_MAGNITUDE") else e.value.code == 3
+
+
 def test_no_oracle_in_product_path(pkg):
     """The product library neither links nor loads anything under oracle/."""
     maps = open("/proc/self/maps").read()
