@@ -18,6 +18,7 @@ S, D, F = 3, 192, 293
 jobs = []
 for i in range(K):
     ctx = pkg.Context(0)
+    ctx.set_option(4, int(os.environ.get("CLUSTER", "1")))  # SD_OPT_LINKAGE_CLUSTER: 0 = one-CTA merge loop
     emb, _ = synth.embeddings(100 + i, Cn, S, D, n_speakers=3 + i % 3, nan_frac=0.05)
     seg = synth.segmentations(200 + i, Cn, F, S)
     b = (seg > 0.5).astype(np.float64)
