@@ -1793,6 +1793,10 @@ __global__ void __launch_bounds__(1024)
     // start[node] = sum of offsets up to the root: pointer jumping between two buffers
     int *upA = w.up, *accA = w.acc, *upB = w.up2, *accB = w.acc2;
     for (;;) {
+        __syncthreads();  // every thread has read the verdict of the previous round before it is reset (without this
+                          // barrier a fast thread 0 could clear s_live while slower threads had not yet tested it:
+                          // they left the loop one round early and the labels came out wrong -- seen only when other
+                          // kernels shared the SM, i.e. with many contexts in flight)
         if (tid == 0) s_live = 0;
         __syncthreads();
         int live = 0;
@@ -1809,13 +1813,14 @@ __global__ void __launch_bounds__(1024)
         }
         if (live) s_live = 1;
         __syncthreads();
+        const int again = s_live;
         int* t = upA;
         upA = upB;
         upB = t;
         t = accA;
         accA = accB;
         accB = t;
-        if (!s_live) break;
+        if (!again) break;
     }
     w.acc = accA;  // start[] of every node
     // gaps: node k splits [start, start + size) at start + size(first block)
