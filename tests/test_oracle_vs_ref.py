@@ -124,3 +124,50 @@ def test_ingest_rows(oracle, ref, synth, golden_dir):
         a, b = oracle.crop(wave, t), ref.crop(wave, t)
         assert a.shape == b.shape == (80000,) and np.array_equal(a, b)
         assert a.astype(np.float64).sum() == s and (a != 0).sum() == nz
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_next_rows_randomised(oracle, ref, synth, seed):
+    """Randomised geometry for the rows either side of the hot path: masks with empty / one-frame / full rows,
+    different numbers of chunks and speakers, non-binary scores and all four annotation parameters."""
+    rng = np.random.default_rng(100 + seed)
+    B, L, F = int(rng.integers(1, 6)), int(rng.integers(1200, 9000)), int(rng.integers(5, 60))
+    wav = synth.fbank_items(seed, B, L)
+    masks = (rng.random((B, F)) < rng.random()).astype(np.float32)
+    if B > 1:
+        masks[0] = 0
+    if B > 2:
+        masks[1] = 1
+    a, b2 = oracle.mask_compact(wav, masks), ref.mask_compact(wav, masks)
+    assert a[0] == b2[0] and np.array_equal(a[1], b2[1])
+    if a[0] == 0:
+        assert np.array_equal(a[2], b2[2]) and np.array_equal(a[3], b2[3])
+    C = int(rng.integers(12, 40))
+    seg = synth.segmentations(300 + seed, C, 293, 3)
+    bb = oracle.binarize(seg)
+    count, cf = oracle.speaker_count(bb)
+    emb, _ = synth.embeddings(400 + seed, C, 3, 64, n_speakers=int(rng.integers(2, 5)), tiny=())
+    _, hard, _, _ = oracle.clustering_stage(emb, bb)
+    sf = (0.0, 0.5, 5.0, 16000 * (C // 2 + 6))
+    ro, fo = oracle.reconstruct(seg, sf, hard, count, cf)
+    rr, fr = ref.reconstruct(seg, sf, hard, count, cf)
+    assert np.array_equal(ro, rr) and np.array_equal(fo, fr)
+    scores = np.clip(ro * 0.7 + rng.uniform(0, 0.45, ro.shape), 0, 1)
+    for onset, offset, on, off in ((0.5, 0.5, 0.0, 0.5817029476165771), (0.6, 0.35, 0.1, 0.05), (0.5, 0.5, 0.0, 0.0)):
+        so, lo = oracle.to_annotation(scores, fo, onset, offset, on, off)
+        sr, lr = ref.to_annotation(scores, fr, onset, offset, on, off)
+        ko, kr = np.lexsort((lo, so[:, 1], so[:, 0])), np.lexsort((lr, sr[:, 1], sr[:, 0]))
+        assert np.array_equal(so[ko], sr[kr]) and np.array_equal(lo[ko], lr[kr])
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_clustering_stage_randomised(oracle, ref, synth, seed):
+    rng = np.random.default_rng(500 + seed)
+    C = int(rng.integers(8, 70))
+    emb, _ = synth.embeddings(600 + seed, C, 3, 192, n_speakers=int(rng.integers(1, 6)), nan_frac=float(rng.random() * 0.2),
+                              tiny=(2,) if seed % 2 else ())
+    seg = synth.segmentations(700 + seed, C, 293, 3)
+    b = oracle.binarize(seg)
+    rc_o, ho, _, _ = oracle.clustering_stage(emb, b)
+    rc_r, hr = ref.clustering_stage(emb, b)
+    assert rc_o == rc_r == 0 and np.array_equal(ho, hr)
