@@ -65,6 +65,19 @@ int upload_small(sd_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
 }
 }  // namespace sdb
 
+namespace sdb {
+// the one place a latched device status becomes a message
+int status_message(sd_ctx* ctx, int st) {
+    switch (st) {
+        case SD_OK: return SD_OK;
+        case SD_ERR_ZERO_MAGNITUDE: return ctx->fail(st, "Vectors have zero magnitude.");  // SD:494
+        case SD_ERR_CAPACITY:
+            return ctx->fail(st, "more raw clusters than the asynchronous clustering path sizes its buffers for (1024)");
+        default: return ctx->fail(st, "device-side failure %d", st);
+    }
+}
+}  // namespace sdb
+
 using namespace sdb;
 
 struct CtxExtra {
@@ -74,19 +87,14 @@ struct CtxExtra {
     cudaEvent_t ev_in[2] = {}, ev_comp[2] = {}, ev_out[2] = {};
     bool pipe_ready = false;
 };
-static std::vector<std::pair<sd_ctx*, CtxExtra*>> g_extras;  // contexts are few; linear search is fine
 
-static CtxExtra* extra_of(sd_ctx* ctx) {
-    for (auto& e : g_extras)
-        if (e.first == ctx) return e.second;
-    return nullptr;
-}
+// lives in the context itself (no process-wide registry: contexts are created and destroyed from any thread)
+static CtxExtra* extra_of(sd_ctx* ctx) { return static_cast<CtxExtra*>(ctx->extra); }
 
 namespace sdb {
 static Ring* ring_of(sd_ctx* ctx) {
-    for (auto& e : g_extras)
-        if (e.first == ctx) return e.second->ring.base ? &e.second->ring : nullptr;
-    return nullptr;
+    CtxExtra* ex = extra_of(ctx);
+    return ex && ex->ring.base ? &ex->ring : nullptr;
 }
 }  // namespace sdb
 
@@ -119,11 +127,15 @@ int sd_ctx_create(int device, sd_ctx** out) {
         cudaEventCreate(&ctx->ev_start[i]);
         cudaEventCreate(&ctx->ev_stop[i]);
     }
-    cudaMalloc(&ctx->d_status, sizeof(int));
-    cudaMemset(ctx->d_status, 0, sizeof(int));
-    cudaHostAlloc(&ctx->h_status, sizeof(int), cudaHostAllocDefault);
-    cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long));
-    cudaMemset(ctx->d_stats, 0, 8 * sizeof(unsigned long long));
+    if (cudaMalloc(&ctx->d_status, sizeof(int)) != cudaSuccess ||
+        cudaMemset(ctx->d_status, 0, sizeof(int)) != cudaSuccess ||
+        cudaHostAlloc(&ctx->h_status, sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
+        cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(ctx->d_stats, 0, 8 * sizeof(unsigned long long)) != cudaSuccess) {
+        cudaGetLastError();
+        sd_ctx_destroy(ctx);
+        return SD_ERR_CUDA;
+    }
     CtxExtra* ex = new CtxExtra();
     if (cudaHostAlloc(&ex->ring.base, kRingSlots * kRingSlotBytes, cudaHostAllocDefault) == cudaSuccess) {
         for (int i = 0; i < kRingSlots; ++i) cudaEventCreateWithFlags(&ex->ring.ev[i], cudaEventDisableTiming);
@@ -131,7 +143,7 @@ int sd_ctx_create(int device, sd_ctx** out) {
         ex->ring.base = nullptr;
         cudaGetLastError();
     }
-    g_extras.emplace_back(ctx, ex);
+    ctx->extra = ex;
     *out = ctx;
     return SD_OK;
 }
@@ -153,9 +165,7 @@ void sd_ctx_destroy(sd_ctx* ctx) {
         cudaEventDestroy(ctx->ev_start[i]);
         cudaEventDestroy(ctx->ev_stop[i]);
     }
-    for (size_t i = 0; i < g_extras.size(); ++i)
-        if (g_extras[i].first == ctx) {
-            CtxExtra* ex = g_extras[i].second;
+    if (CtxExtra* ex = extra_of(ctx)) {
             if (ex->ring.base) {
                 for (int k = 0; k < kRingSlots; ++k) cudaEventDestroy(ex->ring.ev[k]);
                 cudaFreeHost(ex->ring.base);
@@ -170,8 +180,7 @@ void sd_ctx_destroy(sd_ctx* ctx) {
                 cudaStreamDestroy(ex->s_out);
             }
             delete ex;
-            g_extras.erase(g_extras.begin() + i);
-            break;
+            ctx->extra = nullptr;
         }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -196,6 +205,7 @@ int sd_sync(sd_ctx* ctx) {
 }
 int sd_malloc(sd_ctx* ctx, size_t bytes, void** dptr) {
     if (!ctx || !dptr) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -211,6 +221,7 @@ int sd_free(sd_ctx* ctx, void* dptr) {
 }
 int sd_host_alloc(sd_ctx* ctx, size_t bytes, void** hptr) {
     if (!ctx || !hptr) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);
     cudaError_t e = cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault);
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -244,16 +255,19 @@ int sd_memset(sd_ctx* ctx, void* dst, int value, size_t bytes) {
 }
 int sd_timer_start(sd_ctx* ctx, int slot) {
     if (!ctx || slot < 0 || slot >= 16) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);
     SD_CUDA(ctx, cudaEventRecord(ctx->ev_start[slot], ctx->stream));
     return SD_OK;
 }
 int sd_timer_stop(sd_ctx* ctx, int slot) {
     if (!ctx || slot < 0 || slot >= 16) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);
     SD_CUDA(ctx, cudaEventRecord(ctx->ev_stop[slot], ctx->stream));
     return SD_OK;
 }
 int sd_timer_elapsed_ms(sd_ctx* ctx, int slot, float* ms) {
     if (!ctx || !ms || slot < 0 || slot >= 16) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);
     SD_CUDA(ctx, cudaEventSynchronize(ctx->ev_stop[slot]));
     SD_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev_start[slot], ctx->ev_stop[slot]));
     return SD_OK;
@@ -285,6 +299,7 @@ int sd_ctx_set_option(sd_ctx* ctx, int option, int value) {
 
 int sd_debug_counters(sd_ctx* ctx, int64_t* out8, int reset) {
     if (!ctx || !out8) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);
     SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     SD_CUDA(ctx, cudaMemcpy(out8, ctx->d_stats, 8 * sizeof(int64_t), cudaMemcpyDeviceToHost));
     if (reset) SD_CUDA(ctx, cudaMemset(ctx->d_stats, 0, 8 * sizeof(int64_t)));
@@ -654,10 +669,7 @@ int sd_clean_segmentations(sd_ctx* ctx, const double* binarized, int C, int F, i
 static int check_status(sd_ctx* ctx) {
     SD_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const int st = *ctx->h_status;
-    if (st == SD_ERR_ZERO_MAGNITUDE) return ctx->fail(st, "Vectors have zero magnitude.");
-    if (st) return ctx->fail(st, "device-side failure %d", st);
-    return SD_OK;
+    return sdb::status_message(ctx, *ctx->h_status);
 }
 
 static int reset_status(sd_ctx* ctx) {
@@ -705,8 +717,7 @@ int sd_linkage_dev(sd_ctx* ctx, const double* d_x, int N, int D, double* d_Z) {
     cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, d_x && d_Z, "sd_linkage_dev: null pointer");
     SD_REQUIRE(ctx, N > 1 && D > 0, "sd_linkage_dev: need N > 1, D > 0");
-    int rc = reset_status(ctx);
-    if (rc) return rc;
+    // enqueue only: the status word belongs to the caller (sd_status_reset / sd_status_check)
     return linkage_launch(ctx, d_x, N, D, d_Z, SD_PDIST_EXACT_F64);
 }
 

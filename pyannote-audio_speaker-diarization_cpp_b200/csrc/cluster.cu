@@ -1968,11 +1968,18 @@ __global__ void __launch_bounds__(1024)
     const int tid = threadIdx.x;
     if (d_k) {  // asynchronous path: the cluster count of fcluster is only known on the device
         K = *d_k;
-        if (K < 1 || K > k_cap) {
-            if (tid == 0) atomicExch(w.status, SD_ERR_CAPACITY);
-            K = K < 1 ? 1 : k_cap;
-        }
         __syncthreads();  // everybody has read *d_k before thread 0 may overwrite it (num_clusters aliases it)
+        if (K < 1 || K > k_cap) {
+            // labels run up to K-1 but count/map/rank/sums are sized for k_cap: latch the error and leave a safe
+            // one-cluster result behind instead of indexing past the workspace (the later kernels see K = 1)
+            for (int i = tid; i < N; i += blockDim.x) w.labels[i] = 0;
+            if (tid == 0) {
+                atomicExch(w.status, SD_ERR_CAPACITY);
+                *w.num_clusters = 1;
+                *w.need_means = 0;
+            }
+            return;
+        }
     }
     for (int l = tid; l <= K; l += blockDim.x) {
         w.count[l] = 0;
@@ -2216,12 +2223,8 @@ template <int MODE>
 static int linkage_launch_mode(sd_ctx* ctx, const LinkWork* d_works, const int* d_ns, int problems, int max_n,
                                const int* d_run_flags) {
     const size_t smem = link_smem_bytes(MODE, max_n);
-    static size_t configured = 0;
-    if (smem > configured) {
-        SD_CUDA(ctx, cudaFuncSetAttribute(linkage_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)(MODE == LK_GLOBAL ? smem : (size_t)227 * 1024 - 1024)));
-        configured = (size_t)227 * 1024;
-    }
+    if (kernel_setup(ctx, linkage_kernel<MODE>, (int)(MODE == LK_GLOBAL ? smem : (size_t)227 * 1024 - 1024)) < 0)
+        return SD_ERR_CUDA;
     linkage_kernel<MODE><<<problems, LK_THREADS, smem, ctx->stream>>>(d_works, d_ns, d_run_flags);
     SD_LAUNCH_CHECK(ctx);
     return SD_OK;
@@ -2242,12 +2245,7 @@ template <int MODE, int T>
 static int linkage_fast_launch_mode(sd_ctx* ctx, const LinkWork* d_works, const int* d_ns, int problems, int max_n,
                                     int* d_need_exact) {
     const size_t smem = MODE == LF_SMEM ? linkfast_smem_bytes(max_n) : 64;
-    static bool configured = false;
-    if (!configured) {
-        SD_CUDA(ctx, cudaFuncSetAttribute(linkage_fast_kernel<MODE, T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          220 * 1024));
-        configured = true;
-    }
+    if (kernel_setup(ctx, linkage_fast_kernel<MODE, T>, 220 * 1024) < 0) return SD_ERR_CUDA;
     linkage_fast_kernel<MODE, T><<<problems, T, smem, ctx->stream>>>(d_works, d_ns, d_need_exact);
     SD_LAUNCH_CHECK(ctx);
     return SD_OK;
@@ -2257,12 +2255,7 @@ template <int T, bool GREPL>
 static int linkage_cluster_launch(sd_ctx* ctx, const LinkWork* d_works, const int* d_ns, int problems, int max_n,
                                   int* d_need_exact) {
     const size_t smem = linkcluster_smem_bytes(max_n, GREPL);
-    static bool configured = false;
-    if (!configured) {
-        SD_CUDA(ctx, cudaFuncSetAttribute(linkage_cluster_kernel<T, GREPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          200 * 1024));
-        configured = true;
-    }
+    if (kernel_setup(ctx, linkage_cluster_kernel<T, GREPL>, 200 * 1024) < 0) return SD_ERR_CUDA;
     linkage_cluster_kernel<T, GREPL><<<problems * kLcCtas, T, smem, ctx->stream>>>(d_works, d_ns, d_need_exact);
     SD_LAUNCH_CHECK(ctx);
     return SD_OK;
@@ -2379,11 +2372,7 @@ int fcluster_launch(sd_ctx* ctx, const double* d_Z, int N, double cutoff, int* d
     w.newc = ip + 10 * (size_t)N;
     const size_t smem = sizeof(int) * (11 * (size_t)N + 8);
     const int use_smem = smem <= (size_t)200 * 1024;
-    static bool configured = false;
-    if (!configured) {
-        SD_CUDA(ctx, cudaFuncSetAttribute(fcluster_par_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
-    }
+    if (kernel_setup(ctx, fcluster_par_kernel, 200 * 1024) < 0) return SD_ERR_CUDA;
     fcluster_par_kernel<<<1, 1024, use_smem ? smem : 0, ctx->stream>>>(d_Z, N, cutoff, w, use_smem, d_T, d_num, d_flag);
     SD_LAUNCH_CHECK(ctx);
     fcluster_seq_kernel<<<1, 32, 0, ctx->stream>>>(d_Z, N, cutoff, reinterpret_cast<double*>(base + o_md),
@@ -2505,7 +2494,7 @@ int clustering_launch(sd_ctx* ctx, const double* d_emb, int C, int S, int D, con
         if (ctx->h_status)
             SD_CUDA(ctx, cudaMemcpyAsync(ctx->h_status, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (ctx->h_status && *ctx->h_status) return ctx->fail(*ctx->h_status, "Vectors have zero magnitude.");
+        if (ctx->h_status && *ctx->h_status) return status_message(ctx, *ctx->h_status);
         if (K < 1 || K > N) return ctx->fail(SD_ERR_CUDA, "cluster post-processing produced %d clusters", K);
     }
     char* base = (char*)ctx->scratch(BUF_CL_OUT, sizeof(double) * (size_t)K * D);

@@ -6,7 +6,10 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/sdb200.h"
@@ -88,6 +91,7 @@ struct sd_ctx {
     int linkage_threads = 0;                // tuning hook: 0 = auto, 512 or 1024
     int linkage_cluster = 1;                // 1 = spread the merge loop over an 8-CTA cluster when the state fits
     int stft_variant = 0;                   // tuning hook: 0 = 4 CTAs/SM (<=102 regs), 1 = 3 CTAs/SM
+    void* extra = nullptr;                  // api.cu's CtxExtra (pinned upload ring, copy streams), owned by the context
 
     int fail(int code, const char* fmt, ...) {
         char b[512];
@@ -145,6 +149,39 @@ struct sd_ctx {
 
 namespace sdb {
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and occupancy are per DEVICE and per kernel: remember what was
+// done for every (device, kernel) pair behind a mutex, so that contexts on several GPUs and on several host threads
+// of one process all get the opt-in (a process-wide `static bool` would skip it on the second GPU).
+// Returns the kernel's resident blocks per SM for (threads, smem) when `threads` > 0, else 0.
+template <typename Kernel>
+inline int kernel_setup(sd_ctx* ctx, Kernel kernel, int max_dyn_smem, int threads = 0, size_t smem = 0) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, std::pair<int, int>> done;  // -> (smem opted in, blocks per SM)
+    const void* fn = reinterpret_cast<const void*>(kernel);
+    std::lock_guard<std::mutex> lock(mu);
+    auto& e = done[std::make_pair(ctx->device, fn)];
+    if (max_dyn_smem > e.first) {
+        cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem);
+        if (err != cudaSuccess) {
+            cudaGetLastError();
+            ctx->fail(SD_ERR_CUDA, "cudaFuncSetAttribute(%d B dynamic shared memory): %s", max_dyn_smem,
+                      cudaGetErrorString(err));
+            return -1;
+        }
+        e.first = max_dyn_smem;
+        e.second = 0;
+    }
+    if (threads > 0 && e.second == 0) {
+        int b = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, threads, smem) != cudaSuccess) {
+            cudaGetLastError();
+            b = 1;
+        }
+        e.second = b < 1 ? 1 : b;
+    }
+    return e.second;
+}
+
 // ---- internal launch entry points (device pointers, enqueue only) ----
 int stft_launch(sd_ctx* ctx, const float* d_wav, int B, int L, const sd_stft_params* p, float* d_out);
 int fbank_launch(sd_ctx* ctx, const float* d_wav, int B, int L, const float* d_lens, const sd_fbank_params* p,
@@ -160,6 +197,9 @@ int trim_launch(sd_ctx* ctx, const double* d_bin, int C, int F, int K, int nl, i
 int trim_sum_launch(sd_ctx* ctx, const double* d_bin, int C, int F, int K, int nl, int Ft, double* d_out);
 int rint_launch(sd_ctx* ctx, const double* d_in, int64_t n, int32_t* d_out);
 int clean_launch(sd_ctx* ctx, const double* d_bin, int64_t rows, int K, double* d_out);
+
+// latched device status word -> sd_status + message (api.cu)
+int status_message(sd_ctx* ctx, int st);
 
 // host-side scalar helpers shared by several translation units
 int np_rint_host(double v);

@@ -329,11 +329,7 @@ int pdist_tc_launch(sd_ctx* ctx, const double* d_xn, int N, int D, double* Dm, l
     if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS)
         return ctx->fail(SD_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
 
-    static bool configured = false;
-    if (!configured) {
-        SD_CUDA(ctx, cudaFuncSetAttribute(pdist_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        configured = true;
-    }
+    if (kernel_setup(ctx, pdist_tc_kernel, (int)SMEM_BYTES) < 0) return SD_ERR_CUDA;
     Params p;
     p.xn = d_xn;
     p.norms = d_norm;

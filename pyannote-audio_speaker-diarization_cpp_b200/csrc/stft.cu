@@ -490,14 +490,9 @@ static int ensure_tables(sd_ctx* ctx, const sd_stft_params* p) {
 template <int GROUPS, int MINB>
 static int launch_cfg(sd_ctx* ctx, const float* d_wav, int B, int L, int T, float* d_out) {
     using Cfg = StftCfg<GROUPS>;
-    static int blocks_per_sm = 0;
-    if (!blocks_per_sm) {
-        SD_CUDA(ctx, cudaFuncSetAttribute(stft400_kernel<GROUPS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)Cfg::kSmemBytesStft));
-        SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, stft400_kernel<GROUPS, MINB>,
-                                                                   Cfg::kThreads, Cfg::kSmemBytesStft));
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-    }
+    const int blocks_per_sm = kernel_setup(ctx, stft400_kernel<GROUPS, MINB>, (int)Cfg::kSmemBytesStft, Cfg::kThreads,
+                                           Cfg::kSmemBytesStft);
+    if (blocks_per_sm < 0) return SD_ERR_CUDA;
     const int tiles_per_item = (T + Cfg::kTileFrames - 1) / Cfg::kTileFrames;
     const long total = (long)B * tiles_per_item;
     long grid = (long)ctx->num_sms * blocks_per_sm;
@@ -593,14 +588,8 @@ int fbank_launch(sd_ctx* ctx, const float* d_wav, int B, int L, const float* d_l
     fill_int_kernel2<<<(B + 255) / 256, 256, 0, ctx->stream>>>(d_max, B, (int)0x80000000);  // below every key
     SD_LAUNCH_CHECK(ctx);
     using Cfg = StftCfg<8>;
-    static int blocks_per_sm = 0;
-    if (!blocks_per_sm) {
-        SD_CUDA(ctx, cudaFuncSetAttribute(fbank400_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)Cfg::kSmemBytes));
-        SD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fbank400_kernel<8, 3>, Cfg::kThreads,
-                                                                   Cfg::kSmemBytes));
-        if (blocks_per_sm < 1) blocks_per_sm = 1;
-    }
+    const int blocks_per_sm = kernel_setup(ctx, fbank400_kernel<8, 3>, (int)Cfg::kSmemBytes, Cfg::kThreads, Cfg::kSmemBytes);
+    if (blocks_per_sm < 0) return SD_ERR_CUDA;
     const int tiles_per_item = (T + Cfg::kTileFrames - 1) / Cfg::kTileFrames;
     const long total = (long)B * tiles_per_item;
     long grid = (long)ctx->num_sms * blocks_per_sm;

@@ -119,3 +119,14 @@ def fbank_items(seed, n_items, L):
         keep = int(rng.uniform(0.05, 1.0) * L)
         x[i, keep:] = 0.0
     return np.clip(x, -1.0, 1.0)
+
+
+def stress_embeddings(seed=205, N=50000, D=256, S=12):
+    """configs[4] (clustering stress): N un-normalised D-dimensional embeddings of S planted speakers.
+    Returns (x [N, D] fp64, speaker [N])."""
+    rng = np.random.default_rng(seed)
+    cen = rng.standard_normal((S, D))
+    cen /= np.linalg.norm(cen, axis=1, keepdims=True)
+    spk = rng.integers(0, S, N)
+    x = (cen[spk] + (0.45 / np.sqrt(2 * D)) * rng.standard_normal((N, D))) * rng.uniform(5, 30, (N, 1))
+    return x, spk
