@@ -10,14 +10,19 @@
 // Session::Run does not run a model.  It records the input tensors it was
 // handed (that is exactly what the reference would feed to emd4.onnx /
 // segment2.onnx) into ort_stub::captured and returns zero tensors of the
-// documented output shapes.
+// documented output shapes -- or, when ort_stub::config().deterministic is set,
+// the input-independent stand-in outputs of model_standins.h, which lets the
+// whole pipeline run end to end (tests/dropin).
 #pragma once
 
 #include <cstdint>
+#include <cstdio>
 #include <cstring>
 #include <memory>
 #include <string>
 #include <vector>
+
+#include "model_standins.h"
 
 struct OrtStatus;
 struct OrtSessionOptions {};
@@ -35,6 +40,24 @@ struct Captured {
 inline std::vector<Captured>& captured() {
     static std::vector<Captured> c;
     return c;
+}
+// Whole-pipeline mode (tests/dropin): set by the harness before the pipeline runs.
+struct Config {
+    bool deterministic = false;   // answer with model_standins.h instead of zeros
+    std::vector<int> seg_rows;    // rows the caller keeps from each segmentation call (SegmentModel::infer always
+                                  // submits 32); gives every row its chunk number
+    std::string capture_dir;      // when set, every embedding-model input goes to <dir>/emb_input_NN.f32 (+ lens)
+    int seg_calls = 0, emb_calls = 0;
+};
+inline Config& config() {
+    static Config c;
+    return c;
+}
+inline void dump_f32(const std::string& path, const float* p, size_t n) {
+    if (FILE* f = std::fopen(path.c_str(), "wb")) {
+        std::fwrite(p, sizeof(float), n, f);
+        std::fclose(f);
+    }
 }
 }  // namespace ort_stub
 
@@ -127,6 +150,30 @@ struct Session {
         for (auto d : out.shape) n *= static_cast<size_t>(d);
         out.own.assign(n, 0.0f);
         out.count = n;
+        ort_stub::Config& cfg = ort_stub::config();
+        if (is_embedding()) {
+            if (!cfg.capture_dir.empty() && n_in == 2) {
+                char name[64];
+                std::snprintf(name, sizeof(name), "/emb_input_%02d.f32", cfg.emb_calls);
+                ort_stub::dump_f32(cfg.capture_dir + name, cap[0].data.data(), cap[0].data.size());
+                std::snprintf(name, sizeof(name), "/emb_lens_%02d.f32", cfg.emb_calls);
+                ort_stub::dump_f32(cfg.capture_dir + name, cap[1].data.data(), cap[1].data.size());
+            }
+            if (cfg.deterministic)
+                for (int64_t r = 0; r < batch; ++r)
+                    ort_stub::standin::embedding(cfg.emb_calls * static_cast<int>(batch) + static_cast<int>(r),
+                                                 out.own.data() + r * 192);
+            cfg.emb_calls++;
+        } else {
+            if (cfg.deterministic) {
+                int first = 0;  // chunk number of row 0 = rows kept from the earlier calls
+                for (int i = 0; i < cfg.seg_calls; ++i)
+                    first += i < static_cast<int>(cfg.seg_rows.size()) ? cfg.seg_rows[i] : static_cast<int>(batch);
+                for (int64_t r = 0; r < batch; ++r)
+                    ort_stub::standin::segmentation(first + static_cast<int>(r), out.own.data() + r * 293 * 3);
+            }
+            cfg.seg_calls++;
+        }
         std::vector<Value> res;
         res.push_back(std::move(out));
         return res;

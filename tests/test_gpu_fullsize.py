@@ -1,5 +1,7 @@
 """GPU: BASELINE.json configurations at full size, checked through size-independent properties (and, where the
 CPU oracle still finishes in tens of seconds, bit for bit)."""
+import hashlib
+import json
 import os
 
 import numpy as np
@@ -77,25 +79,34 @@ def test_cfg3_one_hour_clustering_bit_exact(ctx, oracle, synth):
     assert np.array_equal(ctx.fcluster(Z, THRESH), oracle.fcluster(Z, THRESH))
 
 
-def test_cfg5_clustering_stress_50k(ctx, oracle):
-    """configs[4]: 50 000 x 256 embeddings.  The reference itself is invalid here (its int condensed index
-    overflows for N > 46 341, clustering.cpp:236-242) and scipy needs ~10 minutes, so: structural validity,
-    the centroid-distance property on sampled merges, fcluster against the CPU restatement on the GPU's Z, and
-    recovery of the planted speakers."""
-    N, D, S = 50000, 256, 12
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_cfg5_clustering_stress_50k(ctx, oracle, synth):
+    """configs[4]: 50 000 x 256 embeddings, bit for bit.  The reference itself is invalid here (its int condensed
+    index overflows for N > 46 341, clustering.cpp:236-242); the known answer is the SHA-256 of the dendrogram and
+    labels that scipy 1.18.1 linkage(method="centroid") / fcluster AND the C restatement both produce
+    (oracle/make_golden_cfg5.py, ~20 CPU-minutes, tests/golden/cfg5_sha256.json).  Plus the size-independent
+    properties: structural validity, centroid distances on sampled merges, recovery of the planted speakers."""
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "cfg5_sha256.json")))
+    N, D, S = gold["config"]["N"], gold["config"]["D"], gold["config"]["S"]
+    x, spk = synth.stress_embeddings(gold["config"]["seed"], N, D, S)
+    assert sha(x) == gold["input_sha256"]
     rng = np.random.default_rng(205)
-    cen = rng.standard_normal((S, D))
-    cen /= np.linalg.norm(cen, axis=1, keepdims=True)
-    spk = rng.integers(0, S, N)
-    x = (cen[spk] + (0.45 / np.sqrt(2 * D)) * rng.standard_normal((N, D))) * rng.uniform(5, 30, (N, 1))
     xn = ctx.normalize_embeddings(x)
+    assert sha(xn) == gold["normalized_sha256"]
     assert np.abs(np.linalg.norm(xn, axis=1) - 1).max() < 1e-6
     Z = ctx.linkage(xn)
+    for k, h in gold["Z_prefix_sha256"].items():  # locates a divergence if there ever is one
+        assert sha(Z[:int(k)]) == h, "dendrogram differs from scipy within the first %s merges" % k
+    assert sha(Z) == gold["Z_sha256"]
     check_dendrogram(Z, N)
     assert centroid_distance_property(Z, xn, rng, samples=60) < 1e-9
     T = ctx.fcluster(Z, THRESH)
+    assert sha(T.astype(np.int32)) == gold["labels_sha256"]
     assert np.array_equal(T, oracle.fcluster(Z, THRESH))
-    assert T.max() == S
+    assert T.max() == S == gold["n_clusters"]
     # every flat cluster is one planted speaker
     for c in range(1, S + 1):
         assert len(np.unique(spk[T == c])) == 1

@@ -40,8 +40,9 @@ def test_aggregate_other_geometry(oracle, ref, synth):
 @pytest.mark.parametrize("N,D,seed", [(2, 4, 0), (3, 192, 1), (50, 16, 2), (257, 192, 3), (700, 192, 4)])
 def test_linkage_fcluster(oracle, ref, N, D, seed):
     rng = np.random.default_rng(seed)
-    x = oracle.normalize(rng.standard_normal((N, D)))
-    assert np.array_equal(x, ref.normalize(x * 1.0)) or True
+    raw = rng.standard_normal((N, D)) * rng.uniform(0.01, 30.0, (N, 1))  # un-normalised, like ECAPA embeddings
+    x = oracle.normalize(raw)
+    assert np.array_equal(x, ref.normalize(raw))  # Helper::normalizeEmbeddings, float-rounded norm (SD:330-357)
     assert np.array_equal(oracle.pdist(x), ref.pdist(x))
     Zo, Zr = oracle.linkage(x), ref.linkage(x)
     assert np.array_equal(Zo, Zr)
