@@ -86,18 +86,31 @@ int sd_flush_l2(sd_ctx* ctx);
  * of EmbeddingModel1::_infer (SD:1889-1917): centre zero padding n_fft/2, periodic Hamming window,
  * n_fft-point real DFT, one-sided, un-normalised, layout [B][T][n_fft/2+1][{re,im}] fp32, T = 1 + L/hop. */
 typedef enum sd_window_kind { SD_WINDOW_HAMMING_PERIODIC = 0, SD_WINDOW_POVEY = 1, SD_WINDOW_CUSTOM = 2 } sd_window_kind;
+/* Where frame t starts and what lies beyond the ends of the signal:
+ *  SD_FRAMES_CENTER_ZERO   t*hop - n_fft/2, zeros: torch::stft(center=true, "constant"), the reference (SD:2008);
+ *                          T = 1 + L/hop
+ *  SD_FRAMES_KALDI_REFLECT t*hop - (n_fft/2 - hop/2), the signal mirrored about its ends: Kaldi snip_edges=false;
+ *                          T = (L + hop/2) / hop
+ *  SD_FRAMES_KALDI_SNIP    t*hop, whole frames only: Kaldi snip_edges=true; T = 1 + (L - n_fft)/hop */
+typedef enum sd_frame_mode { SD_FRAMES_CENTER_ZERO = 0, SD_FRAMES_KALDI_REFLECT = 1, SD_FRAMES_KALDI_SNIP = 2 } sd_frame_mode;
 
 typedef struct sd_stft_params {
     int n_fft;          /* 400 (the only size with a kernel today) */
     int hop;            /* 160 */
     int window_kind;    /* sd_window_kind */
     const float* window; /* HOST pointer to n_fft floats when SD_WINDOW_CUSTOM, else NULL */
-    float preemph;      /* 0 = off (reference); 0.97 = Kaldi-style per-frame pre-emphasis */
+    float preemph;      /* 0 = off (reference); 0.97 = Kaldi per-frame pre-emphasis y[n] = x[n] - c x[n-1], y[0] = x[0] - c x[0] */
     int pad_batch_to;   /* 32 reproduces _infer's fixed batch (rows >= B are zero); 0 = no padding */
+    int frame_mode;     /* sd_frame_mode; 0 = the reference */
+    int remove_dc_offset; /* Kaldi: subtract the mean of every frame before pre-emphasis; 0 = off (reference) */
 } sd_stft_params;
 
 void sd_stft_default_params(sd_stft_params* p);
-int64_t sd_stft_num_frames(int L, int hop);
+/* Kaldi-compatible framing (kaldi::FrameExtractionOptions defaults at 16 kHz / 25 ms / 10 ms with a 400-point
+ * transform, i.e. round_to_power_of_two=false): povey window, pre-emphasis 0.97, DC removal, snip_edges as given. */
+void sd_stft_kaldi_params(sd_stft_params* p, int snip_edges);
+int64_t sd_stft_num_frames(int L, int hop); /* SD_FRAMES_CENTER_ZERO */
+int64_t sd_stft_num_frames_mode(int L, int n_fft, int hop, int frame_mode);
 /* out must hold max(B, pad_batch_to) * T * (n_fft/2+1) * 2 floats. */
 int sd_stft(sd_ctx* ctx, const float* wav, int B, int L, const sd_stft_params* p, float* out);
 int sd_stft_dev(sd_ctx* ctx, const float* d_wav, int B, int L, const sd_stft_params* p, float* d_out);
@@ -115,8 +128,15 @@ typedef struct sd_fbank_params {
     float top_db;      /* 80 */
     float amin;        /* 1e-10 */
     int mean_norm;     /* 1 */
+    int mel_kind;      /* 0: speechbrain Filterbank (triangles in Hz, mel = 2595 log10(1 + f/700));
+                          1: Kaldi mel banks (triangles in mel, mel = 1127 ln(1 + f/700), bins below n_fft/2 only) */
+    int log_kind;      /* 0: 10 log10 (dB) clamped to max - top_db;  1: natural log, floor amin, no clamp (Kaldi) */
 } sd_fbank_params;
 void sd_fbank_default_params(sd_fbank_params* p);
+/* torchaudio.compliance.kaldi.fbank / kaldi::FbankOptions defaults with an 80-bin bank and a 400-point transform:
+ * low_freq 20, high_freq Nyquist, natural log floored at FLT_EPSILON, no mean normalisation; framing as
+ * sd_stft_kaldi_params. */
+void sd_fbank_kaldi_params(sd_fbank_params* p, int snip_edges);
 int sd_fbank(sd_ctx* ctx, const float* wav, int B, int L, const float* wav_lens, const sd_fbank_params* p, float* out);
 int sd_fbank_dev(sd_ctx* ctx, const float* d_wav, int B, int L, const float* d_wav_lens, const sd_fbank_params* p,
                  float* d_out);
@@ -201,6 +221,13 @@ int sd_clustering_dev(sd_ctx* ctx, const double* d_embeddings, int C, int S, int
                       const double* d_binarized, int F, int32_t* d_hard, double* d_soft, int soft_k_cap,
                       int* num_clusters);
 
+/* sd_clustering with one more optional output: dist[C][S][soft_k_cap] = the cosine distances to the centroids
+ * themselves (Helper::cosineSimilarity inside assign_embeddings, SD:2183; soft = 2 - dist), NaN beyond the cluster
+ * count.  This is what the reference dumps as cpp_dist (SD:2186). */
+int sd_clustering_ex(sd_ctx* ctx, const double* embeddings, int C, int S, int D, const sd_cluster_params* p,
+                     const double* binarized, int F, int32_t* hard, double* soft, double* dist, int soft_k_cap,
+                     int* num_clusters);
+
 /* Asynchronous Cluster::clustering: like sd_clustering_dev, but nothing is read back and the call only enqueues, so
  * that a stream never idles between the kernels of one file (which matters when several files are in flight on
  * different streams).  The caller supplies what the synchronous call reads back at its start: keep_rows (host array,
@@ -275,6 +302,36 @@ int sd_crop_chunks(sd_ctx* ctx, const float* wave, int64_t num_samples, const do
                    double duration, int sample_rate, float* out);
 int sd_crop_chunks_dev(sd_ctx* ctx, const float* d_wave, int64_t num_samples, const double* starts_s, int n_chunks,
                        double duration, int sample_rate, float* d_out);
+
+/* ---- stage intermediates (WRITE_DATA builds of the reference) ------------------------------------------
+ * The bodies this library replaces write their intermediates to /tmp/cpp_<stage>.txt when the reference is built with
+ * WRITE_DATA (consumer: pipeline/script/verifyEveryStepResult.py:6-17).  The fused kernels never materialise them;
+ * these entry points compute each one on the device so that the host shim can re-emit the dumps, following the
+ * reference's own call structure (host pointers, synchronous).
+ * sd_binarize_rows_stages    : `on`, `same_as`, `well_defined_idx` of binarize_ndarray (SD:1574-1633).  All [R][F];
+ *                              well_defined_idx rows are -1 padded, *idx_cols = the width the reference writes
+ *                              (longest row, Helper::wellDefinedIndex SD:623-651).
+ * sd_trim_sum                : np.sum(trimmed, axis=-1) of speaker_count (SD:1701-1714) -> out[C][F - floor(F*left) -
+ *                              floor(F*right)].
+ * sd_mask_interpolate        : Helper::interpolate (SD:746-767): masks[B][F] -> imasks[B][L] (0/1) and counts[B] =
+ *                              imasks.sum(dim=1), the wav_lens before normalisation (SD:2466-2476).
+ * sd_clustered_segmentations : clusteredSegmentations of reconstruct (SD:2815-2838): out[C][F][cols], NaN where no
+ *                              local speaker of the chunk belongs to the cluster.
+ * sd_to_diarization          : to_diarization after its aggregate (SD:2672-2764): activations[n_frames][cols] on
+ *                              window act_frames (the aggregate's post_frames, num_samples included) + count ->
+ *                              out[rows][cols]; optional sorted_speakers[rows][cols] (SD:2720-2730) and
+ *                              crop4 = {first activation row, rows, first count row, count rows} (crop_segment). */
+int sd_binarize_rows_stages(sd_ctx* ctx, const double* scores, int R, int F, double onset, uint8_t* on,
+                            int32_t* same_as, int32_t* well_defined_idx, int* idx_cols);
+int sd_trim_sum(sd_ctx* ctx, const double* binarized, int C, int F, int K, double left, double right, double* out);
+int sd_mask_interpolate(sd_ctx* ctx, const float* masks, int B, int F, int L, float threshold, uint8_t* imasks,
+                        int32_t* counts);
+int sd_clustered_segmentations(sd_ctx* ctx, const float* segmentations, int C, int F, int K,
+                               const int32_t* hard_clusters, int cols, double* out);
+int sd_to_diarization(sd_ctx* ctx, const double* activations, int64_t n_frames, int cols, const sd_window* act_frames,
+                      const int32_t* count, int64_t n_count, const sd_window* count_frames, double* out,
+                      int64_t cap_elems, int64_t* rows_out, sd_window* frames_out, int32_t* sorted_speakers,
+                      int64_t* crop4);
 
 #ifdef __cplusplus
 }

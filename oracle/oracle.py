@@ -564,3 +564,63 @@ class Ref:
         out = np.empty(80000 + 8, np.float32)
         n = self.lib.ref_crop(_p(wave, c_fp), wave.size, float(start), _p(out, c_fp))
         return out[:n].copy()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Kaldi-compatible front-end (BASELINE north_star bullet 1).  Not on the reference's path -- the reference frames
+# with torch::stft / Hamming -- so there is no reference code to restate: this follows kaldi::ProcessWindow /
+# kaldi::MelBanks as published (feature-window.cc, mel-computations.cc) in the form torchaudio.compliance.kaldi gives
+# them, in fp64 numpy, and is pinned against torchaudio.compliance.kaldi.fbank itself (tests/test_oracle_golden.py,
+# tests/golden/kaldi_fbank.npz generated by oracle/make_golden_kaldi.py).
+def kaldi_frames(x, snip_edges=False, preemph=0.97, remove_dc_offset=True, n_fft=400, hop=160):
+    """Conditioned, povey-windowed frames [T, n_fft] (fp64) of a 1-D signal."""
+    x = np.asarray(x, np.float64)
+    L = x.shape[0]
+    if snip_edges:
+        T = 0 if L < n_fft else 1 + (L - n_fft) // hop
+        idx = hop * np.arange(T)[:, None] + np.arange(n_fft)[None, :]
+    else:
+        T = (L + hop // 2) // hop
+        idx = hop * np.arange(T)[:, None] - (n_fft // 2 - hop // 2) + np.arange(n_fft)[None, :]
+        idx = np.where(idx < 0, -idx - 1, idx)
+        idx = np.where(idx >= L, 2 * L - 1 - idx, idx)
+    fr = x[idx]
+    if remove_dc_offset:
+        fr = fr - fr.mean(axis=1, keepdims=True)
+    if preemph != 0.0:
+        prev = np.concatenate([fr[:, :1], fr[:, :-1]], axis=1)
+        fr = fr - preemph * prev
+    n = np.arange(n_fft)
+    window = (0.5 - 0.5 * np.cos(2.0 * np.pi * n / (n_fft - 1))) ** 0.85
+    return fr * window
+
+
+def kaldi_stft(x, **kw):
+    """[T, 201, 2] fp64 spectrum of the conditioned frames."""
+    X = np.fft.rfft(kaldi_frames(x, **kw), axis=1)
+    return np.stack([X.real, X.imag], axis=-1)
+
+
+def kaldi_mel_banks(n_mels=80, n_fft=400, sample_rate=16000, low_freq=20.0, high_freq=0.0):
+    """[n_mels, n_fft/2 + 1] (last column zero: the Nyquist bin gets no weight)."""
+    nyq = 0.5 * sample_rate
+    high = high_freq + nyq if high_freq <= 0 else high_freq
+    mel = lambda f: 1127.0 * np.log(1.0 + np.asarray(f, np.float64) / 700.0)
+    lo, hi = mel(low_freq), mel(high)
+    delta = (hi - lo) / (n_mels + 1)
+    m = np.arange(n_mels)[:, None]
+    left, center, right = lo + m * delta, lo + (m + 1) * delta, lo + (m + 2) * delta
+    mf = mel(sample_rate / n_fft * np.arange(n_fft // 2))[None, :]
+    w = np.maximum(0.0, np.minimum((mf - left) / (center - left), (right - mf) / (right - center)))
+    return np.concatenate([w, np.zeros((n_mels, 1))], axis=1)
+
+
+def kaldi_fbank(x, n_mels=80, snip_edges=False, preemph=0.97, remove_dc_offset=True, subtract_mean=False):
+    """log mel energies [T, n_mels] like torchaudio.compliance.kaldi.fbank(dither=0, round_to_power_of_two=False,
+    window_type="povey", use_power=True, use_log_fbank=True, low_freq=20, high_freq=0)."""
+    X = np.fft.rfft(kaldi_frames(x, snip_edges, preemph, remove_dc_offset), axis=1)
+    e = (np.abs(X) ** 2) @ kaldi_mel_banks(n_mels).T
+    out = np.log(np.maximum(e, float(np.finfo(np.float32).eps)))
+    if subtract_mean:
+        out = out - out.mean(axis=0, keepdims=True)
+    return out

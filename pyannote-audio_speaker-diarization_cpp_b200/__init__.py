@@ -42,12 +42,14 @@ class Window(C.Structure):
 
 class StftParams(C.Structure):
     _fields_ = [("n_fft", C.c_int), ("hop", C.c_int), ("window_kind", C.c_int), ("window", c_fp),
-                ("preemph", C.c_float), ("pad_batch_to", C.c_int)]
+                ("preemph", C.c_float), ("pad_batch_to", C.c_int), ("frame_mode", C.c_int),
+                ("remove_dc_offset", C.c_int)]
 
 
 class FbankParams(C.Structure):
     _fields_ = [("stft", StftParams), ("n_mels", C.c_int), ("f_min", C.c_float), ("f_max", C.c_float),
-                ("sample_rate", C.c_int), ("top_db", C.c_float), ("amin", C.c_float), ("mean_norm", C.c_int)]
+                ("sample_rate", C.c_int), ("top_db", C.c_float), ("amin", C.c_float), ("mean_norm", C.c_int),
+                ("mel_kind", C.c_int), ("log_kind", C.c_int)]
 
 
 class ClusterParams(C.Structure):
@@ -74,6 +76,8 @@ EXPORTS = [
     "sd_mask_compact_file_dev", "sd_reconstruct_rows", "sd_reconstruct", "sd_reconstruct_dev", "sd_to_annotation",
     "sd_to_annotation_dev", "sd_ingest_pcm16", "sd_ingest_pcm16_dev", "sd_slide_geometry", "sd_crop_chunks",
     "sd_crop_chunks_dev", "sd_clustering_async_dev", "sd_status_reset", "sd_status_check",
+    "sd_clustering_ex", "sd_binarize_rows_stages", "sd_trim_sum", "sd_mask_interpolate", "sd_clustered_segmentations",
+    "sd_to_diarization", "sd_stft_kaldi_params", "sd_stft_num_frames_mode", "sd_fbank_kaldi_params",
 ]
 
 _lib = None
@@ -160,6 +164,15 @@ def lib():
         "sd_clustering_async_dev": (i, [vp, vp, i, i, i, C.POINTER(ClusterParams), vp, i, vp, i, vp, vp, i, vp]),
         "sd_status_reset": (i, [vp]),
         "sd_status_check": (i, [vp]),
+        "sd_stft_kaldi_params": (None, [C.POINTER(StftParams), i]),
+        "sd_stft_num_frames_mode": (i64, [i, i, i, i]),
+        "sd_fbank_kaldi_params": (None, [C.POINTER(FbankParams), i]),
+        "sd_clustering_ex": (i, [vp, vp, i, i, i, C.POINTER(ClusterParams), vp, i, vp, vp, vp, i, c_ip]),
+        "sd_binarize_rows_stages": (i, [vp, vp, i, i, d, vp, vp, vp, c_ip]),
+        "sd_trim_sum": (i, [vp, vp, i, i, i, d, d, vp]),
+        "sd_mask_interpolate": (i, [vp, vp, i, i, i, C.c_float, vp, vp]),
+        "sd_clustered_segmentations": (i, [vp, vp, i, i, i, vp, i, vp]),
+        "sd_to_diarization": (i, [vp, vp, i64, i, W, vp, i64, W, vp, i64, c_lp, W, vp, c_lp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -285,12 +298,20 @@ class Context:
             p.window = self._win_keep.ctypes.data_as(c_fp)
         return p
 
-    def stft(self, wav, pad_batch_to=0, window=None, window_kind=0):
+    def stft_kaldi_params(self, snip_edges=False, preemph=0.97, remove_dc_offset=True):
+        """Kaldi framing: povey window, per-frame pre-emphasis / DC removal, snip_edges as given."""
+        p = StftParams()
+        self.L.sd_stft_kaldi_params(C.byref(p), int(snip_edges))
+        p.preemph = preemph
+        p.remove_dc_offset = int(remove_dc_offset)
+        return p
+
+    def stft(self, wav, pad_batch_to=0, window=None, window_kind=0, params=None):
         """EmbeddingModel1::infer up to the ORT input: [max(B,pad)][T][201][2] fp32."""
         wav = np.ascontiguousarray(wav, np.float32)
         B, Ls = wav.shape
-        p = self.stft_params(pad_batch_to, window, window_kind)
-        T = self.L.sd_stft_num_frames(Ls, p.hop)
+        p = params or self.stft_params(pad_batch_to, window, window_kind)
+        T = self.L.sd_stft_num_frames_mode(Ls, p.n_fft, p.hop, p.frame_mode)
         out = np.empty((max(B, pad_batch_to), T, p.n_fft // 2 + 1, 2), np.float32)
         self._check(self.L.sd_stft(self.h, _ptr(wav), B, Ls, C.byref(p), _ptr(out)))
         return out
@@ -313,12 +334,21 @@ class Context:
         self.L.sd_fbank_default_params(C.byref(p))
         return p
 
-    def fbank(self, wav, wav_lens, params=None):
+    def fbank_kaldi_params(self, snip_edges=False, preemph=0.97, remove_dc_offset=True, n_mels=80):
+        """torchaudio.compliance.kaldi.fbank defaults on a 400-point transform (round_to_power_of_two=False)."""
+        p = FbankParams()
+        self.L.sd_fbank_kaldi_params(C.byref(p), int(snip_edges))
+        p.stft.preemph = preemph
+        p.stft.remove_dc_offset = int(remove_dc_offset)
+        p.n_mels = n_mels
+        return p
+
+    def fbank(self, wav, wav_lens=None, params=None):
         wav = np.ascontiguousarray(wav, np.float32)
-        wav_lens = np.ascontiguousarray(wav_lens, np.float32)
         B, Ls = wav.shape
+        wav_lens = np.ascontiguousarray(np.ones(B) if wav_lens is None else wav_lens, np.float32)
         p = params or self.fbank_params()
-        T = self.L.sd_stft_num_frames(Ls, p.stft.hop)
+        T = self.L.sd_stft_num_frames_mode(Ls, p.stft.n_fft, p.stft.hop, p.stft.frame_mode)
         out = np.empty((B, T, p.n_mels), np.float32)
         self._check(self.L.sd_fbank(self.h, _ptr(wav), B, Ls, _ptr(wav_lens), C.byref(p), _ptr(out)))
         return out

@@ -17,7 +17,7 @@ int cluster_labels_launch(sd_ctx* ctx, const double* d_x, int N, int D, const sd
                           int* d_num, int k_cap);
 int clustering_launch(sd_ctx* ctx, const double* d_emb, int C, int S, int D, const int* h_keep, int n_keep,
                       const sd_cluster_params* p, const double* d_binarized, int F, int* d_hard, double* d_soft,
-                      int soft_k_cap, int* num_clusters_out, int* d_num_out);
+                      int soft_k_cap, int* num_clusters_out, int* d_num_out, double* d_dist = nullptr);
 int row_valid_launch(sd_ctx* ctx, const double* d_emb, int R, int D, unsigned char* d_valid);
 int mask_compact_launch(sd_ctx* ctx, const float* d_wav, const long* d_wav_base, long item_stride, long wav_limit,
                         const float* d_masks, int R, int L, int F, int batch, int min_num_samples, float* d_signals,
@@ -327,9 +327,29 @@ void sd_stft_default_params(sd_stft_params* p) {
     p->window = nullptr;
     p->preemph = 0.f;
     p->pad_batch_to = 0;
+    p->frame_mode = SD_FRAMES_CENTER_ZERO;
+    p->remove_dc_offset = 0;
+}
+
+void sd_stft_kaldi_params(sd_stft_params* p, int snip_edges) {
+    if (!p) return;
+    sd_stft_default_params(p);
+    p->window_kind = SD_WINDOW_POVEY;
+    p->preemph = 0.97f;
+    p->remove_dc_offset = 1;
+    p->frame_mode = snip_edges ? SD_FRAMES_KALDI_SNIP : SD_FRAMES_KALDI_REFLECT;
 }
 
 int64_t sd_stft_num_frames(int L, int hop) { return hop > 0 ? 1 + L / hop : 0; }
+
+int64_t sd_stft_num_frames_mode(int L, int n_fft, int hop, int frame_mode) {
+    if (hop <= 0 || n_fft <= 0) return 0;
+    switch (frame_mode) {
+        case SD_FRAMES_KALDI_REFLECT: return (L + hop / 2) / hop;
+        case SD_FRAMES_KALDI_SNIP: return L < n_fft ? 0 : 1 + (L - n_fft) / hop;
+        default: return 1 + L / hop;
+    }
+}
 
 int sd_stft_dev(sd_ctx* ctx, const float* d_wav, int B, int L, const sd_stft_params* p, float* d_out) {
     if (!ctx) return SD_ERR_INVALID;
@@ -348,7 +368,7 @@ int sd_stft(sd_ctx* ctx, const float* wav, int B, int L, const sd_stft_params* p
     cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, wav && out && p, "sd_stft: null pointer");
     SD_REQUIRE(ctx, B > 0 && L > 0, "sd_stft: B and L must be positive");
-    const int64_t T = sd_stft_num_frames(L, p->hop);
+    const int64_t T = sd_stft_num_frames_mode(L, p->n_fft, p->hop, p->frame_mode);
     const size_t in_item = sizeof(float) * (size_t)L;
     const size_t out_item = sizeof(float) * (size_t)T * (p->n_fft / 2 + 1) * 2;
     CtxExtra* ex = extra_of(ctx);
@@ -415,6 +435,20 @@ void sd_fbank_default_params(sd_fbank_params* p) {
     p->top_db = 80.f;
     p->amin = 1e-10f;
     p->mean_norm = 1;
+    p->mel_kind = 0;
+    p->log_kind = 0;
+}
+
+void sd_fbank_kaldi_params(sd_fbank_params* p, int snip_edges) {
+    if (!p) return;
+    sd_fbank_default_params(p);
+    sd_stft_kaldi_params(&p->stft, snip_edges);
+    p->f_min = 20.f;           /* kaldi::MelBanksOptions low_freq */
+    p->f_max = 0.f;            /* high_freq 0 = Nyquist */
+    p->amin = 1.1920929e-07f;  /* std::numeric_limits<float>::epsilon(), the floor before the log */
+    p->mean_norm = 0;
+    p->mel_kind = 1;
+    p->log_kind = 1;
 }
 
 int sd_fbank_dev(sd_ctx* ctx, const float* d_wav, int B, int L, const float* d_wav_lens, const sd_fbank_params* p,
@@ -432,7 +466,7 @@ int sd_fbank(sd_ctx* ctx, const float* wav, int B, int L, const float* wav_lens,
     cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, wav && out && p && wav_lens, "sd_fbank: null pointer");
     SD_REQUIRE(ctx, B > 0 && L > 0, "sd_fbank: B and L must be positive");
-    const int64_t T = sd_stft_num_frames(L, p->stft.hop);
+    const int64_t T = sd_stft_num_frames_mode(L, p->stft.n_fft, p->stft.hop, p->stft.frame_mode);
     const size_t in_bytes = sizeof(float) * (size_t)B * L;
     const size_t out_bytes = sizeof(float) * (size_t)B * T * p->n_mels;
     float* d_in = (float*)ctx->scratch(BUF_STFT_IN, in_bytes);
@@ -884,6 +918,12 @@ int sd_status_check(sd_ctx* ctx) {
 
 int sd_clustering(sd_ctx* ctx, const double* embeddings, int C, int S, int D, const sd_cluster_params* p,
                   const double* binarized, int F, int32_t* hard, double* soft, int soft_k_cap, int* num_clusters) {
+    return sd_clustering_ex(ctx, embeddings, C, S, D, p, binarized, F, hard, soft, nullptr, soft_k_cap, num_clusters);
+}
+
+int sd_clustering_ex(sd_ctx* ctx, const double* embeddings, int C, int S, int D, const sd_cluster_params* p,
+                     const double* binarized, int F, int32_t* hard, double* soft, double* dist, int soft_k_cap,
+                     int* num_clusters) {
     if (!ctx) return SD_ERR_INVALID;
     cudaSetDevice(ctx->device);  // the current device is per host thread: calls may come from any thread
     SD_REQUIRE(ctx, embeddings && hard && p, "sd_clustering: null pointer");
@@ -903,11 +943,15 @@ int sd_clustering(sd_ctx* ctx, const double* embeddings, int C, int S, int D, co
         if (!d_bin) return SD_ERR_NOMEM;
         SD_CUDA(ctx, cudaMemcpyAsync(d_bin, binarized, bbytes, cudaMemcpyHostToDevice, ctx->stream));
     }
-    if (soft && soft_k_cap > 0) {
-        d_soft = (double*)ctx->scratch(BUF_CL_SOFT, sizeof(double) * (size_t)R * soft_k_cap);
-        if (!d_soft) return SD_ERR_NOMEM;
+    double* d_dist = nullptr;
+    if ((soft || dist) && soft_k_cap > 0) {
+        const size_t sb = sizeof(double) * (size_t)R * soft_k_cap;
+        double* d_both = (double*)ctx->scratch(BUF_CL_SOFT, 2 * sb);
+        if (!d_both) return SD_ERR_NOMEM;
         // entries beyond the number of clusters stay NaN
-        SD_CUDA(ctx, cudaMemsetAsync(d_soft, 0xff, sizeof(double) * (size_t)R * soft_k_cap, ctx->stream));
+        SD_CUDA(ctx, cudaMemsetAsync(d_both, 0xff, 2 * sb, ctx->stream));
+        if (soft) d_soft = d_both;
+        if (dist) d_dist = d_both + (size_t)R * soft_k_cap;
     }
     // filter_embeddings (speakerDiarizer.cpp:2222-2229): the host already holds the rows
     std::vector<int> keep;
@@ -917,9 +961,12 @@ int sd_clustering(sd_ctx* ctx, const double* embeddings, int C, int S, int D, co
     int rc = reset_status(ctx);
     if (rc) return rc;
     rc = clustering_launch(ctx, d_emb, C, S, D, keep.data(), (int)keep.size(), p, d_bin, F, d_hard, d_soft, soft_k_cap,
-                           num_clusters, nullptr);
+                           num_clusters, nullptr, d_dist);
     if (rc) return rc;
     SD_CUDA(ctx, cudaMemcpyAsync(hard, d_hard, sizeof(int) * (size_t)R, cudaMemcpyDeviceToHost, ctx->stream));
+    if (d_dist)
+        SD_CUDA(ctx, cudaMemcpyAsync(dist, d_dist, sizeof(double) * (size_t)R * soft_k_cap, cudaMemcpyDeviceToHost,
+                                     ctx->stream));
     if (d_soft)
         SD_CUDA(ctx, cudaMemcpyAsync(soft, d_soft, sizeof(double) * (size_t)R * soft_k_cap, cudaMemcpyDeviceToHost,
                                      ctx->stream));

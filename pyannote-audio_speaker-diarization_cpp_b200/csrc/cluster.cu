@@ -2071,6 +2071,8 @@ struct AssignWork {
     const int* labels;   // [N]
     double* cent;        // [K][D]
     double* soft;        // optional [R][soft_k_cap]
+    double* dist;        // optional [R][soft_k_cap]: the cosine distances themselves (cpp_dist stage dump)
+    double* dist_k;      // scratch [R][K] behind `dist`
     int* hard;           // [R]
     const double* binarized;  // optional [C][F][S]
     int* status;
@@ -2090,6 +2092,7 @@ __global__ void __launch_bounds__(256) assign_dist_kernel(AssignWork w, int R, i
         d = NAN;
     }
     soft[(size_t)r * ld_soft + k] = __dsub_rn(2.0, d);
+    if (w.dist_k) w.dist_k[(size_t)r * ld_soft + k] = d;
 }
 
 // one warp per embedding row: first strict maximum over the centroids (Helper::argmax, speakerDiarizer.cpp:
@@ -2108,6 +2111,7 @@ __global__ void __launch_bounds__(256) assign_argmax_kernel(AssignWork w, int R,
         for (int k = 0; k < K; ++k) {
             const double v = soft[(size_t)r * ld_soft + k];
             if (w.soft && k < user_cap) w.soft[(size_t)r * user_cap + k] = v;
+            if (w.dist && k < user_cap) w.dist[(size_t)r * user_cap + k] = w.dist_k[(size_t)r * ld_soft + k];
             if (v > best) {
                 best = v;
                 arg = k;
@@ -2448,7 +2452,7 @@ int cluster_labels_launch(sd_ctx* ctx, const double* d_x, int N, int D, const sd
 // d_num_out != nullptr: nothing is read back, the final cluster count is copied to *d_num_out on the device.
 int clustering_launch(sd_ctx* ctx, const double* d_emb, int C, int S, int D, const int* h_keep, int n_keep,
                       const sd_cluster_params* p, const double* d_binarized, int F, int* d_hard, double* d_soft,
-                      int soft_k_cap, int* num_clusters_out, int* d_num_out) {
+                      int soft_k_cap, int* num_clusters_out, int* d_num_out, double* d_dist) {
     const int R = C * S;
     const int N = n_keep;
     const bool async = d_num_out != nullptr;
@@ -2505,6 +2509,12 @@ int clustering_launch(sd_ctx* ctx, const double* d_emb, int C, int S, int D, con
     w.labels = d_labels;
     w.cent = reinterpret_cast<double*>(base);
     w.soft = d_soft;
+    w.dist = d_dist;
+    w.dist_k = nullptr;
+    if (d_dist) {
+        w.dist_k = (double*)ctx->scratch(BUF_GENERIC_A, sizeof(double) * (size_t)R * K);
+        if (!w.dist_k) return SD_ERR_NOMEM;
+    }
     w.hard = d_hard;
     w.binarized = d_binarized;
     w.status = ctx->d_status;

@@ -51,7 +51,6 @@ __global__ void __launch_bounds__(128)
     if (i >= rows) return;
     double* o = out + i * Kc;
     for (int k = 0; k < Kc; ++k) o[k] = 0.0;
-    if (i >= crow) return;
     const double* a = act + (a0 + i) * Kc;
     int* order = order_scratch + i * Kc;
     for (int k = 0; k < Kc; ++k) {
@@ -63,6 +62,7 @@ __global__ void __launch_bounds__(128)
         }
         order[j] = k;
     }
+    if (i >= crow) return;  // sorted for every row (the reference's sorted_speakers), ones only where a count exists
     int cnt = count[c0 + i];
     if (cnt > Kc) cnt = Kc;
     for (int j = 0; j < cnt; ++j) o[order[j]] = 1.0;
@@ -108,11 +108,11 @@ struct ReconGeom {
     long rows, crow;
 };
 
-static ReconGeom recon_geometry(int C, const sd_window* chunks, int64_t n_count, const sd_window* cf) {
+// crop of to_diarization (SD:2686-2713) for activations[NF] on window `post` and count[n_count] on window `cf`
+static ReconGeom crop_geometry(int64_t NF, const sd_window& post, int64_t n_count, const sd_window* cf) {
     ReconGeom g;
-    const double target = chunks->start + chunks->duration + (double)(size_t)(C - 1) * chunks->step;
-    g.NF = closest_frame_host(chunks->start, cf->step, cf->duration, target) + 1;
-    g.post = sd_window{chunks->start, cf->step, cf->duration, chunks->num_samples};
+    g.NF = NF;
+    g.post = post;
     // extents (SD:2691-2706)
     const double a_end = (g.post.start + (0 - .5) * g.post.step + .5 * g.post.duration) + (double)g.NF * g.post.step;
     const double c_end = (cf->start + (0 - .5) * cf->step + .5 * cf->duration) + (double)n_count * cf->step;
@@ -123,6 +123,48 @@ static ReconGeom recon_geometry(int C, const sd_window* chunks, int64_t n_count,
     g.rows = g.act.r1 - g.act.r0;
     g.crow = g.cnt.r1 - g.cnt.r0;
     return g;
+}
+
+static ReconGeom recon_geometry(int C, const sd_window* chunks, int64_t n_count, const sd_window* cf) {
+    const double target = chunks->start + chunks->duration + (double)(size_t)(C - 1) * chunks->step;
+    const int64_t NF = closest_frame_host(chunks->start, cf->step, cf->duration, target) + 1;
+    return crop_geometry(NF, sd_window{chunks->start, cf->step, cf->duration, chunks->num_samples}, n_count, cf);
+}
+
+// The pieces of reconstruct on their own (stage dumps of verifyEveryStepResult.py: clustered_segmentations,
+// to_diarization_activations, cropped_activations, cropped_count, sorted_speakers).
+int clustered_scores_launch(sd_ctx* ctx, const float* d_seg, int C, int F, int K, const int* d_hard, int Kc,
+                            double* d_out) {
+    const size_t n_cs = (size_t)C * F * Kc;
+    clustered_scores_kernel<<<(unsigned)((n_cs + 255) / 256), 256, 0, ctx->stream>>>(d_seg, d_hard, C, F, K, Kc, d_out);
+    SD_LAUNCH_CHECK(ctx);
+    return SD_OK;
+}
+
+// to_diarization without its aggregate (SD:2672-2764): d_act[NF][Kc] on window `act_frames` (the post_frames of the
+// aggregate, num_samples included), count on `cf`.  crop4 = {first activation row, rows, first count row, count rows}.
+int to_diarization_launch(sd_ctx* ctx, const double* d_act, int64_t NF, int Kc, const sd_window* act_frames,
+                          const int* d_count, int64_t n_count, const sd_window* cf, double* d_out, int64_t cap_elems,
+                          int* d_order, int64_t* rows_out, sd_window* frames_out, int64_t* crop4) {
+    const ReconGeom g = crop_geometry(NF, *act_frames, n_count, cf);
+    if (rows_out) *rows_out = g.rows;
+    if (frames_out) *frames_out = sd_window{g.act.new_start, g.post.step, g.post.duration, 0};
+    const long crow = g.crow < g.rows ? g.crow : g.rows;
+    if (crop4) {
+        crop4[0] = g.act.r0;
+        crop4[1] = g.rows;
+        crop4[2] = g.cnt.r0;
+        crop4[3] = g.crow;
+    }
+    if (g.rows * Kc > cap_elems)
+        return ctx->fail(SD_ERR_CAPACITY, "sd_to_diarization: need %lld elements, have %lld", (long long)(g.rows * Kc),
+                         (long long)cap_elems);
+    if (g.rows > 0) {
+        top_count_kernel<<<(unsigned)((g.rows + 127) / 128), 128, 0, ctx->stream>>>(d_act, g.act.r0, d_count, g.cnt.r0,
+                                                                                   g.rows, crow, Kc, d_order, d_out);
+        SD_LAUNCH_CHECK(ctx);
+    }
+    return SD_OK;
 }
 
 int reconstruct_rows(int C, const sd_window* chunks, int64_t n_count, const sd_window* cf, int64_t* rows,

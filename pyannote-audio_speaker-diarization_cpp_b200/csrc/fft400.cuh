@@ -172,6 +172,55 @@ SD_HD void stft_phase1_tab(const float* sig, int fa_off, int fb_off, const float
     }
 }
 
+// ---- Kaldi-compatible per-frame conditioning (north_star bullet 1) -------------------------------------------------
+// kaldi::ProcessWindow (feature-window.cc) as restated by torchaudio.compliance.kaldi._get_window: optional DC removal
+// (subtract the mean of the frame), pre-emphasis y[n] = x[n] - c x[n-1] with y[0] = x[0] - c x[0], then the window
+// (povey).  With DC removal the two steps collapse to y[n] = (x[n] - c x[n-1]) - (1 - c) * mean for every n.
+// extra padded offset of sample o (0..399) of an even / odd frame
+SD_HD constexpr int sig_pad_even_at(int o) { return o / kHop == 0 ? 0 : o / kHop == 1 ? kPadEven : kPadEven + kPadOdd; }
+SD_HD constexpr int sig_pad_odd_at(int o) { return o / kHop == 0 ? 0 : o / kHop == 1 ? kPadOdd : kPadEven + kPadOdd; }
+
+// sum of this thread's 20 samples of frame A (x) and frame B (y); the group adds its 20 partials for the frame mean
+SD_HD float2 stft_frame_partial_sums(const float* sig, int fa_off, int fb_off, int r) {
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int n1 = 0; n1 < 20; ++n1) {
+        const int o = 20 * n1 + r;
+        sa += sig[fa_off + o + sig_pad_even(n1)];
+        sb += sig[fb_off + o + sig_pad_odd(n1)];
+    }
+    return make_float2(sa, sb);
+}
+
+// phase 1 with pre-emphasis coefficient c and the per-frame offsets dc = (1 - c) * mean (zero when DC removal is off)
+SD_HD void stft_phase1_kaldi(const float* sig, int fa_off, int fb_off, const float* wtab, const float2* twp, int g, int r,
+                             float2* xchg, float c, float2 dc) {
+    float2 v[20];
+#pragma unroll
+    for (int n1 = 0; n1 < 20; ++n1) {
+        const int o = 20 * n1 + r;
+        const float w = wtab[o];
+        const int pa = fa_off + o + sig_pad_even(n1), pb = fb_off + o + sig_pad_odd(n1);
+        // previous sample: one float to the left, except across a hop-segment boundary (r == 0 at n1 = 8, 16) and
+        // at the start of the frame, where Kaldi uses the first sample itself
+        int qa = pa - 1, qb = pb - 1;
+        if (r == 0) {
+            qa = n1 > 0 ? fa_off + (20 * n1 - 1) + sig_pad_even_at(n1 > 0 ? 20 * n1 - 1 : 0) : pa;
+            qb = n1 > 0 ? fb_off + (20 * n1 - 1) + sig_pad_odd_at(n1 > 0 ? 20 * n1 - 1 : 0) : pb;
+        }
+        const float xa = sig[pa] - c * sig[qa] - dc.x, xb = sig[pb] - c * sig[qb] - dc.y;
+        v[n1] = make_float2(xa * w, xb * w);
+    }
+    dft20(v);
+    float2* dst = xchg + g * kGroupStride + r;
+#pragma unroll
+    for (int k1 = 0; k1 < 20; ++k1) {
+        float2 y = v[dft20_slot(k1)];
+        if (k1 > 0) y = cmul(y, twp[k1 * kTwRow]);
+        dst[k1 * kXchgRow] = y;
+    }
+}
+
 // phase 2 split in two so that the exchange buffer can be reused for the spectrum: load + transform ...
 SD_HD void stft_phase2_load(const float2* xchg, int g, int r, float2 (&v)[20]) {
     const float2* src = xchg + g * kGroupStride + r * kXchgRow;

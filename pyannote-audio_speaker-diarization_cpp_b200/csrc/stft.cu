@@ -49,16 +49,30 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// Where frame t starts (sample t*hop - lead) and what lies beyond the ends of the item:
+//   lead 200, zeros      torch::stft(center=true, pad_mode="constant") -- the reference (speakerDiarizer.cpp:2008)
+//   lead 120, reflection Kaldi snip_edges=false: frame midpoints at t*hop + hop/2, the signal mirrored about its ends
+//                        (x[-1-s] / x[2L-1-s]; torchaudio.compliance.kaldi._get_strided)
+//   lead 0               Kaldi snip_edges=true: only whole frames (nothing lies outside)
+struct FrameGeom {
+    int lead;
+    int reflect;
+};
+__device__ __forceinline__ float edge_sample(const float* __restrict__ src, long s, int L, int reflect) {
+    if (reflect) s = s < 0 ? -s - 1 : (s >= L ? 2L * L - 1 - s : s);
+    return (s >= 0 && s < L) ? src[s] : 0.f;
+}
+
 // Stage the samples of an edge tile (item b, frames [t0, t0 + kTileFrames)) into the padded buffer: sample j of
-// the tile (item index t0*hop - n_fft/2 + j) goes to sig[sig_pos(j)].  Out-of-range samples are the
-// zeros of torch::stft's centre padding (pad_mode "constant").  16-byte pieces never straddle a hop boundary.
+// the tile (item index t0*hop - lead + j) goes to sig[sig_pos(j)].  Out-of-range samples are zeros or the
+// mirrored signal (FrameGeom).  16-byte pieces never straddle a hop boundary.
 template <int GROUPS>
 __device__ __forceinline__ void stage_tile(float* sig, const float* __restrict__ wav, int L, long tile,
-                                           int tiles_per_item, bool aligned16) {
+                                           int tiles_per_item, bool aligned16, FrameGeom fg) {
     using Cfg = StftCfg<GROUPS>;
     const int b = (int)(tile / tiles_per_item);
     const int ti = (int)(tile - (long)b * tiles_per_item);
-    const long s0 = (long)ti * Cfg::kTileFrames * kHop - kNfft / 2;
+    const long s0 = (long)ti * Cfg::kTileFrames * kHop - fg.lead;
     const float* src = wav + (size_t)b * L;
     if (aligned16) {
         for (int c = threadIdx.x; c < Cfg::kSigFloats / 4; c += Cfg::kThreads) {
@@ -69,10 +83,10 @@ __device__ __forceinline__ void stage_tile(float* sig, const float* __restrict__
                 cp_async16(dst, src + s);
             else {
                 float4 v;
-                v.x = (s >= 0 && s < L) ? src[s] : 0.f;
-                v.y = (s + 1 >= 0 && s + 1 < L) ? src[s + 1] : 0.f;
-                v.z = (s + 2 >= 0 && s + 2 < L) ? src[s + 2] : 0.f;
-                v.w = (s + 3 >= 0 && s + 3 < L) ? src[s + 3] : 0.f;
+                v.x = edge_sample(src, s, L, fg.reflect);
+                v.y = edge_sample(src, s + 1, L, fg.reflect);
+                v.z = edge_sample(src, s + 2, L, fg.reflect);
+                v.w = edge_sample(src, s + 3, L, fg.reflect);
                 *reinterpret_cast<float4*>(dst) = v;
             }
         }
@@ -83,7 +97,7 @@ __device__ __forceinline__ void stage_tile(float* sig, const float* __restrict__
             if (s >= 0 && s < L)
                 cp_async4(dst, src + s);
             else
-                dst[0] = 0.f;
+                dst[0] = edge_sample(src, s, L, fg.reflect);
         }
     }
 }
@@ -117,11 +131,34 @@ __device__ __forceinline__ void bulk_g2s(void* smem, const void* gmem, unsigned 
                  : "memory");
 }
 
-template <int GROUPS, int MINB>
+// Kaldi-mode arguments: pre-emphasis coefficient and whether the frame mean is removed first
+struct KaldiArgs {
+    float preemph;
+    int remove_dc;
+};
+
+// (1 - c) * mean of the two frames of pair g, for every thread of the group (block-wide: contains a barrier)
+template <int GROUPS>
+__device__ __forceinline__ float2 frame_dc_offsets(const float* sig, int g, int r, float2* part, KaldiArgs ka) {
+    if (!ka.remove_dc) return make_float2(0.f, 0.f);
+    part[threadIdx.x] = stft_frame_partial_sums(sig, sig_frame_off(2 * g), sig_frame_off(2 * g + 1), r);
+    __syncthreads();
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int k = 0; k < kRadix; ++k) {
+        const float2 q = part[g * kRadix + k];
+        sa += q.x;
+        sb += q.y;
+    }
+    const float f = (1.f - ka.preemph) / (float)kNfft;
+    return make_float2(sa * f, sb * f);
+}
+
+template <int GROUPS, int MINB, bool KALDI>
 __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     stft400_kernel(const float* __restrict__ wav, float* __restrict__ out, int L, int T, int tiles_per_item,
                    long total_tiles, const float* __restrict__ window, const float2* __restrict__ twiddle,
-                   int aligned16) {
+                   int aligned16, FrameGeom fg, KaldiArgs ka) {
     using Cfg = StftCfg<GROUPS>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xbuf = reinterpret_cast<float2*>(smem_raw);                 // phase 1 -> phase 2 transpose
@@ -130,6 +167,7 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     float* sig = wtab + kNfft;                                          // padded samples of the tile
     float2* zup = xbuf;  // upper half of the spectrum: reuses the transpose buffer once phase 2 has loaded it
     __shared__ __align__(8) uint64_t bar;
+    __shared__ float2 dc_part[KALDI ? GROUPS * kRadix : 1];
 
     const int g = threadIdx.x / kRadix;
     const int r = threadIdx.x - g * kRadix;
@@ -147,13 +185,13 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     // one per hop-sized segment (the padded layout), completing on an mbarrier.
     auto interior = [&](long tile) -> bool {
         const int ti = (int)(tile % tiles_per_item);
-        const long s0 = (long)ti * Cfg::kTileFrames * kHop - kNfft / 2;
+        const long s0 = (long)ti * Cfg::kTileFrames * kHop - fg.lead;
         return aligned16 && s0 >= 0 && s0 + Cfg::kSigFloats <= L;
     };
     auto issue_bulk = [&](long tile) {  // thread 0 only
         const int b = (int)(tile / tiles_per_item);
         const int ti = (int)(tile - (long)b * tiles_per_item);
-        const long s0 = (long)ti * Cfg::kTileFrames * kHop - kNfft / 2;
+        const long s0 = (long)ti * Cfg::kTileFrames * kHop - fg.lead;
         const float* src = wav + (size_t)b * L + s0;
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // earlier generic reads of sig vs async writes
         mbar_expect_tx(&bar, Cfg::kSigFloats * sizeof(float));
@@ -181,12 +219,17 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     }
     for (; tile < total_tiles; tile += gridDim.x) {
         if (!fetched) {
-            stage_tile<GROUPS>(sig, wav, L, tile, tiles_per_item, aligned16 != 0);
+            stage_tile<GROUPS>(sig, wav, L, tile, tiles_per_item, aligned16 != 0, fg);
             cp_async_commit();
             cp_async_wait<0>();
             __syncthreads();
         }
-        stft_phase1_tab(sig, sig_frame_off(2 * g), sig_frame_off(2 * g + 1), wtab, twp, g, r, xbuf);
+        if (KALDI) {
+            const float2 dc = frame_dc_offsets<GROUPS>(sig, g, r, dc_part, ka);
+            stft_phase1_kaldi(sig, sig_frame_off(2 * g), sig_frame_off(2 * g + 1), wtab, twp, g, r, xbuf, ka.preemph, dc);
+        } else {
+            stft_phase1_tab(sig, sig_frame_off(2 * g), sig_frame_off(2 * g + 1), wtab, twp, g, r, xbuf);
+        }
         __syncthreads();  // the transpose is complete and sig is free: the next tile's samples may land already,
                           // under the shadow of phase 2 and the stores
         const long next = tile + gridDim.x;
@@ -243,11 +286,12 @@ __host__ __device__ __forceinline__ float float_from_order_key(int k) {
 #endif
 }
 
-template <int GROUPS, int MINB>
+template <int GROUPS, int MINB, bool KALDI>
 __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     fbank400_kernel(const float* __restrict__ wav, float* __restrict__ out, int L, int T, int tiles_per_item,
                     long total_tiles, const float* __restrict__ window, const float2* __restrict__ twiddle,
-                    int aligned16, const MelTable* __restrict__ mel, int n_mels, float amin, int* __restrict__ item_max) {
+                    int aligned16, const MelTable* __restrict__ mel, int n_mels, float amin, float log_scale,
+                    int* __restrict__ item_max, FrameGeom fg, KaldiArgs ka) {
     using Cfg = StftCfg<GROUPS>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xbuf = reinterpret_cast<float2*>(smem_raw);
@@ -258,6 +302,7 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     float* pw = reinterpret_cast<float*>(xbuf);  // power spectra [frame][201], aliases the transpose buffer
     __shared__ __align__(8) uint64_t bar;
     __shared__ MelTable smel;
+    __shared__ float2 dc_part[KALDI ? GROUPS * kRadix : 1];
 
     const int g = threadIdx.x / kRadix;
     const int r = threadIdx.x - g * kRadix;
@@ -274,13 +319,13 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
 
     auto interior = [&](long tile) -> bool {
         const int ti = (int)(tile % tiles_per_item);
-        const long s0 = (long)ti * Cfg::kTileFrames * kHop - kNfft / 2;
+        const long s0 = (long)ti * Cfg::kTileFrames * kHop - fg.lead;
         return aligned16 && s0 >= 0 && s0 + Cfg::kSigFloats <= L;
     };
     auto issue_bulk = [&](long tile) {
         const int b = (int)(tile / tiles_per_item);
         const int ti = (int)(tile - (long)b * tiles_per_item);
-        const long s0 = (long)ti * Cfg::kTileFrames * kHop - kNfft / 2;
+        const long s0 = (long)ti * Cfg::kTileFrames * kHop - fg.lead;
         const float* src = wav + (size_t)b * L + s0;
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
         mbar_expect_tx(&bar, Cfg::kSigFloats * sizeof(float));
@@ -291,24 +336,34 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
         }
     };
 
+    // One thread polls the mbarrier, the others learn about the arrival through the block barrier that the tile loop
+    // needs anyway (as in stft400_kernel: with every warp polling, a sixth of the issued instructions were
+    // try_wait / branch).
     unsigned parity = 0;
     long tile = blockIdx.x;
     bool fetched = false;
     if (tile < total_tiles && interior(tile)) {
-        if (threadIdx.x == 0) issue_bulk(tile);
+        if (threadIdx.x == 0) {
+            issue_bulk(tile);
+            mbar_wait(&bar, parity);
+        }
+        parity ^= 1;
         fetched = true;
+        __syncthreads();
     }
     for (; tile < total_tiles; tile += gridDim.x) {
-        if (fetched) {
-            mbar_wait(&bar, parity);
-            parity ^= 1;
-        } else {
-            stage_tile<GROUPS>(sig, wav, L, tile, tiles_per_item, aligned16 != 0);
+        if (!fetched) {
+            stage_tile<GROUPS>(sig, wav, L, tile, tiles_per_item, aligned16 != 0, fg);
             cp_async_commit();
             cp_async_wait<0>();
             __syncthreads();
         }
-        stft_phase1_tab(sig, sig_frame_off(2 * g), sig_frame_off(2 * g + 1), wtab, twp, g, r, xbuf);
+        if (KALDI) {
+            const float2 dc = frame_dc_offsets<GROUPS>(sig, g, r, dc_part, ka);
+            stft_phase1_kaldi(sig, sig_frame_off(2 * g), sig_frame_off(2 * g + 1), wtab, twp, g, r, xbuf, ka.preemph, dc);
+        } else {
+            stft_phase1_tab(sig, sig_frame_off(2 * g), sig_frame_off(2 * g + 1), wtab, twp, g, r, xbuf);
+        }
         __syncthreads();
         float2 v[20];
         stft_phase2_load(xbuf, g, r, v);
@@ -365,8 +420,9 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
                 for (int j = 0; j < Cfg::kTileFrames / kFramesPerPass; ++j) {
                     const int f = slot + j * kFramesPerPass;
                     if (t0 + f < T) {
-                        // 10 log10(x) = (10 / log2(10)) log2(x); MUFU.LG2 is accurate to ~1e-6 dB here
-                        const float db = 3.01029995663981195f * __log2f(fmaxf(acc[j], amin));
+                        // 10 log10(x) = (10 / log2(10)) log2(x) (log_scale = 3.0103; ln 2 for Kaldi's natural log);
+                        // MUFU.LG2 is accurate to ~1e-6 dB here
+                        const float db = log_scale * __log2f(fmaxf(acc[j], amin));
                         out[((size_t)b * T + t0 + f) * n_mels + m] = db;
                         vmax = fmaxf(vmax, db);
                     }
@@ -376,6 +432,10 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
         if ((threadIdx.x & 31) == 0 && vmax > -INFINITY) atomicMax(item_max + b, float_order_key(vmax));
+        if (fetched) {
+            if (threadIdx.x == 0) mbar_wait(&bar, parity);  // the next tile's samples have landed
+            parity ^= 1;
+        }
         __syncthreads();  // pw consumed before the next tile's phase 1 writes xbuf
     }
 }
@@ -487,20 +547,36 @@ static int ensure_tables(sd_ctx* ctx, const sd_stft_params* p) {
     return SD_OK;
 }
 
-template <int GROUPS, int MINB>
-static int launch_cfg(sd_ctx* ctx, const float* d_wav, int B, int L, int T, float* d_out) {
+// frame geometry of a parameter set; returns the number of frames of an L-sample item
+static int frame_geometry(const sd_stft_params* p, int L, FrameGeom* fg) {
+    switch (p->frame_mode) {
+        case SD_FRAMES_KALDI_REFLECT:
+            *fg = FrameGeom{kNfft / 2 - kHop / 2, 1};
+            return (L + kHop / 2) / kHop;
+        case SD_FRAMES_KALDI_SNIP:
+            *fg = FrameGeom{0, 0};
+            return L < kNfft ? 0 : 1 + (L - kNfft) / kHop;
+        default:
+            *fg = FrameGeom{kNfft / 2, 0};
+            return 1 + L / kHop;
+    }
+}
+static bool kaldi_conditioning(const sd_stft_params* p) { return p->preemph != 0.f || p->remove_dc_offset != 0; }
+
+template <int GROUPS, int MINB, bool KALDI>
+static int launch_cfg(sd_ctx* ctx, const float* d_wav, int B, int L, int T, float* d_out, FrameGeom fg, KaldiArgs ka) {
     using Cfg = StftCfg<GROUPS>;
-    const int blocks_per_sm = kernel_setup(ctx, stft400_kernel<GROUPS, MINB>, (int)Cfg::kSmemBytesStft, Cfg::kThreads,
-                                           Cfg::kSmemBytesStft);
+    const int blocks_per_sm = kernel_setup(ctx, stft400_kernel<GROUPS, MINB, KALDI>, (int)Cfg::kSmemBytesStft,
+                                           Cfg::kThreads, Cfg::kSmemBytesStft);
     if (blocks_per_sm < 0) return SD_ERR_CUDA;
     const int tiles_per_item = (T + Cfg::kTileFrames - 1) / Cfg::kTileFrames;
     const long total = (long)B * tiles_per_item;
     long grid = (long)ctx->num_sms * blocks_per_sm;
     if (grid > total) grid = total;
     const int aligned = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_wav) & 15) == 0);
-    stft400_kernel<GROUPS, MINB><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytesStft, ctx->stream>>>(
+    stft400_kernel<GROUPS, MINB, KALDI><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytesStft, ctx->stream>>>(
         d_wav, d_out, L, T, tiles_per_item, total, ctx->d_window, reinterpret_cast<const float2*>(ctx->d_twiddle),
-        aligned);
+        aligned, fg, ka);
     SD_LAUNCH_CHECK(ctx);
     return SD_OK;
 }
@@ -509,13 +585,22 @@ int stft_launch(sd_ctx* ctx, const float* d_wav, int B, int L, const sd_stft_par
     if (p->n_fft != kNfft || p->hop != kHop)
         return ctx->fail(SD_ERR_UNSUPPORTED, "sd_stft: only n_fft=400 / hop=160 has a kernel (got %d / %d)", p->n_fft,
                          p->hop);
-    if (p->preemph != 0.f) return ctx->fail(SD_ERR_UNSUPPORTED, "sd_stft: pre-emphasis is not implemented yet");
     if (p->window_kind == SD_WINDOW_CUSTOM && !p->window)
         return ctx->fail(SD_ERR_INVALID, "sd_stft: SD_WINDOW_CUSTOM needs a window pointer");
+    if (p->frame_mode < 0 || p->frame_mode > SD_FRAMES_KALDI_SNIP)
+        return ctx->fail(SD_ERR_INVALID, "sd_stft: unknown frame_mode %d", p->frame_mode);
     int rc = ensure_tables(ctx, p);
     if (rc) return rc;
-    const int T = 1 + L / kHop;
-    rc = ctx->stft_variant == 1 ? launch_cfg<8, 3>(ctx, d_wav, B, L, T, d_out) : launch_cfg<8, 4>(ctx, d_wav, B, L, T, d_out);
+    FrameGeom fg;
+    const int T = frame_geometry(p, L, &fg);
+    if (T < 1) return ctx->fail(SD_ERR_INVALID, "sd_stft: %d samples give no frame in this frame_mode", L);
+    if (fg.reflect && L < kNfft) return ctx->fail(SD_ERR_INVALID, "sd_stft: reflection needs at least n_fft samples");
+    const KaldiArgs ka{p->preemph, p->remove_dc_offset};
+    if (kaldi_conditioning(p))
+        rc = launch_cfg<8, 3, true>(ctx, d_wav, B, L, T, d_out, fg, ka);
+    else
+        rc = ctx->stft_variant == 1 ? launch_cfg<8, 3, false>(ctx, d_wav, B, L, T, d_out, fg, ka)
+                                    : launch_cfg<8, 4, false>(ctx, d_wav, B, L, T, d_out, fg, ka);
     if (rc) return rc;
     if (p->pad_batch_to > B) {  // _infer: rows beyond the real batch are zeros (speakerDiarizer.cpp:1904)
         size_t row = (size_t)T * kBins * 2 * sizeof(float);
@@ -563,46 +648,97 @@ static int build_mel_table(const sd_fbank_params* p, MelTable& t) {
     return SD_OK;
 }
 
+// Kaldi mel banks (kaldi::MelBanks, no VTLN; torchaudio.compliance.kaldi.get_mel_banks): n_mels triangles equally
+// spaced on mel = 1127 ln(1 + f/700) between f_min and f_max (0 = Nyquist), evaluated at the centres of the n_fft/2
+// lower FFT bins (the Nyquist bin gets no weight), slopes linear in mel.
+static int build_mel_table_kaldi(const sd_fbank_params* p, MelTable& t) {
+    const int n_mels = p->n_mels, n_fft_bins = kNfft / 2;
+    if (n_mels < 1 || n_mels > 128) return SD_ERR_UNSUPPORTED;
+    auto mel = [](double f) { return 1127.0 * std::log(1.0 + f / 700.0); };
+    const double nyquist = 0.5 * p->sample_rate, bin_width = (double)p->sample_rate / kNfft;
+    const double high = p->f_max <= 0.f ? nyquist + p->f_max : (double)p->f_max;
+    const double mel_lo = mel(p->f_min), mel_hi = mel(high), delta = (mel_hi - mel_lo) / (n_mels + 1);
+    int used = 0;
+    for (int m = 0; m < n_mels; ++m) {
+        const double left = mel_lo + m * delta, center = left + delta, right = center + delta;
+        int lo = -1, hi = -1;
+        std::vector<float> wts(n_fft_bins, 0.f);
+        for (int i = 0; i < n_fft_bins; ++i) {
+            const double mf = mel(bin_width * i);
+            const double up = (mf - left) / (center - left), down = (right - mf) / (right - center);
+            const double v = std::max(0.0, std::min(up, down));
+            wts[i] = (float)v;
+            if (v > 0.0) {
+                if (lo < 0) lo = i;
+                hi = i;
+            }
+        }
+        t.lo[m] = lo < 0 ? 0 : lo;
+        t.cnt[m] = lo < 0 ? 0 : hi - lo + 1;
+        t.off[m] = used;
+        if (used + t.cnt[m] > 1024) return SD_ERR_UNSUPPORTED;
+        for (int i = 0; i < t.cnt[m]; ++i) t.w[used + i] = wts[t.lo[m] + i];
+        used += t.cnt[m];
+    }
+    return SD_OK;
+}
+
 int fbank_launch(sd_ctx* ctx, const float* d_wav, int B, int L, const float* d_lens, const sd_fbank_params* p,
                  float* d_out) {
     const sd_stft_params* sp = &p->stft;
     if (sp->n_fft != kNfft || sp->hop != kHop)
         return ctx->fail(SD_ERR_UNSUPPORTED, "sd_fbank: only n_fft=400 / hop=160 has a kernel");
-    if (sp->preemph != 0.f) return ctx->fail(SD_ERR_UNSUPPORTED, "sd_fbank: pre-emphasis is not implemented yet");
+    if (sp->frame_mode < 0 || sp->frame_mode > SD_FRAMES_KALDI_SNIP)
+        return ctx->fail(SD_ERR_INVALID, "sd_fbank: unknown frame_mode %d", sp->frame_mode);
     int rc = ensure_tables(ctx, sp);
     if (rc) return rc;
-    const int key = p->n_mels * 1000003 + (int)p->f_min * 7919 + (int)p->f_max + p->sample_rate * 31;
+    const int key = p->n_mels * 1000003 + (int)p->f_min * 7919 + (int)p->f_max + p->sample_rate * 31 + p->mel_kind * 104729;
     if (!ctx->d_mel || ctx->mel_key != key) {
         MelTable t;
         std::memset(&t, 0, sizeof(t));
-        rc = build_mel_table(p, t);
+        rc = p->mel_kind == 1 ? build_mel_table_kaldi(p, t) : build_mel_table(p, t);
         if (rc) return ctx->fail(rc, "sd_fbank: unsupported mel configuration (n_mels=%d)", p->n_mels);
         if (!ctx->d_mel) SD_CUDA(ctx, cudaMalloc(&ctx->d_mel, sizeof(MelTable)));
         SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         SD_CUDA(ctx, cudaMemcpy(ctx->d_mel, &t, sizeof(MelTable), cudaMemcpyHostToDevice));
         ctx->mel_key = key;
     }
-    const int T = 1 + L / kHop;
+    FrameGeom fg;
+    const int T = frame_geometry(sp, L, &fg);
+    if (T < 1) return ctx->fail(SD_ERR_INVALID, "sd_fbank: %d samples give no frame in this frame_mode", L);
+    if (fg.reflect && L < kNfft) return ctx->fail(SD_ERR_INVALID, "sd_fbank: reflection needs at least n_fft samples");
+    const KaldiArgs ka{sp->preemph, sp->remove_dc_offset};
+    const bool kaldi = kaldi_conditioning(sp);
+    const float log_scale = p->log_kind == 1 ? 0.69314718055994531f : 3.01029995663981195f;  // ln 2 | 10 / log2(10)
+    const float top_db = p->log_kind == 1 ? INFINITY : p->top_db;
     int* d_max = (int*)ctx->scratch(BUF_FB_TMP, sizeof(int) * (size_t)B);
     if (!d_max) return SD_ERR_NOMEM;
     fill_int_kernel2<<<(B + 255) / 256, 256, 0, ctx->stream>>>(d_max, B, (int)0x80000000);  // below every key
     SD_LAUNCH_CHECK(ctx);
     using Cfg = StftCfg<8>;
-    const int blocks_per_sm = kernel_setup(ctx, fbank400_kernel<8, 3>, (int)Cfg::kSmemBytes, Cfg::kThreads, Cfg::kSmemBytes);
+    const int blocks_per_sm =
+        kaldi ? kernel_setup(ctx, fbank400_kernel<8, 3, true>, (int)Cfg::kSmemBytes, Cfg::kThreads, Cfg::kSmemBytes)
+              : kernel_setup(ctx, fbank400_kernel<8, 3, false>, (int)Cfg::kSmemBytes, Cfg::kThreads, Cfg::kSmemBytes);
     if (blocks_per_sm < 0) return SD_ERR_CUDA;
     const int tiles_per_item = (T + Cfg::kTileFrames - 1) / Cfg::kTileFrames;
     const long total = (long)B * tiles_per_item;
     long grid = (long)ctx->num_sms * blocks_per_sm;
     if (grid > total) grid = total;
     const int aligned = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_wav) & 15) == 0);
-    fbank400_kernel<8, 3><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream>>>(
-        d_wav, d_out, L, T, tiles_per_item, total, ctx->d_window, reinterpret_cast<const float2*>(ctx->d_twiddle),
-        aligned, reinterpret_cast<const MelTable*>(ctx->d_mel), p->n_mels, p->amin, d_max);
+    if (kaldi)
+        fbank400_kernel<8, 3, true><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream>>>(
+            d_wav, d_out, L, T, tiles_per_item, total, ctx->d_window, reinterpret_cast<const float2*>(ctx->d_twiddle),
+            aligned, reinterpret_cast<const MelTable*>(ctx->d_mel), p->n_mels, p->amin, log_scale, d_max, fg, ka);
+    else
+        fbank400_kernel<8, 3, false><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream>>>(
+            d_wav, d_out, L, T, tiles_per_item, total, ctx->d_window, reinterpret_cast<const float2*>(ctx->d_twiddle),
+            aligned, reinterpret_cast<const MelTable*>(ctx->d_mel), p->n_mels, p->amin, log_scale, d_max, fg, ka);
     SD_LAUNCH_CHECK(ctx);
     const int total_e = T * p->n_mels;
     const size_t nsm = sizeof(double) * (size_t)FN_THREADS;
     (void)total_e;
-    fbank_norm_kernel<<<B, FN_THREADS, nsm, ctx->stream>>>(d_out, T, p->n_mels, d_max, d_lens, p->top_db, p->mean_norm);
+    if (p->log_kind == 1 && !p->mean_norm) return SD_OK;  // Kaldi default: no clamp, no normalisation -> nothing to do
+    fbank_norm_kernel<<<B, FN_THREADS, nsm, ctx->stream>>>(d_out, T, p->n_mels, d_max, d_lens, top_db, p->mean_norm);
     SD_LAUNCH_CHECK(ctx);
     return SD_OK;
 }

@@ -13,8 +13,20 @@
 //
 // Errors: the reference asserts or throws std::runtime_error; the shim throws std::runtime_error carrying
 // sd_last_error().  SD_ERR_ZERO_MAGNITUDE maps to the reference's message "Vectors have zero magnitude.".
+//
+// Stage dumps.  Built with WRITE_DATA, the reference writes /tmp/cpp_<stage>.txt files from INSIDE several of the
+// bodies replaced here (SD:1271-1275, 1627-1636, 1696-1723, 2074, 2186, 2206, 2330-2331, 2453-2454, 2491, 2654,
+// 2716-2717, 2732, 2841; consumer pipeline/script/verifyEveryStepResult.py).  To keep them, include this header
+// AFTER the reference's debugWrite* templates (SD:87-245) with
+//     #define SDB200_DUMP1(data, ...) debugWrite(data, __VA_ARGS__)
+//     #define SDB200_DUMP2(data, ...) debugWrite2d(data, __VA_ARGS__)
+//     #define SDB200_DUMP3(data, ...) debugWrite3d(data, __VA_ARGS__)
+// (tests/dropin/patch_reference.py does exactly that).  The shim then takes the decomposed route -- the same call
+// structure as the reference body, every piece computed by a libsdb200 call -- and hands each intermediate to the
+// reference's own writer, so the files are byte-identical.  Without the macros the fused calls are used.
 #pragma once
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
@@ -26,6 +38,12 @@
 #include <vector>
 
 #include "../../include/sdb200.h"
+
+#if defined(SDB200_DUMP1) && defined(SDB200_DUMP2) && defined(SDB200_DUMP3)
+#define SDB200_STAGE_DUMPS 1
+#else
+#define SDB200_STAGE_DUMPS 0
+#endif
 
 namespace sdb200 {
 
@@ -154,6 +172,32 @@ inline EmbeddingInput embedding_input(const vec2f& data, const vec1f& lens, int 
     return out;
 }
 
+// The rest of EmbeddingModel1::_infer (SD:1930-1975) on that input: build the two tensors, run the session, unpack
+// `rows` embeddings.  Templated on the ONNX Runtime types so that this header needs no ORT include; with it the body
+// of EmbeddingModel1::infer (SD:1977) becomes
+//     auto in = sdb200::embedding_input( data, lens, m_batchSize );
+//     return sdb200::run_embedding_model<Ort::Value, Ort::RunOptions>( *session_, memory_info_, input_node_names_,
+//                                                                      output_node_names_, in, data.size());
+// and the signature, the batch-of-32 padding and the output layout stay exactly the reference's.
+template <class Value, class RunOptions, class Session, class MemoryInfo>
+vec2f run_embedding_model(Session& session, MemoryInfo& memory_info, const std::vector<const char*>& input_names,
+                          const std::vector<const char*>& output_names, EmbeddingInput& in, size_t rows) {
+    std::vector<Value> inputs;
+    inputs.emplace_back(Value::template CreateTensor<float>(memory_info, in.audio.data(), in.audio.size(), in.dims, 4));
+    int64_t lens_dims[1] = {static_cast<int64_t>(in.wav_lens.size())};
+    inputs.emplace_back(
+        Value::template CreateTensor<float>(memory_info, in.wav_lens.data(), in.wav_lens.size(), lens_dims, 1));
+    auto outputs = session.Run(RunOptions{nullptr}, input_names.data(), inputs.data(), inputs.size(),
+                               output_names.data(), output_names.size());
+    const float* o = outputs[0].template GetTensorData<float>();
+    const auto shape = outputs[0].GetTensorTypeAndShapeInfo().GetShape();
+    const size_t dim = static_cast<size_t>(shape[2]);  // [batch][1][192]
+    vec2f res(rows, vec1f(dim));
+    for (size_t i = 0; i < rows; ++i)
+        for (size_t j = 0; j < dim; ++j) res[i][j] = o[i * dim + j];
+    return res;
+}
+
 // The 4-D vector the reference builds at SD:2018-2036 ([B][T][201][2]); kept for callers that want that shape.
 inline vec4f stft(const vec2f& data) {
     Context& c = context();
@@ -192,6 +236,23 @@ vec2d aggregate(const vec3d& scoreData, const SW& scores_frames, const SW& pre_f
     std::vector<double> flat = detail::flatten3<double, double>(scoreData), out(static_cast<size_t>(NF) * K);
     int64_t n = 0;
     sd_window post;
+#if SDB200_STAGE_DUMPS
+    {   // SD:1271-1275: masks / scores (NaN -> 0), and the sums before the division and the `missing` fill
+        vec3d masks(C, vec2d(F, vec1d(K, 1.0))), scores = scoreData;
+        for (int i = 0; i < C; ++i)
+            for (int j = 0; j < F; ++j)
+                for (int k = 0; k < K; ++k)
+                    if (std::isnan(scoreData[i][j][k])) masks[i][j][k] = scores[i][j][k] = 0.0;
+        std::vector<double> sum(out.size()), cnt(out.size()), msk(out.size());
+        c.check(sd_aggregate(c.get(), flat.data(), C, F, K, &cw, &fw, hamming ? 1 : 0, 0.0, 1, epsilon, sum.data(), NF,
+                             &n, &post, cnt.data(), msk.data()));
+        SDB200_DUMP3(masks, "cpp_masks_in_aggregate");
+        SDB200_DUMP3(scores, "cpp_scores_in_aggregate");
+        SDB200_DUMP2((detail::unflatten2<double, double>(sum, NF, K)), "cpp_aggregated_output");
+        SDB200_DUMP2((detail::unflatten2<double, double>(msk, NF, K)), "cpp_aggregated_mask");
+        SDB200_DUMP2((detail::unflatten2<double, double>(cnt, NF, K)), "cpp_overlapping_chunk_count");
+    }
+#endif
     c.check(sd_aggregate(c.get(), flat.data(), C, F, K, &cw, &fw, hamming ? 1 : 0, missing, skip_average ? 1 : 0,
                          epsilon, out.data(), NF, &n, &post, nullptr, nullptr));
     detail::from_window(post, post_frames);
@@ -203,18 +264,35 @@ vec2d aggregate(const vec3d& scoreData, const SW& scores_frames, const SW& pre_f
 // ---------------------------------------------------------------------------------------------------
 constexpr double kOnset = 0.4442333667381752;  // SegmentModel::m_diarization_segmentation_threashold, SD:1339
 
+inline std::vector<std::vector<bool>> binarize_ndarray(const vec2d& scores, double onset = 0.5,
+                                                       bool initialState = false);
+
 inline vec3d binarize_swf(const vec3f& scores, bool initial_state = false, double onset = kOnset) {  // SD:1506
     Context& c = context();
     const int C = static_cast<int>(scores.size()), F = static_cast<int>(scores[0].size()),
               K = static_cast<int>(scores[0][0].size());
+#if SDB200_STAGE_DUMPS
+    {   // the reference's route, "c f k -> (c k) f" / binarize_ndarray / back (SD:1512-1562), so that its dumps appear
+        vec2d rows(static_cast<size_t>(C) * K, vec1d(F));
+        for (int i = 0; i < C; ++i)
+            for (int j = 0; j < F; ++j)
+                for (int k = 0; k < K; ++k) rows[static_cast<size_t>(i) * K + k][j] = scores[i][j][k];
+        const auto b = binarize_ndarray(rows, onset, initial_state);
+        vec3d r(C, vec2d(F, vec1d(K)));
+        for (int i = 0; i < C; ++i)
+            for (int j = 0; j < F; ++j)
+                for (int k = 0; k < K; ++k) r[i][j][k] = b[static_cast<size_t>(i) * K + k][j];
+        return r;
+    }
+#endif
     std::vector<float> flat = detail::flatten3<float, float>(scores);
     std::vector<double> out(flat.size());
     c.check(sd_binarize(c.get(), flat.data(), C, F, K, onset, initial_state ? 1 : 0, out.data()));
     return detail::unflatten3<double, double>(out, C, F, K);
 }
 
-inline std::vector<std::vector<bool>> binarize_ndarray(const vec2d& scores, double onset = 0.5,
-                                                       bool initialState = false) {  // SD:1565
+// SD:1565
+inline std::vector<std::vector<bool>> binarize_ndarray(const vec2d& scores, double onset, bool initialState) {
     Context& c = context();
     const int R = static_cast<int>(scores.size()), F = static_cast<int>(scores[0].size());
     std::vector<double> flat = detail::flatten2<double, double>(scores);
@@ -223,6 +301,32 @@ inline std::vector<std::vector<bool>> binarize_ndarray(const vec2d& scores, doub
     std::vector<std::vector<bool>> r(R, std::vector<bool>(F));
     for (int i = 0; i < R; ++i)
         for (int j = 0; j < F; ++j) r[i][j] = out[static_cast<size_t>(i) * F + j] != 0;
+#if SDB200_STAGE_DUMPS
+    {   // SD:1626-1636
+        std::vector<uint8_t> on(flat.size());
+        std::vector<int32_t> same(flat.size()), wdi(flat.size());
+        int cols = 0;
+        c.check(sd_binarize_rows_stages(c.get(), flat.data(), R, F, onset, on.data(), same.data(), wdi.data(), &cols));
+        std::vector<std::vector<bool>> on2(R, std::vector<bool>(F)), init(R, std::vector<bool>(F, initialState));
+        std::vector<std::vector<int>> same2(R, std::vector<int>(F)), wdi2(R, std::vector<int>(cols)),
+            samples(R, std::vector<int>(F));
+        for (int i = 0; i < R; ++i) {
+            for (int j = 0; j < F; ++j) {
+                on2[i][j] = on[static_cast<size_t>(i) * F + j] != 0;
+                same2[i][j] = same[static_cast<size_t>(i) * F + j];
+                samples[i][j] = i;
+            }
+            for (int j = 0; j < cols; ++j) wdi2[i][j] = wdi[static_cast<size_t>(i) * F + j];
+        }
+        SDB200_DUMP2(scores, "cpp_binarize_score");
+        SDB200_DUMP2(same2, "cpp_same_as");
+        SDB200_DUMP2(on2, "cpp_on");
+        SDB200_DUMP2(wdi2, "cpp_well_defined_idx");
+        SDB200_DUMP2(init, "cpp_initial_state");
+        SDB200_DUMP2(samples, "cpp_samples");
+        SDB200_DUMP2(r, "cpp_binary_ndarray");
+    }
+#endif
     return r;
 }
 
@@ -249,6 +353,26 @@ std::vector<int> speaker_count(const vec3f& /*segmentations*/, const vec3d& bina
     Context& c = context();
     const int C = static_cast<int>(binarized.size()), F = static_cast<int>(binarized[0].size()),
               K = static_cast<int>(binarized[0][0].size());
+#if SDB200_STAGE_DUMPS
+    {   // the reference's route trim -> sum over classes -> aggregate -> np.rint with its dumps (SD:1688-1737)
+        SW trimmed_frames = pre_frame, chunk_frames = pre_frame;
+        chunk_frames.start = 0.0;
+        chunk_frames.step = chunk_step;
+        chunk_frames.duration = chunk_duration;
+        const vec3d trimmed = trim(binarized, 0.1, 0.1, chunk_frames, trimmed_frames);
+        SDB200_DUMP3(trimmed, "cpp_trimmed");
+        const size_t Ft = trimmed[0].size();
+        std::vector<double> flat = detail::flatten3<double, double>(binarized), sum(static_cast<size_t>(C) * Ft);
+        c.check(sd_trim_sum(c.get(), flat.data(), C, F, K, 0.1, 0.1, sum.data()));
+        const vec3d sum_trimmed = detail::unflatten3<double, double>(sum, C, Ft, 1);
+        SDB200_DUMP3(sum_trimmed, "cpp_sum_trimmed");
+        const vec2d count_data = aggregate(sum_trimmed, trimmed_frames, pre_frame, count_frames, false, 0.0, false);
+        SDB200_DUMP2(count_data, "cpp_count_data");
+        std::vector<int> res(count_data.size());
+        for (size_t i = 0; i < res.size(); ++i) res[i] = sd_np_rint(count_data[i][0]);
+        return res;
+    }
+#endif
     sd_window cw;
     cw.start = 0.0;
     cw.step = chunk_step;
@@ -348,8 +472,37 @@ public:
         }
         std::vector<int32_t> hard(static_cast<size_t>(C) * S);
         int k = 0;
+#if SDB200_STAGE_DUMPS
+        bool assigned = true;
+        {   // SD:2073-2075, and the dumps of cluster() (SD:2329-2332) which the reference reaches from here
+            vec2d filtered;
+            for (const auto& chunk : embeddings)
+                for (const auto& e : chunk)
+                    if (!std::isnan(e[0])) filtered.push_back(e);
+            SDB200_DUMP2(filtered, "cpp_filtered_embeddings");
+            const int n = static_cast<int>(filtered.size());
+            int nc = num_clusters, lo = min_clusters, hi = max_clusters;  // set_num_clusters, SD:2261-2296
+            if (nc != -1) lo = nc; else if (lo == -1) lo = 1;
+            lo = std::max(1, std::min(n, lo));
+            if (nc == -1 && hi == -1) hi = n;  // (`max_clusters == num_clusters;` at SD:2278 is a no-op comparison)
+            hi = std::max(1, std::min(n, hi));
+            if (lo > hi) lo = hi;
+            if (lo == hi) nc = lo;
+            assigned = hi >= 2;  // SD:2081-2088: otherwise everything is cluster 0 and assign_embeddings is skipped
+            if (assigned) cluster(filtered, lo, hi, nc);
+        }
+#endif
         c.check(sd_clustering(c.get(), flat.data(), C, S, D, &p, binarized ? bin.data() : nullptr, F, hard.data(),
                               nullptr, 0, &k));
+#if SDB200_STAGE_DUMPS
+        if (assigned && k > 0) {  // SD:2185-2207 (assign_embeddings): distances to the k centroids, soft = 2 - dist
+            std::vector<double> soft(static_cast<size_t>(C) * S * k), dist(soft.size());
+            c.check(sd_clustering_ex(c.get(), flat.data(), C, S, D, &p, binarized ? bin.data() : nullptr, F, hard.data(),
+                                     soft.data(), dist.data(), k, &k));
+            SDB200_DUMP2((detail::unflatten2<double, double>(dist, static_cast<size_t>(C) * S, k)), "cpp_dist", true);
+            SDB200_DUMP3((detail::unflatten3<double, double>(soft, C, S, k)), "cpp_soft_clusters", true);
+        }
+#endif
         hard_clusters = detail::unflatten2<int32_t, int>(hard, C, S);
     }
 
@@ -364,6 +517,16 @@ public:
         p.max_clusters = max_clusters;
         std::vector<double> flat = detail::flatten2<double, double>(embeddings);
         std::vector<int32_t> lab(static_cast<size_t>(N));
+#if SDB200_STAGE_DUMPS
+        {   // SD:2319-2332: normalised copy and the raw fcluster labels - 1
+            vec2d normalized = embeddings;
+            normalizeEmbeddings(normalized);
+            std::vector<int> clusters = Clustering::cluster(normalized, static_cast<double>(p.threshold));
+            for (auto& v : clusters) v -= 1;
+            SDB200_DUMP2(normalized, "cpp_norm_embeddings");
+            SDB200_DUMP1(clusters, "cpp_clusters");
+        }
+#endif
         c.check(sd_cluster_labels(c.get(), flat.data(), N, D, &p, lab.data()));
         return std::vector<int>(lab.begin(), lab.end());
     }
@@ -378,8 +541,9 @@ public:
 // Returns false when even the longest item is shorter than min_num_samples -- the reference then fills the
 // embeddings with NaN and skips the model (SD:2479-2486).  `too_short[i]` marks items whose embedding the
 // reference overwrites with NaN after inference (SD:2545-2556).
+// `dump_number`: the running batch number getEmbedding appends to its dump names (SD:2442-2454, 2489-2491).
 inline bool masked_signals(const vec2f& waveforms, const vec2f& masks, int min_num_samples, vec2f& signals,
-                           vec1f& wav_lens, std::vector<bool>& too_short) {
+                           vec1f& wav_lens, std::vector<bool>& too_short, int dump_number = 0) {
     Context& c = context();
     const int B = static_cast<int>(waveforms.size()), L = static_cast<int>(waveforms[0].size()),
               F = static_cast<int>(masks[0].size());
@@ -390,6 +554,24 @@ inline bool masked_signals(const vec2f& waveforms, const vec2f& masks, int min_n
     int all_short = 0;
     c.check(sd_mask_compact(c.get(), w.data(), m.data(), B, L, F, min_num_samples, sig.data(), wav_lens.data(), ts.data(),
                             &all_short));
+#if SDB200_STAGE_DUMPS
+    {   // SD:2452-2455 (masks, imasks) and, unless the whole batch is too short, SD:2488-2492 (raw wav_lens)
+        std::vector<uint8_t> im(w.size());
+        std::vector<int32_t> counts(static_cast<size_t>(B));
+        c.check(sd_mask_interpolate(c.get(), m.data(), B, F, L, 0.5f, im.data(), counts.data()));
+        std::vector<std::vector<bool>> imasks(B, std::vector<bool>(L));
+        for (int i = 0; i < B; ++i)
+            for (int j = 0; j < L; ++j) imasks[i][j] = im[static_cast<size_t>(i) * L + j] != 0;
+        SDB200_DUMP2(masks, std::string("cpp_masks") + std::to_string(dump_number), true);
+        SDB200_DUMP2(imasks, std::string("cpp_imasks") + std::to_string(dump_number));
+        if (!all_short) {
+            vec1f raw(counts.begin(), counts.end());
+            SDB200_DUMP1(raw, std::string("cpp_wav_lens") + std::to_string(dump_number));
+        }
+    }
+#else
+    (void)dump_number;
+#endif
     signals = detail::unflatten2<float, float>(sig, static_cast<size_t>(B), static_cast<size_t>(L));
     too_short.assign(ts.begin(), ts.end());
     return all_short == 0;
@@ -411,6 +593,38 @@ vec2d reconstruct(const vec3f& segmentations, const SW& segmentations_frames,
     for (int32_t h : hard) kc = h > kc ? h : kc;
     kc += 1;
     int64_t rows = 0;
+#if SDB200_STAGE_DUMPS
+    {   // the reference's route with its dumps: clusteredSegmentations (SD:2840-2842) -> to_diarization: aggregate
+        // (whose own dumps appear too), crop_segment, sorted_speakers (SD:2653-2654, 2715-2718, 2731-2733)
+        std::vector<double> cs(static_cast<size_t>(C) * F * kc);
+        c.check(sd_clustered_segmentations(c.get(), seg.data(), C, F, K, hard.data(), kc, cs.data()));
+        const vec3d clustered = detail::unflatten3<double, double>(cs, C, F, kc);
+        SDB200_DUMP3(clustered, "cpp_clustered_segmentations");
+        SW act_frames = count_frames;
+        const vec2d activations = aggregate(clustered, segmentations_frames, count_frames, act_frames, false, 0.0, true);
+        SDB200_DUMP2(activations, "cpp_to_diarization_activations");
+        const sd_window aw = detail::to_window(act_frames);
+        std::vector<double> act = detail::flatten2<double, double>(activations), bin(act.size() + 1);
+        std::vector<int32_t> order(act.size() + 1);
+        int64_t crop[4] = {0, 0, 0, 0};
+        sd_window fr;
+        c.check(sd_to_diarization(c.get(), act.data(), static_cast<int64_t>(activations.size()), kc, &aw, count.data(),
+                                  static_cast<int64_t>(count.size()), &cf, bin.data(), static_cast<int64_t>(bin.size()),
+                                  &rows, &fr, order.data(), crop));
+        const vec2d cropped_activations(activations.begin() + crop[0], activations.begin() + crop[0] + crop[1]);
+        std::vector<std::vector<int>> cropped_count(static_cast<size_t>(crop[3]), std::vector<int>(1)),
+            sorted_speakers = detail::unflatten2<int32_t, int>(order, static_cast<size_t>(rows), kc);
+        for (int64_t i = 0; i < crop[3]; ++i) cropped_count[i][0] = std::min<int>(count[crop[2] + i], kc);  // SD:2672-2678
+        SDB200_DUMP2(cropped_activations, "cpp_cropped_activations");
+        SDB200_DUMP2(cropped_count, "cpp_cropped_count");
+        SDB200_DUMP2(sorted_speakers, "cpp_sorted_speakers");
+        activations_frames.start = fr.start;
+        activations_frames.step = fr.step;
+        activations_frames.duration = fr.duration;
+        bin.resize(static_cast<size_t>(rows) * kc);
+        return detail::unflatten2<double, double>(bin, static_cast<size_t>(rows), static_cast<size_t>(kc));
+    }
+#endif
     c.check(sd_reconstruct_rows(C, &cw, static_cast<int64_t>(count.size()), &cf, &rows, nullptr));
     std::vector<double> out(static_cast<size_t>(rows > 0 ? rows : 0) * kc + 1);
     int cols = 0;

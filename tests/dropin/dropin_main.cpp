@@ -1,6 +1,9 @@
-// TEST INFRASTRUCTURE.  Runs the reference program -- its own main(), speakerDiarization() (SD:2937-3234) and the
-// final segment printout (SD:3437-3440) -- on a wav file, with the two ONNX forward passes answered by the
-// deterministic stand-ins of oracle/ref_harness/ort_stub/model_standins.h.
+// TEST INFRASTRUCTURE.  Runs the reference pipeline -- speakerDiarization() (SD:2937-3234), the function the
+// reference's main() calls -- on a wav file and prints the speaker segments the way that main() does (SD:3434-3441),
+// with the two ONNX forward passes answered by the deterministic stand-ins of
+// oracle/ref_harness/ort_stub/model_standins.h.  (The reference's main() itself cannot be called under another name:
+// it has no return statement, SD:3418-3442, which is only legal for the real main; renamed, gcc -O2 lets it run off
+// its end into whatever function follows.)
 //
 // Two binaries are built from this file (tests/dropin/Makefile):
 //   dropin_reference  DROPIN_TU = the reference translation unit as it lies in /root/reference, unmodified
@@ -39,7 +42,10 @@ int main(int argc, char** argv) {
     cfg.seg_rows.push_back(1);
     if (argc > 2) cfg.capture_dir = argv[2];
 
-    char a1[] = "segment2.onnx", a2[] = "emd4.onnx";
-    char* args[4] = {argv[0], a1, a2, argv[1]};
-    return reference_main(4, args);
+    auto res = speakerDiarization(argv[1], "segment2.onnx", "emd4.onnx");
+    std::cout << "----------------------------------------------------" << std::endl;
+    for (const auto& dr : res.finalResult())  // SD:3437-3440
+        std::cout << "[" << dr.start << " -- " << dr.end << "]" << " --> Speaker_" << dr.label << std::endl;
+    std::cout << "----------------------------------------------------" << std::endl;
+    return 0;
 }

@@ -1,0 +1,86 @@
+"""GPU: Kaldi-compatible mode of the front-end kernels (BASELINE north_star bullet 1: povey window, per-frame
+pre-emphasis; plus Kaldi's DC removal and its two framings) through the C-ABI.
+
+  * sd_stft with sd_stft_kaldi_params   vs the fp64 numpy restatement oracle.kaldi_stft (<= 1e-4 abs)
+  * sd_fbank with sd_fbank_kaldi_params vs torchaudio.compliance.kaldi.fbank itself, frozen in
+    tests/golden/kaldi_fbank.npz (oracle/make_golden_kaldi.py): <= 1e-4 in the log domain on mel energies above 3e-4,
+    <= 2e-3 on near-silent bins (both sides are fp32 there; the fp64 restatement shows the same spread against
+    torchaudio, tests/test_kaldi_oracle.py)
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kaldi_fbank.npz")
+
+
+@pytest.fixture(scope="module")
+def ctx(pkg):
+    c = pkg.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("snip", [False, True])
+@pytest.mark.parametrize("dc", [False, True])
+@pytest.mark.parametrize("pre", [0.97, 0.0])
+def test_kaldi_stft_vs_restatement(ctx, synth, snip, dc, pre):
+    if pre == 0.0 and not dc:
+        pytest.skip("plain framing is the non-Kaldi kernel (covered with the reference's window elsewhere)")
+    wav = synth.fbank_items(91, 5, 24000)
+    wav[1] += 0.1  # DC offset
+    wav[4] = synth.waveform(92, 1.5)[:24000]
+    got = ctx.stft(wav, params=ctx.stft_kaldi_params(snip_edges=snip, preemph=pre, remove_dc_offset=dc))
+    T = 1 + (24000 - 400) // 160 if snip else (24000 + 80) // 160
+    assert got.shape == (5, T, 201, 2)
+    for b in range(5):
+        want = O.kaldi_stft(wav[b], snip_edges=snip, preemph=pre, remove_dc_offset=dc)
+        assert np.abs(got[b] - want).max() < 1e-4
+
+
+def test_kaldi_stft_long_items_edges_and_interior(ctx, synth):
+    """L = 160 000 (cfg2 items): interior tiles come through the bulk-copy path, the first and last tile through the
+    mirrored edge path."""
+    wav = synth.fbank_items(93, 3, 160000)
+    wav[2, 150000:] = 0.3  # energy right at the mirrored end
+    got = ctx.stft(wav, params=ctx.stft_kaldi_params(snip_edges=False))
+    assert got.shape == (3, 1000, 201, 2)
+    want = O.kaldi_stft(wav[2], snip_edges=False)
+    assert np.abs(got[2] - want).max() < 1e-4
+    want0 = O.kaldi_stft(wav[0], snip_edges=False)
+    assert np.abs(got[0, :40] - want0[:40]).max() < 1e-4 and np.abs(got[0, -40:] - want0[-40:]).max() < 1e-4
+
+
+def test_kaldi_fbank_vs_torchaudio_golden(ctx):
+    g = np.load(GOLD)
+    wav = g["wav"]
+    n = 0
+    for k in g.files:
+        if not k.startswith("fbank_"):
+            continue
+        snip, dc, pre = bool(int(k[10])), bool(int(k[14])), int(k.split("pre")[1]) / 100.0
+        got = ctx.fbank(wav, params=ctx.fbank_kaldi_params(snip_edges=snip, preemph=pre, remove_dc_offset=dc))
+        want = g[k]
+        assert got.shape == want.shape
+        err = np.abs(got - want)
+        loud = want > -8.0
+        assert err[loud].max() < 1e-4, (k, float(err[loud].max()))
+        assert err.max() < 2e-3, (k, float(err.max()))
+        n += 1
+    assert n == 8
+
+
+def test_kaldi_fbank_mean_normalisation(ctx):
+    """CMN on top of the Kaldi features (subtract_mean=True in torchaudio): column means removed."""
+    g = np.load(GOLD)
+    p = ctx.fbank_kaldi_params(snip_edges=False)
+    p.mean_norm = 1
+    got = ctx.fbank(g["wav"], params=p)
+    want = g["fbank_snip0_dc1_pre97"]
+    want = want - want.mean(axis=1, keepdims=True)
+    assert np.abs(got - want).max() < 2e-3
+    assert np.abs(got.mean(axis=1)).max() < 1e-4
