@@ -50,3 +50,59 @@ def test_clustering_from_many_contexts(pkg, synth, oracle, use_async):
             j["ctx"].free(j[q])
         j["ctx"].close()
     assert all(ok), ok
+
+
+def test_contexts_created_and_destroyed_while_others_work(pkg, synth, oracle):
+    """The pinned upload ring and copy streams live inside each sd_ctx (round 1 kept them in a process-wide vector
+    that sd_ctx_create / sd_ctx_destroy reallocated under the other threads' iterators): threads that keep creating
+    and destroying contexts must not disturb a thread that is clustering."""
+    emb, _ = synth.embeddings(321, 150, 3, 192, n_speakers=4)
+    want = oracle.clustering_stage(emb)[1]
+    stop = []
+
+    def churn():
+        n = 0
+        while not stop:
+            c = pkg.Context(0)
+            c.normalize_embeddings(np.ones((4, 8)))
+            c.close()
+            n += 1
+        return n
+
+    def work():
+        c = pkg.Context(0)
+        ok = all(np.array_equal(c.clustering(emb)[0], want) for _ in range(25))
+        c.close()
+        return ok
+
+    with ThreadPoolExecutor(max_workers=5) as pool:
+        churners = [pool.submit(churn) for _ in range(3)]
+        workers = [pool.submit(work) for _ in range(2)]
+        ok = [w.result() for w in workers]
+        stop.append(1)
+        assert all(c.result() > 0 for c in churners)
+    assert all(ok)
+
+
+def test_two_gpus_in_one_process(pkg, synth, oracle):
+    """A context on a second GPU of the same process: the >48 KB dynamic shared memory opt-in and the occupancy of
+    every kernel are kept per (device, kernel) (round 1 used process-wide static flags, so device 1 never got the
+    attribute and its STFT / linkage / fcluster launches failed).  Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process (run under `gpurun --gpus 2`)")
+    wav = synth.fbank_items(5, 6, 80000)
+    emb, _ = synth.embeddings(77, 500, 3, 192, n_speakers=5)  # N ~ 1 425: linkage state beyond 48 KB of shared memory
+    want_stft = oracle.stft(wav)
+    want_hard = oracle.clustering_stage(emb)[1]
+
+    def on(device):
+        c = pkg.Context(device)
+        ok = np.abs(c.stft(wav) - want_stft).max() < 1e-4 and np.array_equal(c.clustering(emb)[0], want_hard)
+        ok = ok and np.isfinite(c.fbank(wav, np.ones(6, np.float32))).all()
+        c.close()
+        return ok
+
+    assert on(0) and on(1)          # one after the other: device 0 configures first, device 1 must still work
+    with ThreadPoolExecutor(max_workers=2) as pool:  # and concurrently from two host threads
+        assert all(pool.map(on, [1, 0]))

@@ -110,3 +110,35 @@ def test_embedding_model_inputs_within_1e4(dropin_run):
     print("max |STFT(sdb200) - STFT(reference, libtorch fp64)| = %.3g (%s)" %
           (worst, "all elements" if full is not None else "sampled frames"))
     assert worst < 1e-4
+
+
+def _read_dump(name):
+    rows = []
+    with open("/tmp/" + name) as f:
+        for line in f:
+            line = line.strip().rstrip(",")
+            if line:
+                rows.append([float(v) for v in line.split(",")])
+    return np.array(rows)
+
+
+def test_select_masks_against_the_pipeline_own_choice(dropin_run, pkg):
+    """sd_select_masks_dev (the clean-vs-raw mask choice, speakerDiarizer.cpp:3047-3082) is inline code of
+    speakerDiarization() in the reference, so it can only be observed through the pipeline: the masks handed to
+    getEmbedding are dumped as cpp_masks<n> (SD:2453), and those dumps are byte-identical to the unmodified
+    reference's (test above).  Feed the dumped binarized segmentations to the kernel and compare."""
+    gold, rec, _, _ = dropin_run
+    assert all(rec["dumps"][n] == gold["dumps"][n] for n in rec["dumps"] if n.startswith("cpp_masks"))
+    b = _read_dump("cpp_binarized_segmentations.txt").reshape(-1, 293, 3)
+    n_items = b.shape[0] * 3
+    masks = np.concatenate([_read_dump("cpp_masks%d.txt" % n) for n in range((n_items + 31) // 32)])
+    assert masks.shape == (n_items, 293)
+    min_num_frames = float(np.ceil(293 * 640 / (5.0 * 16000)))  # SD:3013
+    ctx = pkg.Context(0)
+    try:
+        got = ctx.select_masks(b, min_num_frames)
+    finally:
+        ctx.close()
+    assert np.array_equal(got, masks.astype(np.float32))
+    clean = b * (b.sum(2, keepdims=True) < 2)
+    assert (clean != b).any(), "the scenario has no overlapped speech: the choice would be vacuous"
