@@ -66,8 +66,8 @@ for n_chunks, opt in ((110, {}), (110, {4: 0}), (110, {1: 1}), (400, {})):
 masks = (synth.segmentations(5, 8, 293, 3)[:, :, 0] > 0.5).astype(np.float32)
 w8 = synth.fbank_items(6, 8, 80000)
 rc, s_o, l_o, t_o = o.mask_compact(w8, masks)
-sig, lens, ts, inv = ctx.mask_compact(w8, masks)
-check("mask_compact", np.array_equal(sig, s_o))
+rc_g, sig, lens, ts = ctx.mask_compact(w8, masks)
+check("mask_compact", rc_g == rc and np.array_equal(sig, s_o) and np.array_equal(lens, l_o))
 count, cf = o.speaker_count(b)
 hard24 = (np.arange(24 * 3).reshape(24, 3) % 3).astype(np.int32)
 sf = (0.0, 0.5, 5.0, 16000 * 17)

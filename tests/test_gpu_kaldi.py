@@ -4,8 +4,8 @@ pre-emphasis; plus Kaldi's DC removal and its two framings) through the C-ABI.
   * sd_stft with sd_stft_kaldi_params   vs the fp64 numpy restatement oracle.kaldi_stft (<= 1e-4 abs)
   * sd_fbank with sd_fbank_kaldi_params vs torchaudio.compliance.kaldi.fbank itself, frozen in
     tests/golden/kaldi_fbank.npz (oracle/make_golden_kaldi.py): <= 1e-4 in the log domain on mel energies above 3e-4,
-    <= 2e-3 on near-silent bins (both sides are fp32 there; the fp64 restatement shows the same spread against
-    torchaudio, tests/test_kaldi_oracle.py)
+    <= 5e-3 on near-silent bins (both sides are fp32 there: log of energies around 1e-6 amplifies the FFT's rounding
+    noise; the fp64 restatement shows the same spread against torchaudio, tests/test_kaldi_oracle.py)
 """
 import os
 
@@ -69,7 +69,7 @@ def test_kaldi_fbank_vs_torchaudio_golden(ctx):
         err = np.abs(got - want)
         loud = want > -8.0
         assert err[loud].max() < 1e-4, (k, float(err[loud].max()))
-        assert err.max() < 2e-3, (k, float(err.max()))
+        assert err.max() < 5e-3, (k, float(err.max()))
         n += 1
     assert n == 8
 
@@ -82,5 +82,5 @@ def test_kaldi_fbank_mean_normalisation(ctx):
     got = ctx.fbank(g["wav"], params=p)
     want = g["fbank_snip0_dc1_pre97"]
     want = want - want.mean(axis=1, keepdims=True)
-    assert np.abs(got - want).max() < 2e-3
+    assert np.abs(got - want).max() < 5e-3
     assert np.abs(got.mean(axis=1)).max() < 1e-4
