@@ -38,10 +38,17 @@ import __graft_entry__ as ge  # noqa: E402
 METRIC = "audio-sec/sec of fbank+aggregation+clustering path; fbank GB/s vs HBM peak"
 UNIT = "audio-s/s"
 
-WORKLOAD = dict(
-    name="configs[1]: synthetic 10-min 16 kHz mono, 10 s chunks / 1 s step, 3 local speakers",
-    audio_seconds=600.0, window_s=10.0, step_s=1.0, frames_per_chunk=589, local_speakers=3, embedding_dim=192,
-    n_fft=400, hop=160, diar_clusters=4)
+WORKLOADS = {
+    # the configuration BASELINE.json's metric is quoted on (weak scaling: `--files` such files per GPU per step)
+    "cfg2": dict(name="configs[1]: synthetic 10-min 16 kHz mono, 10 s chunks / 1 s step, 3 local speakers",
+                 audio_seconds=600.0, window_s=10.0, step_s=1.0, frames_per_chunk=589, local_speakers=3,
+                 embedding_dim=192, n_fft=400, hop=160, diar_clusters=4, total_files=None, scaling="weak"),
+    # configs[3]: a fixed batch of 64 five-minute files sharded over the GPUs (strong scaling)
+    "cfg4": dict(name="configs[3]: batch of 64 synthetic 5-min files sharded across the GPUs, 10 s chunks / 1 s step",
+                 audio_seconds=300.0, window_s=10.0, step_s=1.0, frames_per_chunk=589, local_speakers=3,
+                 embedding_dim=192, n_fft=400, hop=160, diar_clusters=4, total_files=64, scaling="strong"),
+}
+WORKLOAD = dict(WORKLOADS["cfg2"])
 
 
 def geometry():
@@ -131,14 +138,12 @@ def build_inputs(synth, geo, seed, want_wav=True):
 
 
 class FileJob:
-    """One file of the batch: its own library context on its own CUDA stream, device-resident inputs and outputs."""
+    """One file of the batch: device-resident inputs and outputs (allocated through `ctx`).  File 0 of a rank also
+    owns what the single-file pass needs (the context itself, its stream and the per-stage event timers)."""
 
-    def __init__(self, pkg, synth, geo, local, seed, base_wav, index, torch):
+    def __init__(self, pkg, synth, geo, ctx, seed, base_wav, index, torch, stft_slot=None):
         import ctypes as C
-        self.C, self.pkg, self.geo = C, pkg, geo
-        self.stream = torch.cuda.Stream()
-        self.ctx = ctx = pkg.Context(local)
-        ctx.set_stream(self.stream.cuda_stream)
+        self.C, self.pkg, self.geo, self.ctx = C, pkg, geo, ctx
         C_, F, S, items, L, T, D, Kd = (geo[k] for k in ("C", "F", "S", "items", "L", "T", "D", "Kd"))
         # distinct audio per file without regenerating 1.1 GB of noise: a circular shift of the rank's base items
         self.wav_items = base_wav if index == 0 else np.roll(base_wav, 997 * index, axis=1)
@@ -151,7 +156,9 @@ class FileJob:
         self.d_seg = ctx.to_device(self.seg)
         self.d_emb = ctx.to_device(self.emb)
         self.d_diar = ctx.to_device(self.diar)
-        self.d_stft = ctx.malloc(items * T * 201 * 2 * 4)
+        # the 2.9 GB STFT tensor of a file is consumed by the embedding network right away: files that run on the
+        # same worker (one after the other) share one output buffer
+        self.d_stft = stft_slot if stft_slot is not None else ctx.malloc(items * T * 201 * 2 * 4)
         self.d_bin = ctx.malloc(C_ * F * S * 8)
         self.d_cnt = ctx.malloc(self.cap_cnt * 4)
         self.d_agg = ctx.malloc(self.NFd * Kd * 8)
@@ -160,15 +167,19 @@ class FileJob:
         self.n_out, self.cf, self.post, self.kc = C.c_int64(), pkg.Window(), pkg.Window(), C.c_int()
         self.hard_t = torch.empty(C_ * S, dtype=torch.int32, device="cuda")  # torch-owned so NCCL can gather it
         self.d_hard = self.hard_t.data_ptr()
-        # what the synchronous clustering call reads back at its start: the rows that hold an embedding
-        self.keep = np.flatnonzero(~np.isnan(self.emb.reshape(C_ * S, D)[:, 0])).astype(np.int32)
-        self.d_kc = ctx.malloc(4)
         if index > 0:
             self.wav_items = None  # the host copy of a shifted file is not needed again
 
-    use_async = False
+    def sd_file(self):
+        """The same file as an sd_file of the batch API (device pointers)."""
+        g = self.geo
+        return self.pkg.make_file(g["C"], g["F"], g["S"], g["L"], g["D"], self.chunks, self.frames, Kd=g["Kd"],
+                                  wav_items=self.d_wav, segmentations=self.d_seg, embeddings=self.d_emb,
+                                  diar_scores=self.d_diar, stft=self.d_stft, binarized=self.d_bin, count=self.d_cnt,
+                                  count_cap=self.cap_cnt, hard=self.d_hard, diar=self.d_agg)
 
     def step(self, timed=False):
+        """One file alone through the *_dev entry points, with per-stage event timers when `timed`."""
         C, ctx, pkg = self.C, self.ctx, self.pkg
         vp = C.c_void_p
         C_, F, S, items, L, D, Kd = (self.geo[k] for k in ("C", "F", "S", "items", "L", "D", "Kd"))
@@ -184,13 +195,8 @@ class FileJob:
         if timed:
             ctx.timer_stop(2)
             ctx.timer_start(3)
-        if self.use_async:  # nothing is read back: the stream never idles between the kernels of this file
-            ctx._check(ctx.L.sd_clustering_async_dev(ctx.h, vp(self.d_emb), C_, S, D, C.byref(self.cp), pkg._ptr(self.keep),
-                                                     self.keep.size, vp(self.d_bin), F, vp(self.d_hard), None, 0,
-                                                     vp(self.d_kc)))
-        else:
-            ctx._check(ctx.L.sd_clustering_dev(ctx.h, vp(self.d_emb), C_, S, D, C.byref(self.cp), vp(self.d_bin), F,
-                                               vp(self.d_hard), None, 0, C.byref(self.kc)))
+        ctx._check(ctx.L.sd_clustering_dev(ctx.h, vp(self.d_emb), C_, S, D, C.byref(self.cp), vp(self.d_bin), F,
+                                           vp(self.d_hard), None, 0, C.byref(self.kc)))
         if timed:
             ctx.timer_stop(3)
             ctx.timer_start(4)
@@ -200,27 +206,31 @@ class FileJob:
         if timed:
             ctx.timer_stop(4)
 
-    def step_and_sync(self):
-        self.step()
-        self.ctx.sync()
+
+def load_shard():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sdb200_shard", os.path.join(ge.PKG_DIR, "shard.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
 
 
 def run_product(args, rank, world):
     import ctypes as C
-    from concurrent.futures import ThreadPoolExecutor
 
     import torch
     import torch.distributed as dist
 
     pkg = ge.load_package()
     synth = ge.load_synth()
+    shard = load_shard()
     geo = geometry()
     local = int(os.environ.get("LOCAL_RANK", rank))
-    # Host threads waiting for the GPU spin by default, which is the fastest (1 GPU: 235.7 k audio-s/s, yield
-    # 202.6 k, blocking 158.8 k) until the ranks' worker threads outnumber the host cores (8 GPUs x 8 files on 32
-    # cores: spin 1.20 M, yield 1.36 M): then they yield.  SDB_SCHED=spin|yield|blocking overrides.
+    workers = max(1, args.files)
+    # Host threads waiting for the GPU spin by default, which is the fastest until the ranks' worker threads outnumber
+    # the host cores: then they yield.  SDB_SCHED=spin|yield|blocking overrides.
     sched = os.environ.get("SDB_SCHED", "")
-    if not sched and world * max(1, args.files) > (os.cpu_count() or 1):
+    if not sched and world * workers > (os.cpu_count() or 1):
         sched = "yield"
     if sched:
         from cuda import cudart
@@ -233,17 +243,27 @@ def run_product(args, rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     C_, F, S, items, L, T, D, Kd = (geo[k] for k in ("C", "F", "S", "items", "L", "T", "D", "Kd"))
-    nfiles = max(1, args.files)
+
+    # ---- the batch and its shards: whole files go to ranks, longest-processing-time first (shard.assign_files, the
+    # sharder the gloo tests cover); weak scaling = `--files` files per GPU, strong (cfg4) = a fixed batch of 64
+    total_files = WORKLOAD["total_files"] or world * workers
+    durations = [WORKLOAD["audio_seconds"]] * total_files
+    bins = shard.assign_files(durations, world)
+    mine = bins[rank]
+    nfiles = len(mine)
+    workers = min(workers, max(nfiles, 1))
+    ctx = pkg.Context(local)
+    stream0 = torch.cuda.Stream()
+    ctx.set_stream(stream0.cuda_stream)
     base_wav = synth.fbank_items(1000 * rank + 102, items, L)
-    jobs = [FileJob(pkg, synth, geo, local, 1000 * rank + 17 * i, base_wav, i, torch) for i in range(nfiles)]
+    stft_slots = [ctx.malloc(items * T * 201 * 2 * 4) for _ in range(workers)]
+    jobs = [FileJob(pkg, synth, geo, ctx, 17 * fid, base_wav, k, torch, stft_slots[k % workers])
+            for k, fid in enumerate(mine)]
     job0 = jobs[0]
-    ctx = job0.ctx
     wav_items, seg, emb, diar = job0.wav_items, job0.seg, job0.emb, job0.diar
     chunks, frames, NFd, cap_cnt = job0.chunks, job0.frames, job0.NFd, job0.cap_cnt
     sp, cp, n_out, cf, post, kc = job0.sp, job0.cp, job0.n_out, job0.cf, job0.post, job0.kc
     d_seg, d_bin, d_hard = job0.d_seg, job0.d_bin, job0.d_hard
-    all_hard = torch.empty((max(args.steps, args.warmup), nfiles, C_ * S), dtype=torch.int32, device="cuda")
-    gathered = [torch.empty_like(all_hard) for _ in range(world)] if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -265,124 +285,131 @@ def run_product(args, rank, world):
     single_ms = ctx.timer_ms(0) / args.steps
     barrier()
 
-    # ---- pass 2 (the headline): the batch of files, one host thread + context + stream per file, each running its
-    # file `steps` times without waiting for the others (a per-step join makes every step as slow as its slowest
-    # file: 25-27 ms instead of 21 ms per 8 files), so that the latency-bound clustering of one file runs concurrently
-    # with the other files' work instead of leaving 140 SMs idle.  The labels of every (step, file) stay on the
-    # device and are gathered over the ranks with ONE NCCL all_gather at the end of the timed region -- the only
-    # collective on the path (KBs).
-    pool = ThreadPoolExecutor(max_workers=nfiles, initializer=torch.cuda.set_device, initargs=(local,))
-
-    def worker(j, idx, nsteps):
-        j.use_async = args.async_clustering
-        j.ctx._check(j.ctx.L.sd_status_reset(j.ctx.h))
-        for s_ in range(nsteps):
-            j.step()
-            with torch.cuda.stream(j.stream):
-                all_hard[s_, idx].copy_(j.hard_t, non_blocking=True)
-        j.ctx._check(j.ctx.L.sd_status_check(j.ctx.h))  # synchronises; device-side errors of all steps surface here
-        j.use_async = False
+    # ---- pass 2 (the headline): the rank's files through the native batch API (sd_batch_*): `workers` files in
+    # flight, each on its own sd_ctx + stream driven by a library-owned host thread, all steps queued at once (file i
+    # stays on worker i % workers, so consecutive steps of a file never overlap with themselves).  The latency-bound
+    # clustering of one file then runs under the bandwidth-bound STFT of the others.  The labels stay on the device
+    # and are gathered over the ranks with ONE all_gather at the end of the timed region (shard.gather_results) -- the
+    # only collective on the path (KBs).
+    batch = pkg.Batch(local, workers)
+    files = (pkg.SdFile * nfiles)(*[j.sd_file() for j in jobs])
 
     def run_batch(nsteps):
-        for f_ in [pool.submit(worker, j, i, nsteps) for i, j in enumerate(jobs)]:
-            f_.result()
+        for _ in range(nsteps):
+            batch.submit(files, pkg.SD_BATCH_DEVICE)
+        batch.wait()
+        labels = torch.stack([j.hard_t for j in jobs])
         if world > 1:
-            dist.all_gather(gathered, all_hard)
+            packed = torch.full((max(len(b_) for b_ in bins), 2 + C_ * S), -1, dtype=torch.int32, device="cuda")
+            packed[:nfiles, 0] = torch.tensor(mine, dtype=torch.int32, device="cuda")
+            packed[:nfiles, 1] = C_ * S
+            packed[:nfiles, 2:] = labels
+            outs = [torch.empty_like(packed) for _ in range(world)]
+            dist.all_gather(outs, packed)
+            return outs
+        return [labels]
 
     run_batch(args.warmup)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = sum(j.ctx.launch_count() for j in jobs)
+    launches0 = batch.launch_count()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     main_stream = torch.cuda.current_stream()
-    ev0.record(main_stream)  # the device is idle here (barrier above); every file stream starts after this point
-    run_batch(args.steps)
-    for j in jobs:
-        main_stream.wait_stream(j.stream)
+    ev0.record(main_stream)  # the device is idle here (barrier above); every worker stream starts after this point
+    gathered = run_batch(args.steps)  # returns after every worker stream was synchronised
     ev1.record(main_stream)
     torch.cuda.synchronize()
     total_ms = ev0.elapsed_time(ev1)
     barrier()
-    launches = sum(j.ctx.launch_count() for j in jobs) - launches0
+    launches = batch.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     if world > 1:
         t = torch.tensor([total_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
+        seen = sorted(int(v) for o in gathered for v in o[:, 0].tolist() if v >= 0)
+        assert seen == list(range(total_files)), "gather lost files: %s" % seen
     ms_per_step = total_ms / args.steps
-    value = world * nfiles * WORKLOAD["audio_seconds"] / (ms_per_step / 1e3)
-    pool.shutdown()
+    value = total_files * WORKLOAD["audio_seconds"] / (ms_per_step / 1e3)
 
-    # ---- e2e: host-pointer C-ABI calls, pinned buffers, H2D/D2H inside the timed region
-    h_wav = ctx.host_alloc(wav_items.shape, np.float32)
-    h_wav[...] = wav_items
-    h_stft = ctx.host_alloc((items, T, 201, 2), np.float32)
-    h_seg = ctx.host_alloc(seg.shape, np.float32)
-    h_seg[...] = seg
-    h_bin = ctx.host_alloc(seg.shape, np.float64)
-    h_cnt = ctx.host_alloc((cap_cnt,), np.int32)
-    h_emb = ctx.host_alloc(emb.shape, np.float64)
-    h_emb[...] = emb
-    h_hard = ctx.host_alloc((C_, S), np.int32)
-    h_diar = ctx.host_alloc(diar.shape, np.float64)
-    h_diar[...] = diar
-    h_agg = ctx.host_alloc((NFd, Kd), np.float64)
-    P = pkg._ptr
-
-    def step_e2e():
-        ctx._check(ctx.L.sd_stft(ctx.h, P(h_wav), items, L, C.byref(sp), P(h_stft)))
-        ctx._check(ctx.L.sd_binarize(ctx.h, P(h_seg), C_, F, S, pkg.ONSET, 0, P(h_bin)))
-        ctx._check(ctx.L.sd_speaker_count(ctx.h, P(h_bin), C_, F, S, C.byref(chunks), C.byref(frames), P(h_cnt),
-                                          cap_cnt, C.byref(n_out), C.byref(cf)))
-        ctx._check(ctx.L.sd_clustering(ctx.h, P(h_emb), C_, S, D, C.byref(cp), P(h_bin), F, P(h_hard), None, 0,
-                                       C.byref(kc)))
-        ctx._check(ctx.L.sd_aggregate(ctx.h, P(h_diar), C_, F, Kd, C.byref(chunks), C.byref(frames), 0, 0.0, 1, pkg.EPS,
-                                      P(h_agg), NFd, C.byref(n_out), C.byref(post), None, None))
-
-    h2d = wav_items.nbytes + seg.nbytes + h_bin.nbytes * 2 + emb.nbytes + diar.nbytes
-    d2h = h_stft.nbytes + h_bin.nbytes + int(n_out.value or NFd) * 4 + h_hard.nbytes + h_agg.nbytes
-    e2e_steps = max(2, min(args.steps, 5))
-    step_e2e()
+    # ---- e2e: the same batch API with HOST pointers (pinned buffers): every step copies each file's inputs to the
+    # device and brings every result back, the files in flight overlapping their copies and kernels
+    e2e_files = min(nfiles, 3)
+    hosts, keep = [], []
+    for k in range(e2e_files):
+        j = jobs[k]
+        hb = dict(wav=ctx.host_alloc((items, L), np.float32), stft=ctx.host_alloc((items, T, 201, 2), np.float32),
+                  seg=ctx.host_alloc(j.seg.shape, np.float32), bin=ctx.host_alloc(j.seg.shape, np.float64),
+                  cnt=ctx.host_alloc((cap_cnt,), np.int32), emb=ctx.host_alloc(j.emb.shape, np.float64),
+                  hard=ctx.host_alloc((C_, S), np.int32), diar=ctx.host_alloc(j.diar.shape, np.float64),
+                  agg=ctx.host_alloc((NFd, Kd), np.float64))
+        hb["wav"][...] = wav_items if k == 0 else np.roll(wav_items, 997 * k, axis=1)
+        hb["seg"][...], hb["emb"][...], hb["diar"][...] = j.seg, j.emb, j.diar
+        keep.append(hb)
+        hosts.append(pkg.make_file(C_, F, S, L, D, chunks, frames, Kd=Kd, wav_items=hb["wav"], segmentations=hb["seg"],
+                                   embeddings=hb["emb"], diar_scores=hb["diar"], stft=hb["stft"], binarized=hb["bin"],
+                                   count=hb["cnt"], count_cap=cap_cnt, hard=hb["hard"], diar=hb["agg"]))
+    hfiles = (pkg.SdFile * e2e_files)(*hosts)
+    hb = keep[0]
+    # sd_clustering re-uploads the binarized scores, sd_speaker_count uploads them too (host-pointer calls are
+    # self-contained): counted
+    h2d = hb["wav"].nbytes + hb["seg"].nbytes + hb["bin"].nbytes * 2 + hb["emb"].nbytes + hb["diar"].nbytes
+    d2h = hb["stft"].nbytes + hb["bin"].nbytes + NFd * 4 + hb["hard"].nbytes + hb["agg"].nbytes
+    e2e_steps = max(2, min(args.steps, 4))
+    batch.run(hfiles, pkg.SD_BATCH_HOST)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        step_e2e()
+        batch.submit(hfiles, pkg.SD_BATCH_HOST)
+    batch.wait()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    assert np.array_equal(keep[0]["hard"].ravel(), jobs[0].hard_t.cpu().numpy()), "host and device paths disagree"
     if world > 1:
         t = torch.tensor([e2e_s], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = world * WORKLOAD["audio_seconds"] / e2e_s
+    e2e_value = world * e2e_files * WORKLOAD["audio_seconds"] / e2e_s
+    batch.close()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     next_rows = next_rows_timing(ctx, pkg, synth, geo, d_seg, d_bin, d_hard, chunks, frames) if world == 1 else None
+    configs = other_configs_timing(ctx, pkg, synth) if world == 1 and not args.no_configs else None
     peak, peak_src = measured_peaks()
     stft_ms = stage_ms[1] / args.steps
     stft_bytes = items * (4 * L + 4 * T * 201 * 2)
     achieved = stft_bytes / (stft_ms / 1e3) / 1e9
-    n_merge = int((~np.isnan(emb[:, :, 0])).sum()) - 1
+    n_emb = int((~np.isnan(emb[:, :, 0])).sum())
+    n_merge = n_emb - 1
+    cl_ms = stage_ms[3] / args.steps
+    pcie_d2h_gbs = 55.0
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 stft / f64 aggregation+clustering",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": WORKLOAD["scaling"], "vs_baseline": None,
+        "dtype": "f32 stft / f64 aggregation+clustering",
         "data": "synthetic (seeded; stand-ins for segment2.onnx / emd4.onnx outputs, see synth.py)",
         "config": {"workload": WORKLOAD["name"], "chunks": C_, "frames_per_chunk": F, "local_speakers": S,
                    "stft_items": items, "samples_per_item": L, "embeddings": items, "embedding_dim": D,
                    "l2_policy": "inputs larger than L2 (STFT streams 3.99 GB per file)",
-                   "files_per_step_per_gpu": nfiles,
-                   "concurrency": "one host thread + sd_ctx + CUDA stream per file of the batch, free-running over "
-                                  "the steps; one all_gather of all labels at the end of the timed region",
+                   "files_per_step": total_files, "files_per_step_per_gpu": nfiles, "files_in_flight_per_gpu": workers,
+                   "concurrency": "sd_batch_* (native): one library-owned host thread + sd_ctx + CUDA stream per file "
+                                  "in flight, all steps queued at once; files assigned to ranks by shard.assign_files "
+                                  "(LPT); one all_gather of the labels at the end of the timed region",
                    "host_wait": sched or "spin (driver default)",
-                   "clustering_call": "sd_clustering_async_dev" if args.async_clustering else "sd_clustering_dev",
                    "parallelism": "file-sharded x%d" % world},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "files_per_step_per_gpu": 1},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * e2e_files,
+                "d2h_bytes_per_step": int(d2h) * e2e_files, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                "files_per_step_per_gpu": e2e_files, "ms_per_file": e2e_s * 1e3 / e2e_files,
+                "call": "sd_batch_submit(SD_BATCH_HOST) + sd_batch_wait, pinned host buffers",
+                "bound": "PCIe D2H: %.2f GB per file at ~%.0f GB/s = %.1f ms per file"
+                         % (d2h / 1e9, pcie_d2h_gbs, d2h / 1e9 / pcie_d2h_gbs * 1e3),
+                "d2h_gbs_achieved": d2h * e2e_files / e2e_s / 1e9},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "stft400_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
@@ -390,22 +417,70 @@ def run_product(args, rank, world):
                      "path_frac": nfiles * stft_bytes / (ms_per_step / 1e3) / 1e9 / peak,
                      "path_frac_note": "STFT algorithmic bytes of the batch / whole step time / peak: how close the "
                                        "whole path runs to the HBM roofline of its bandwidth-bound stage"},
+        "roofline_linkage": {"kernel": "pdist_f64_kernel + linkage_cluster_kernel (clustering stage of one file)",
+                             "bound": "hbm (nominally; the N-1 dependent merges make it latency-bound)",
+                             "algorithmic_bytes": 32 * n_emb * n_emb, "ms": cl_ms,
+                             "achieved": 32 * n_emb * n_emb / (cl_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": 32 * n_emb * n_emb / (cl_ms / 1e3) / 1e9 / peak, "merges": n_merge,
+                             "us_per_merge_upper_bound": cl_ms * 1e3 / max(n_merge, 1)},
         "single_file": {"ms_per_file": single_ms, "value": WORKLOAD["audio_seconds"] / (single_ms / 1e3),
                         "stages_ms": {"stft": stft_ms, "binarize+speaker_count": stage_ms[2] / args.steps,
-                                      "clustering": stage_ms[3] / args.steps, "aggregate_diar": stage_ms[4] / args.steps}},
+                                      "clustering": cl_ms, "aggregate_diar": stage_ms[4] / args.steps}},
         "stages_ms_per_step": {"stft": stft_ms, "binarize+speaker_count": stage_ms[2] / args.steps,
-                               "clustering": stage_ms[3] / args.steps, "aggregate_diar": stage_ms[4] / args.steps},
-        "linkage": {"merges": n_merge, "us_per_merge_upper_bound": stage_ms[3] / args.steps * 1e3 / max(n_merge, 1),
-                    "bound": "latency (N-1 dependent merges)"},
+                               "clustering": cl_ms, "aggregate_diar": stage_ms[4] / args.steps},
         "clocks": clocks,
     }
     if next_rows:
         line["next_rows_ms"] = next_rows
+    if configs:
+        line["configs_ms"] = configs
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(geo, wav_items, seg, emb, diar)
+        cb = cpu_baseline(geo, wav_items, seg, emb, diar)
+        line["cpu_baseline"] = cb
+        if cb.get("value_fft_only"):
+            line["vs_fft_only"] = {"e2e": e2e_value / cb["value_fft_only"], "value": value / cb["value_fft_only"],
+                                   "note": "against the reference with its per-element .item() copy loop and /tmp text "
+                                           "dump taken out (torch::stft alone + its own segmentation / clustering "
+                                           "code): the like-for-like compute ratio"}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def other_configs_timing(ctx, pkg, synth):
+    """The BASELINE configs that are not the bench workload, measured once on rank 0 outside the timed region:
+    configs[0] geometry (1-min file), configs[2] (1-hour meeting, ~10.8 k embeddings) and configs[4] (50 000 x 256
+    clustering stress): pdist + merge loop through sd_linkage_dev, then fcluster; us per merge and the 32 N^2-byte
+    roofline fraction."""
+    import ctypes as C
+    peak, _ = measured_peaks()
+    out = {}
+    for name, N, D in (("cfg1_1min_wav_N327", 327, 192), ("cfg3_1h_meeting_N10773", 10773, 192),
+                       ("cfg5_stress_N50000", 50000, 256)):
+        x, _ = synth.stress_embeddings(200 + D + N % 97, N, D, 6 if N < 20000 else 12)
+        x /= np.linalg.norm(x, axis=1, keepdims=True)
+        d_x = ctx.to_device(np.ascontiguousarray(x, np.float64))
+        d_Z = ctx.malloc(8 * 4 * (N - 1))
+        d_T = ctx.malloc(4 * N)
+        try:
+            ms, pd = [], []
+            for _ in range(2):
+                ctx.timer_start(6)
+                ctx._check(ctx.L.sd_linkage_dev(ctx.h, d_x, N, D, d_Z))
+                ctx.timer_stop(6)
+                ms.append(ctx.timer_ms(6))
+                pd.append(ctx.linkage_stage_ms())
+            t, (pdist_ms, merge_ms) = min(ms), min(pd)
+            out[name] = {"N": N, "D": D, "pdist_plus_merges_ms": t, "pdist_ms": pdist_ms, "merges_ms": merge_ms,
+                         "us_per_merge": merge_ms * 1e3 / (N - 1),
+                         "algorithmic_gb": 32.0 * N * N / 1e9, "gbs": 32.0 * N * N / (merge_ms / 1e3) / 1e9,
+                         "frac_of_hbm": 32.0 * N * N / (merge_ms / 1e3) / 1e9 / peak,
+                         "pdist_f64_tflops": 3.0 * D * N * N / 2 / (pdist_ms / 1e3) / 1e12 if pdist_ms else None}
+        finally:
+            ctx.free(d_x)
+            ctx.free(d_Z)
+            ctx.free(d_T)
+    return out
 
 
 def next_rows_timing(ctx, pkg, synth, geo, d_seg, d_bin, d_hard, chunks, frames, reps=5):
@@ -554,10 +629,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--files", type=int, default=8, help="files per step per GPU, processed concurrently")
-    ap.add_argument("--async-clustering", action="store_true",
-                    help="batch pass with sd_clustering_async_dev (no read-backs) instead of sd_clustering_dev; "
-                         "measured slower in the batch (25 vs 20.5 ms per 8 files), see DESIGN.md section 5")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
+                    help="cfg2 (default): BASELINE configs[1], --files 10-min files per GPU per step (weak scaling); "
+                         "cfg4: BASELINE configs[3], 64 five-minute files sharded over the GPUs (strong scaling)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs_ms block (cfg1 / cfg3 / cfg5 sizes)")
     args = ap.parse_args()
+    WORKLOAD.update(WORKLOADS[args.workload])
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

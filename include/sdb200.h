@@ -303,6 +303,54 @@ int sd_crop_chunks(sd_ctx* ctx, const float* wave, int64_t num_samples, const do
 int sd_crop_chunks_dev(sd_ctx* ctx, const float* d_wave, int64_t num_samples, const double* starts_s, int n_chunks,
                        double duration, int sample_rate, float* d_out);
 
+/* ---- batches of files ------------------------------------------------------------------
+ * Files are independent units: a batch keeps `workers` files in flight on one GPU, each on its own sd_ctx (stream +
+ * scratch) driven by a library-owned host thread that runs the per-file sequence of speakerDiarization()
+ * (SD:2937-3234) over the hot path: STFT of the C*S embedding items -> binarize -> speaker_count -> clustering (with
+ * the inactive-speaker mask) -> skip-average aggregate of the diarization scores.  A stage runs when both its input
+ * and its output pointer are set.  One thread submits; file i of a batch runs on worker i % workers, in order.
+ * Pointers are HOST (pinned recommended; H2D/D2H inside, overlapped across the files in flight) or DEVICE.
+ * Multi-GPU: one sd_batch per GPU (one process per GPU, or one batch per device in a process); files are assigned
+ * to GPUs by the caller (shard.assign_files: longest-processing-time first). */
+typedef struct sd_batch sd_batch;
+typedef enum sd_batch_pointers { SD_BATCH_HOST = 0, SD_BATCH_DEVICE = 1 } sd_batch_pointers;
+typedef struct sd_file {
+    /* geometry */
+    int C, F, S;       /* chunks, frames per chunk, local speakers */
+    int L;             /* samples per embedding item */
+    int D;             /* embedding dimension */
+    int Kd;            /* columns of diar_scores (0 = none) */
+    double onset;      /* binarisation threshold (SegmentModel: 0.4442333667381752, SD:1339) */
+    sd_window chunks;  /* chunk window: start, step, duration, num_samples of the file */
+    sd_window frames;  /* model frame window (step = duration = 0.016875, SD:2430-2432) */
+    /* inputs */
+    const float* wav_items;      /* [C*S][L] masked chunk signals */
+    const float* segmentations;  /* [C][F][S] */
+    const double* embeddings;    /* [C][S][D], NaN row = absent */
+    const double* diar_scores;   /* [C][F][Kd], NaN = absent cluster */
+    /* outputs */
+    float* stft;       /* [C*S][T][201][2] */
+    double* binarized; /* [C][F][S] */
+    int32_t* count;    /* [count_cap] */
+    int64_t count_cap;
+    int32_t* hard;     /* [C][S] */
+    double* diar;      /* [sd_aggregate_num_frames(C, chunks, frames)][Kd] */
+    /* results, valid after sd_batch_wait */
+    int64_t n_count;
+    int64_t n_diar;
+    int num_clusters;
+    int status;        /* sd_status of this file */
+    sd_window count_frames;
+} sd_file;
+int sd_batch_create(int device, int workers, sd_batch** out);
+void sd_batch_destroy(sd_batch* b);
+int sd_batch_set_params(sd_batch* b, const sd_stft_params* stft, const sd_cluster_params* cluster); /* NULL = keep */
+int sd_batch_workers(const sd_batch* b);
+void* sd_batch_stream(sd_batch* b, int worker); /* cudaStream_t of a worker (to order the caller's own work) */
+int sd_batch_submit(sd_batch* b, sd_file* files, int n, int pointers); /* returns at once; files must stay alive */
+int sd_batch_wait(sd_batch* b); /* all submitted files done (streams synchronised); first error, 0 if none */
+const char* sd_batch_last_error(const sd_batch* b);
+
 /* ---- stage intermediates (WRITE_DATA builds of the reference) ------------------------------------------
  * The bodies this library replaces write their intermediates to /tmp/cpp_<stage>.txt when the reference is built with
  * WRITE_DATA (consumer: pipeline/script/verifyEveryStepResult.py:6-17).  The fused kernels never materialise them;

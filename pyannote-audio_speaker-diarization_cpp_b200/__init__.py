@@ -57,6 +57,21 @@ class ClusterParams(C.Structure):
                 ("min_clusters", C.c_int), ("max_clusters", C.c_int), ("pdist_mode", C.c_int)]
 
 
+class SdFile(C.Structure):
+    """sd_file of include/sdb200.h: one file of a batch (geometry, input / output pointers, results)."""
+    _fields_ = [("C", C.c_int), ("F", C.c_int), ("S", C.c_int), ("L", C.c_int), ("D", C.c_int), ("Kd", C.c_int),
+                ("onset", C.c_double), ("chunks", Window), ("frames", Window),
+                ("wav_items", C.c_void_p), ("segmentations", C.c_void_p), ("embeddings", C.c_void_p),
+                ("diar_scores", C.c_void_p),
+                ("stft", C.c_void_p), ("binarized", C.c_void_p), ("count", C.c_void_p), ("count_cap", C.c_int64),
+                ("hard", C.c_void_p), ("diar", C.c_void_p),
+                ("n_count", C.c_int64), ("n_diar", C.c_int64), ("num_clusters", C.c_int), ("status", C.c_int),
+                ("count_frames", Window)]
+
+
+SD_BATCH_HOST, SD_BATCH_DEVICE = 0, 1
+
+
 class SdError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("sdb200 error %d: %s" % (code, msg))
@@ -78,6 +93,8 @@ EXPORTS = [
     "sd_crop_chunks_dev", "sd_clustering_async_dev", "sd_status_reset", "sd_status_check",
     "sd_clustering_ex", "sd_binarize_rows_stages", "sd_trim_sum", "sd_mask_interpolate", "sd_clustered_segmentations",
     "sd_to_diarization", "sd_stft_kaldi_params", "sd_stft_num_frames_mode", "sd_fbank_kaldi_params",
+    "sd_batch_create", "sd_batch_destroy", "sd_batch_set_params", "sd_batch_workers", "sd_batch_stream",
+    "sd_batch_submit", "sd_batch_wait", "sd_batch_last_error",
 ]
 
 _lib = None
@@ -173,6 +190,14 @@ def lib():
         "sd_mask_interpolate": (i, [vp, vp, i, i, i, C.c_float, vp, vp]),
         "sd_clustered_segmentations": (i, [vp, vp, i, i, i, vp, i, vp]),
         "sd_to_diarization": (i, [vp, vp, i64, i, W, vp, i64, W, vp, i64, c_lp, W, vp, c_lp]),
+        "sd_batch_create": (i, [i, i, C.POINTER(vp)]),
+        "sd_batch_destroy": (None, [vp]),
+        "sd_batch_set_params": (i, [vp, C.POINTER(StftParams), C.POINTER(ClusterParams)]),
+        "sd_batch_workers": (i, [vp]),
+        "sd_batch_stream": (vp, [vp, i]),
+        "sd_batch_submit": (i, [vp, C.POINTER(SdFile), i, i]),
+        "sd_batch_wait": (i, [vp]),
+        "sd_batch_last_error": (C.c_char_p, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -193,6 +218,61 @@ def _win(w):
 
 
 FRAMES = (0.0, FRAME_STEP, FRAME_DURATION, 0)
+
+
+class Batch:
+    """sd_batch: `workers` files in flight on one GPU, driven by library-owned host threads."""
+
+    def __init__(self, device=0, workers=8):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.sd_batch_create(device, workers, C.byref(h))
+        if rc != SD_OK:
+            raise SdError(rc, "sd_batch_create(device=%d) failed: no usable CUDA device (no CPU fallback exists)" % device)
+        self.h = h
+        self.workers = workers
+
+    def close(self):
+        if self.h:
+            self.L.sd_batch_destroy(self.h)
+            self.h = None
+
+    def submit(self, files, pointers=SD_BATCH_HOST):
+        """files: a ctypes array of SdFile (kept alive by the caller until wait() returns)."""
+        rc = self.L.sd_batch_submit(self.h, files, len(files), pointers)
+        if rc:
+            raise SdError(rc, "sd_batch_submit: invalid arguments")
+
+    def wait(self):
+        rc = self.L.sd_batch_wait(self.h)
+        if rc:
+            raise SdError(rc, (self.L.sd_batch_last_error(self.h) or b"").decode())
+
+    def run(self, files, pointers=SD_BATCH_HOST):
+        self.submit(files, pointers)
+        self.wait()
+
+    def stream(self, worker):
+        return self.L.sd_batch_stream(self.h, worker)
+
+
+def make_file(geo_C, F, S, L, D, chunks, frames=None, onset=None, Kd=0, **ptrs):
+    """Fill an SdFile; pointer arguments are numpy arrays (host mode) or integer device addresses."""
+    f = SdFile()
+    f.C, f.F, f.S, f.L, f.D, f.Kd = geo_C, F, S, L, D, Kd
+    f.onset = ONSET if onset is None else onset
+    f.chunks = _win(chunks)
+    f.frames = _win(frames if frames is not None else FRAMES)
+    for k, v in ptrs.items():
+        if k == "count_cap":
+            f.count_cap = int(v)
+        elif v is None:
+            setattr(f, k, None)
+        elif isinstance(v, np.ndarray):
+            setattr(f, k, v.ctypes.data)
+        else:
+            setattr(f, k, int(v))
+    return f
 
 
 class Context:

@@ -75,3 +75,12 @@ def test_stft_phase_emulation_on_cpu(tmp_path):
                            "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
+
+
+def test_batch_has_no_cpu_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.SdError) as e:
+        pkg.Batch(0, 2)
+    assert e.value.code == pkg.SD_ERR_CUDA

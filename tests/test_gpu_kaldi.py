@@ -3,7 +3,8 @@ pre-emphasis; plus Kaldi's DC removal and its two framings) through the C-ABI.
 
   * sd_stft with sd_stft_kaldi_params   vs the fp64 numpy restatement oracle.kaldi_stft (<= 1e-4 abs)
   * sd_fbank with sd_fbank_kaldi_params vs torchaudio.compliance.kaldi.fbank itself, frozen in
-    tests/golden/kaldi_fbank.npz (oracle/make_golden_kaldi.py): <= 1e-4 in the log domain on mel energies above 3e-4,
+    tests/golden/kaldi_fbank.npz (oracle/make_golden_kaldi.py): <= 2e-4 in the log domain on mel energies above 3e-4
+    (<= 1e-4 against the fp64 restatement, which torchaudio's own fp32 arithmetic also only meets to ~7e-5),
     <= 5e-3 on near-silent bins (both sides are fp32 there: log of energies around 1e-6 amplifies the FFT's rounding
     noise; the fp64 restatement shows the same spread against torchaudio, tests/test_kaldi_oracle.py)
 """
@@ -68,8 +69,12 @@ def test_kaldi_fbank_vs_torchaudio_golden(ctx):
         assert got.shape == want.shape
         err = np.abs(got - want)
         loud = want > -8.0
-        assert err[loud].max() < 1e-4, (k, float(err[loud].max()))
+        # fp32 kernel vs fp32 torchaudio: each is within ~6e-5 of the fp64 restatement on these bins
+        assert err[loud].max() < 2e-4, (k, float(err[loud].max()))
         assert err.max() < 5e-3, (k, float(err.max()))
+        for b in range(wav.shape[0]):  # and against the fp64 restatement: the 1e-4 bar
+            exact = O.kaldi_fbank(wav[b], 80, snip, pre, dc)
+            assert np.abs(got[b] - exact)[exact > -8.0].max() < 1e-4, (k, b)
         n += 1
     assert n == 8
 
