@@ -194,6 +194,8 @@ int sd_normalize(sd_ctx* ctx, double* x, int N, int D);
 int sd_pdist(sd_ctx* ctx, const double* x, int N, int D, int mode, double* condensed);
 int sd_linkage(sd_ctx* ctx, const double* x, int N, int D, double* Z);
 int sd_linkage_dev(sd_ctx* ctx, const double* d_x, int N, int D, double* d_Z);
+/* CUDA-event times of the last linkage on this context: the distance matrix and the N-1 merges (synchronises). */
+int sd_linkage_stage_ms(sd_ctx* ctx, float* pdist_ms, float* merges_ms);
 int sd_fcluster(sd_ctx* ctx, const double* Z, int N, double cutoff, int32_t* T);
 int sd_cluster(sd_ctx* ctx, const double* x, int N, int D, double cutoff, int32_t* T);
 int sd_cosine_cdist(sd_ctx* ctx, const double* a, int na, const double* b, int nb, int D, double* out);
@@ -346,6 +348,7 @@ int sd_batch_create(int device, int workers, sd_batch** out);
 void sd_batch_destroy(sd_batch* b);
 int sd_batch_set_params(sd_batch* b, const sd_stft_params* stft, const sd_cluster_params* cluster); /* NULL = keep */
 int sd_batch_workers(const sd_batch* b);
+int64_t sd_batch_launch_count(const sd_batch* b); /* kernels of this library launched by all workers so far */
 void* sd_batch_stream(sd_batch* b, int worker); /* cudaStream_t of a worker (to order the caller's own work) */
 int sd_batch_submit(sd_batch* b, sd_file* files, int n, int pointers); /* returns at once; files must stay alive */
 int sd_batch_wait(sd_batch* b); /* all submitted files done (streams synchronised); first error, 0 if none */

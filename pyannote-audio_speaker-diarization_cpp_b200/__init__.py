@@ -94,7 +94,7 @@ EXPORTS = [
     "sd_clustering_ex", "sd_binarize_rows_stages", "sd_trim_sum", "sd_mask_interpolate", "sd_clustered_segmentations",
     "sd_to_diarization", "sd_stft_kaldi_params", "sd_stft_num_frames_mode", "sd_fbank_kaldi_params",
     "sd_batch_create", "sd_batch_destroy", "sd_batch_set_params", "sd_batch_workers", "sd_batch_stream",
-    "sd_batch_submit", "sd_batch_wait", "sd_batch_last_error",
+    "sd_batch_submit", "sd_batch_wait", "sd_batch_last_error", "sd_batch_launch_count", "sd_linkage_stage_ms",
 ]
 
 _lib = None
@@ -198,6 +198,8 @@ def lib():
         "sd_batch_submit": (i, [vp, C.POINTER(SdFile), i, i]),
         "sd_batch_wait": (i, [vp]),
         "sd_batch_last_error": (C.c_char_p, [vp]),
+        "sd_batch_launch_count": (i64, [vp]),
+        "sd_linkage_stage_ms": (i, [vp, c_fp, c_fp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -254,6 +256,9 @@ class Batch:
 
     def stream(self, worker):
         return self.L.sd_batch_stream(self.h, worker)
+
+    def launch_count(self):
+        return int(self.L.sd_batch_launch_count(self.h))
 
 
 def make_file(geo_C, F, S, L, D, chunks, frames=None, onset=None, Kd=0, **ptrs):
@@ -377,6 +382,12 @@ class Context:
             p.window_kind = 2
             p.window = self._win_keep.ctypes.data_as(c_fp)
         return p
+
+    def linkage_stage_ms(self):
+        """(pdist ms, merge-loop ms) of the last linkage on this context."""
+        a, b = C.c_float(), C.c_float()
+        self._check(self.L.sd_linkage_stage_ms(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def stft_kaldi_params(self, snip_edges=False, preemph=0.97, remove_dc_offset=True):
         """Kaldi framing: povey window, per-frame pre-emphasis / DC removal, snip_edges as given."""

@@ -154,6 +154,8 @@ void sd_ctx_destroy(sd_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& b : ctx->bufs)
         if (b.p) cudaFree(b.p);
+    for (auto& e : ctx->ev_lk)
+        if (e) cudaEventDestroy(e);
     if (ctx->d_window) cudaFree(ctx->d_window);
     if (ctx->d_twiddle) cudaFree(ctx->d_twiddle);
     if (ctx->d_mel) cudaFree(ctx->d_mel);
@@ -753,6 +755,16 @@ int sd_linkage_dev(sd_ctx* ctx, const double* d_x, int N, int D, double* d_Z) {
     SD_REQUIRE(ctx, N > 1 && D > 0, "sd_linkage_dev: need N > 1, D > 0");
     // enqueue only: the status word belongs to the caller (sd_status_reset / sd_status_check)
     return linkage_launch(ctx, d_x, N, D, d_Z, SD_PDIST_EXACT_F64);
+}
+
+int sd_linkage_stage_ms(sd_ctx* ctx, float* pdist_ms, float* merges_ms) {
+    if (!ctx || !pdist_ms || !merges_ms) return SD_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    SD_REQUIRE(ctx, ctx->ev_lk[0] != nullptr, "sd_linkage_stage_ms: no linkage has run on this context yet");
+    SD_CUDA(ctx, cudaEventSynchronize(ctx->ev_lk[2]));
+    SD_CUDA(ctx, cudaEventElapsedTime(pdist_ms, ctx->ev_lk[0], ctx->ev_lk[1]));
+    SD_CUDA(ctx, cudaEventElapsedTime(merges_ms, ctx->ev_lk[1], ctx->ev_lk[2]));
+    return SD_OK;
 }
 
 int sd_linkage(sd_ctx* ctx, const double* x, int N, int D, double* Z) {

@@ -156,6 +156,13 @@ int sd_batch_set_params(sd_batch* b, const sd_stft_params* sp, const sd_cluster_
 
 int sd_batch_workers(const sd_batch* b) { return b ? (int)b->workers.size() : 0; }
 
+int64_t sd_batch_launch_count(const sd_batch* b) {
+    int64_t n = 0;
+    if (b)
+        for (const auto& w : b->workers) n += sd_launch_count(w.ctx);
+    return n;
+}
+
 void* sd_batch_stream(sd_batch* b, int worker) {
     if (!b || worker < 0 || worker >= (int)b->workers.size()) return nullptr;
     return sd_ctx_stream(b->workers[(size_t)worker].ctx);

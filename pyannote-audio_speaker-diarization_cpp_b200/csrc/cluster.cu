@@ -2348,9 +2348,16 @@ int linkage_launch(sd_ctx* ctx, const double* d_x, int N, int D, double* d_Z, in
     if (N < 2) return SD_OK;
     char* base;
     LinkLayout L;
+    if (!ctx->ev_lk[0])
+        for (auto& e : ctx->ev_lk) SD_CUDA(ctx, cudaEventCreate(&e));
+    SD_CUDA(ctx, cudaEventRecord(ctx->ev_lk[0], ctx->stream));
     int rc = pdist_square(ctx, d_x, N, D, mode, &base, &L);
     if (rc) return rc;
-    return linkage_on_square(ctx, base, L, d_x, N, D, d_Z);
+    SD_CUDA(ctx, cudaEventRecord(ctx->ev_lk[1], ctx->stream));
+    rc = linkage_on_square(ctx, base, L, d_x, N, D, d_Z);
+    if (rc) return rc;
+    SD_CUDA(ctx, cudaEventRecord(ctx->ev_lk[2], ctx->stream));
+    return SD_OK;
 }
 
 // Clustering::fcluster; d_T[N] labels 1..K, d_num receives K
