@@ -30,6 +30,11 @@ import time
 
 import numpy as np
 
+# More than 8 files in flight need more than the default 8 hardware work queues: with CUDA_DEVICE_MAX_CONNECTIONS = 8
+# the 9th stream shares a queue with the 1st and its kernels wait behind that file's 9 ms merge loop (measured:
+# 12 concurrent linkages took two waves, profiles/r02_linkage_concurrent.log).  Must be set before CUDA initialises.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 

@@ -13,6 +13,7 @@
 
 #include <atomic>
 #include <condition_variable>
+#include <cstdlib>
 #include <deque>
 #include <mutex>
 #include <thread>
@@ -114,6 +115,10 @@ extern "C" {
 int sd_batch_create(int device, int workers, sd_batch** out) {
     if (!out || workers < 1 || workers > 64) return SD_ERR_INVALID;
     *out = nullptr;
+    // Streams beyond the number of hardware work queues (8 by default) share a queue and serialise behind each
+    // other's 9 ms merge loops.  Takes effect only if CUDA has not been initialised in this process yet; otherwise
+    // the caller must export it.  Never overrides a value the user has set.
+    if (workers > 8) setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     sd_batch* b = new sd_batch();
     b->device = device;
     sd_stft_default_params(&b->sp);
