@@ -46,6 +46,75 @@ SD_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y
 // multiply by -i (forward-transform rotation)
 SD_HD float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
 
+// Blackwell (sm_100a) has packed fp32 arithmetic -- add / mul / fma on a register pair in ONE issue slot (SASS FADD2 /
+// FMUL2 / FFMA2).  A complex value is exactly such a pair, so the butterflies below issue half the floating-point
+// instructions of the scalar form; the kernel is issue-bound (profiles/r01_stft_v5_ncu_summary.json: 578 M
+// warp-instructions, 57 % of them FADD/FFMA/FMUL), so that is where the time goes.  Multiplication by -i is folded
+// into an FFMA2 with the constant pair (1, -1) / (-1, 1) applied to the swapped operand (x * +-1 is exact, so the
+// results are the scalar ones bit for bit).  The host build (tests/cpp/emulate_stft.cpp) keeps the scalar form.
+#if defined(__CUDA_ARCH__) && !defined(SD_NO_PACKED_F32)
+#define SD_PACKED_F32 1
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 upk2(unsigned long long u) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(u));
+    return r;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
+    return upk2(r);
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
+    return upk2(r);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float bx, float by) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(bx, by)));
+    return upk2(r);
+}
+// a * (bx, by) + c, element-wise
+__device__ __forceinline__ float2 fma2(float2 a, float bx, float by, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(bx, by)), "l"(pk2(c.x, c.y)));
+    return upk2(r);
+}
+// t + (-i) d  and  t - (-i) d
+__device__ __forceinline__ float2 add_mi(float2 t, float2 d) { return fma2(make_float2(d.y, d.x), 1.f, -1.f, t); }
+__device__ __forceinline__ float2 sub_mi(float2 t, float2 d) { return fma2(make_float2(d.y, d.x), -1.f, 1.f, t); }
+
+__device__ __forceinline__ void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
+    const float2 t0 = add2(x0, x2), t1 = sub2(x0, x2), t2 = add2(x1, x3), d = sub2(x1, x3);
+    x0 = add2(t0, t2);
+    x2 = sub2(t0, t2);
+    x1 = add_mi(t1, d);
+    x3 = sub_mi(t1, d);
+}
+
+__device__ __forceinline__ void dft5(float2& x0, float2& x1, float2& x2, float2& x3, float2& x4) {
+    const float c = 0.55901699437494742f;   // (cos(2pi/5) - cos(4pi/5)) / 2
+    const float s1 = 0.95105651629515357f;  // sin(2pi/5)
+    const float s2 = 0.58778525229247313f;  // sin(4pi/5)
+    const float2 t1 = add2(x1, x4), t2 = add2(x2, x3), t3 = sub2(x1, x4), t4 = sub2(x2, x3);
+    const float2 t5 = add2(t1, t2);
+    const float2 m1 = fma2(t5, -0.25f, -0.25f, x0);
+    const float2 d = sub2(t1, t2);
+    const float2 a1 = fma2(d, c, c, m1), a2 = fma2(d, -c, -c, m1);
+    const float2 u1 = fma2(t4, s2, s2, mul2(t3, s1, s1));
+    const float2 u2 = fma2(t4, -s1, -s1, mul2(t3, s2, s2));
+    x0 = add2(x0, t5);
+    x1 = add_mi(a1, u1);
+    x4 = sub_mi(a1, u1);
+    x2 = add_mi(a2, u2);
+    x3 = sub_mi(a2, u2);
+}
+#else
 SD_HD void dft4(float2& x0, float2& x1, float2& x2, float2& x3) {
     float2 t0 = cadd(x0, x2), t1 = csub(x0, x2), t2 = cadd(x1, x3), t3 = mul_mi(csub(x1, x3));
     x0 = cadd(t0, t2);
@@ -74,6 +143,24 @@ SD_HD void dft5(float2& x0, float2& x1, float2& x2, float2& x3, float2& x4) {
     x2 = cadd(a2, u2);
     x3 = csub(a2, u2);
 }
+#endif
+
+// element-wise product of two pairs; (a.x + b.x, a.y - b.y) and (a.y + b.y, b.x - a.x) of the real-pair split
+#if defined(SD_PACKED_F32)
+__device__ __forceinline__ float2 cmul_elem(float2 a, float2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
+    return upk2(r);
+}
+__device__ __forceinline__ float2 split_a(float2 a, float2 b) { return fma2(b, 1.f, -1.f, a); }
+__device__ __forceinline__ float2 split_b(float2 a, float2 b) {
+    return fma2(make_float2(a.y, a.x), 1.f, -1.f, make_float2(b.y, b.x));
+}
+#else
+SD_HD float2 cmul_elem(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+SD_HD float2 split_a(float2 a, float2 b) { return make_float2(a.x + b.x, a.y - b.y); }
+SD_HD float2 split_b(float2 a, float2 b) { return make_float2(a.y + b.y, b.x - a.x); }
+#endif
 
 // Slot of the register array holding input sample n (natural order) == n; after dft20() output bin k is
 // found at slot dft20_slot(k).
@@ -153,14 +240,15 @@ SD_HD int tw_table_source(int e) {  // returns r*20 + k1 of the value stored at 
 }
 
 // phase 1 with the window (wtab[20*n1 + r]) in a shared table and the twiddles behind a per-thread base pointer
-SD_HD void stft_phase1_tab(const float* sig, int fa_off, int fb_off, const float* wtab, const float2* twp, int g, int r,
+// (the table holds the pair (w, w) so that the two frames are windowed by one packed multiply)
+SD_HD void stft_phase1_tab(const float* sig, int fa_off, int fb_off, const float2* wtab, const float2* twp, int g, int r,
                            float2* xchg) {
     float2 v[20];
 #pragma unroll
     for (int n1 = 0; n1 < 20; ++n1) {
         const int o = 20 * n1 + r;
-        const float w = wtab[o];
-        v[n1] = make_float2(sig[fa_off + o + sig_pad_even(n1)] * w, sig[fb_off + o + sig_pad_odd(n1)] * w);
+        const float2 w = wtab[o];
+        v[n1] = cmul_elem(make_float2(sig[fa_off + o + sig_pad_even(n1)], sig[fb_off + o + sig_pad_odd(n1)]), w);
     }
     dft20(v);
     float2* dst = xchg + g * kGroupStride + r;
@@ -193,13 +281,13 @@ SD_HD float2 stft_frame_partial_sums(const float* sig, int fa_off, int fb_off, i
 }
 
 // phase 1 with pre-emphasis coefficient c and the per-frame offsets dc = (1 - c) * mean (zero when DC removal is off)
-SD_HD void stft_phase1_kaldi(const float* sig, int fa_off, int fb_off, const float* wtab, const float2* twp, int g, int r,
+SD_HD void stft_phase1_kaldi(const float* sig, int fa_off, int fb_off, const float2* wtab, const float2* twp, int g, int r,
                              float2* xchg, float c, float2 dc) {
     float2 v[20];
 #pragma unroll
     for (int n1 = 0; n1 < 20; ++n1) {
         const int o = 20 * n1 + r;
-        const float w = wtab[o];
+        const float w = wtab[o].x;
         const int pa = fa_off + o + sig_pad_even(n1), pb = fb_off + o + sig_pad_odd(n1);
         // previous sample: one float to the left, except across a hop-segment boundary (r == 0 at n1 = 8, 16) and
         // at the start of the frame, where Kaldi uses the first sample itself
@@ -320,8 +408,8 @@ SD_HD void stft_split_store(const float2 (&v)[20], const float2* zup, int g, int
     for (int m = 0; m < 10; ++m) {
         const float2 a = v[dft20_slot(m)];
         const float2 b = zm[-20 * m];
-        if (HAS_A) oa[r + 20 * m] = make_float2(a.x + b.x, a.y - b.y);
-        if (HAS_B) ob[r + 20 * m] = make_float2(a.y + b.y, b.x - a.x);
+        if (HAS_A) oa[r + 20 * m] = split_a(a, b);
+        if (HAS_B) ob[r + 20 * m] = split_b(a, b);
     }
     if (r == 0) {  // k = 200: partner of Z[200] is itself
         const float2 a = v[dft20_slot(10)];

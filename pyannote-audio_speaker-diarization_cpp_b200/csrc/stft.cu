@@ -27,7 +27,7 @@ struct StftCfg {
     static constexpr int kSigPadded = sig_padded_size(kSigFloats) + 4;   // staged floats (hop segments padded 8 / 12)
     static constexpr size_t kSigBytes = (size_t)((kSigPadded + 3) / 4 * 4) * sizeof(float);
     static constexpr size_t kZBytes = (size_t)GROUPS * kZStride * sizeof(float2);
-    static constexpr size_t kTablesBytes = (size_t)GROUPS * kGroupStride * sizeof(float2) + kNfft * sizeof(float) +
+    static constexpr size_t kTablesBytes = (size_t)GROUPS * kGroupStride * sizeof(float2) + kNfft * sizeof(float2) +
                                            kTwTableUnits * sizeof(float2);
     // fbank kernel: the upper-spectrum buffer shares storage with the staged samples (dead after phase 1)
     static constexpr size_t kSmemBytes = (kSigBytes > kZBytes ? kSigBytes : kZBytes) + kTablesBytes;
@@ -163,16 +163,18 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xbuf = reinterpret_cast<float2*>(smem_raw);                 // phase 1 -> phase 2 transpose
     float2* twT = xbuf + GROUPS * kGroupStride;                         // twiddle table (see tw_thread_offset)
-    float* wtab = reinterpret_cast<float*>(twT + kTwTableUnits);        // window, pre-scaled by 1/2
-    float* sig = wtab + kNfft;                                          // padded samples of the tile
+    float2* wtab = twT + kTwTableUnits;                                 // window pairs (w, w), pre-scaled by 1/2
+    float* sig = reinterpret_cast<float*>(wtab + kNfft);                // padded samples of the tile
     float2* zup = xbuf;  // upper half of the spectrum: reuses the transpose buffer once phase 2 has loaded it
     __shared__ __align__(8) uint64_t bar;
     __shared__ float2 dc_part[KALDI ? GROUPS * kRadix : 1];
 
     const int g = threadIdx.x / kRadix;
     const int r = threadIdx.x - g * kRadix;
-    for (int i = threadIdx.x; i < kNfft; i += Cfg::kThreads)
-        wtab[i] = 0.5f * window[i];  // exact scaling; lets phase 3 drop its multiplications
+    for (int i = threadIdx.x; i < kNfft; i += Cfg::kThreads) {
+        const float wv = 0.5f * window[i];  // exact scaling; lets phase 3 drop its multiplications
+        wtab[i] = make_float2(wv, wv);
+    }
     for (int e = threadIdx.x; e < kTwTableUnits; e += Cfg::kThreads) twT[e] = twiddle[tw_table_source(e)];
     const float2* twp = twT + tw_thread_offset(threadIdx.x);
     if (threadIdx.x == 0) {
@@ -296,8 +298,8 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xbuf = reinterpret_cast<float2*>(smem_raw);
     float2* twT = xbuf + GROUPS * kGroupStride;
-    float* wtab = reinterpret_cast<float*>(twT + kTwTableUnits);
-    float* sig = wtab + kNfft;
+    float2* wtab = twT + kTwTableUnits;
+    float* sig = reinterpret_cast<float*>(wtab + kNfft);
     float2* zup = reinterpret_cast<float2*>(sig);
     float* pw = reinterpret_cast<float*>(xbuf);  // power spectra [frame][201], aliases the transpose buffer
     __shared__ __align__(8) uint64_t bar;
@@ -306,7 +308,10 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
 
     const int g = threadIdx.x / kRadix;
     const int r = threadIdx.x - g * kRadix;
-    for (int i = threadIdx.x; i < kNfft; i += Cfg::kThreads) wtab[i] = 0.5f * window[i];
+    for (int i = threadIdx.x; i < kNfft; i += Cfg::kThreads) {
+        const float wv = 0.5f * window[i];
+        wtab[i] = make_float2(wv, wv);
+    }
     for (int e = threadIdx.x; e < kTwTableUnits; e += Cfg::kThreads) twT[e] = twiddle[tw_table_source(e)];
     for (int i = threadIdx.x; i < (int)(sizeof(MelTable) / 4); i += Cfg::kThreads)
         reinterpret_cast<int*>(&smel)[i] = reinterpret_cast<const int*>(mel)[i];

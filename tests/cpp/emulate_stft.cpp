@@ -37,8 +37,9 @@ int main() {
         stft_phase3(zbuf.data(), g, t % kRadix, &out[(2 * g) * kBins * 2], &out[(2 * g + 1) * kBins * 2]);
     }
     // variant B (the kernel's): padded staging, shared window / twiddle tables, one exchange buffer
-    std::vector<float> sigp(sig_padded_size(nsig) + 8, 0.f), out2(frames * kBins * 2, 0.f), wtab(w);
-    for (auto& v : wtab) v *= 0.5f;  // the kernel folds the 1/2 of the real-pair split into the window
+    std::vector<float> sigp(sig_padded_size(nsig) + 8, 0.f), out2(frames * kBins * 2, 0.f);
+    std::vector<float2> wtab(w.size());  // (w/2, w/2): the kernel folds the 1/2 of the real-pair split into the window
+    for (size_t i = 0; i < w.size(); ++i) wtab[i] = make_float2(0.5f * w[i], 0.5f * w[i]);
     for (int j = 0; j < nsig; ++j) sigp[sig_pos(j)] = sig[j];
     std::vector<float2> twT(kTwTableUnits), xb(groups * kGroupStride);
     for (int e = 0; e < kTwTableUnits; ++e) {
