@@ -3,7 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-A "step" is one pass of the hot path over a batch of `--files` (default 8) synthetic 10-minute files per GPU, each
+A "step" is one pass of the hot path over a batch of `--files` (default 16) synthetic 10-minute files per GPU, each
 at BASELINE.json configs[1]
 (10 s chunks / 1 s step -> 591 chunks x 589 frames x 3 local speakers, 1 773 STFT items of 160 000 samples,
 1 773 embeddings of dimension 192): STFT of every (chunk, speaker) item, hysteresis binarisation, speaker
@@ -11,10 +11,10 @@ count (trim + aggregate + rint), clustering (normalise, fp64 pdist, centroid lin
 assignment) and the skip-average aggregation of the diarization path.
 
  * `value`   : device-resident (inputs already in HBM), CUDA-event timed, max over ranks; the files of the batch run
-               concurrently (one host thread, library context and CUDA stream per file) so that the latency-bound
-               clustering of one file is hidden under the bandwidth-bound STFT of the others; `single_file` reports
-               one file alone together with the per-stage breakdown
- * `e2e`     : the same step through the host-pointer C-ABI calls (pinned host buffers, H2D + D2H inside)
+               concurrently through the native batch API (sd_batch_*: one library-owned host thread, library context
+               and CUDA stream per file in flight) so that the latency-bound clustering of one file is hidden under the
+               bandwidth-bound STFT of the others; `single_file` reports one file alone with the per-stage breakdown
+ * `e2e`     : the same API with HOST pointers (pinned buffers, H2D + D2H inside the timed region), 3 files in flight
  * `roofline`: the STFT kernel (the HBM-bound kernel the metric names) -- algorithmic bytes / event time
  * `cpu_baseline`: the reference's own code (oracle/_ref) on this box's host cores, bounded sample
 With N > 1 every rank processes its own batch of files (files shard with no data-path collective; the labels of all
@@ -643,7 +643,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--files", type=int, default=8, help="files per step per GPU, processed concurrently")
+    ap.add_argument("--files", type=int, default=16,
+                    help="files per step per GPU, all in flight at once (16: 345 k audio-s/s on one B200, 8: 268 k, "
+                         "24-32: 360-375 k at twice the memory; profiles/r02_bench_v2_*.json)")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
                     help="cfg2 (default): BASELINE configs[1], --files 10-min files per GPU per step (weak scaling); "
                          "cfg4: BASELINE configs[3], 64 five-minute files sharded over the GPUs (strong scaling)")

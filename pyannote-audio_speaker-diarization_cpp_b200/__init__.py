@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsdb200.so")
+LIB_PATH = os.environ.get("SDB200_LIB") or os.path.join(HERE, "libsdb200.so")  # SDB200_LIB: an experiment build
 
 c_fp = C.POINTER(C.c_float)
 c_dp = C.POINTER(C.c_double)

@@ -1038,6 +1038,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// fire-and-forget fetch of one 128-byte line into L2 (no register, no scoreboard)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cluster_barrier_relaxed() {
     asm volatile("barrier.cluster.arrive.relaxed.aligned;\nbarrier.cluster.wait.aligned;" ::: "memory");
 }
@@ -1093,6 +1095,10 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
     const int NG = (n + 31) / 32;
     const int NGl = NG > rank ? (NG - rank + kLcCtas - 1) / kLcCtas : 0;  // groups of this CTA: g = lg * 8 + rank
     const int NGmax = (NG + kLcCtas - 1) / kLcCtas;
+    // A matrix beyond the L2 capacity streams its rows from HBM on every merge: a warp then has only PF groups of
+    // loads in flight per ~1 us round trip.  In that regime the rows' later groups are prefetched into L2 while the
+    // first round is on its way (lanes 0/1: the two 128-byte lines of a 32-row group).
+    const bool cold = (size_t)n * (size_t)w.ld * sizeof(double) > ((size_t)64 << 20);
     // own rows (private to the owning thread)
     double* lb = reinterpret_cast<double*>(lc_smem);
     double* cur = lb + (size_t)NGmax * 32;
@@ -1404,6 +1410,11 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
                 const double* r = w.D + (size_t)x * w.ld;
                 double bv = INFINITY;
                 int bi = -1;
+                if (cold && lane < 2)
+                    for (int lg = warp + NW * PF; lg < NGl; lg += NW) {
+                        const int i0 = (lg * kLcCtas + rank) << 5;
+                        if (i0 + 31 > x) lc::prefetch_l2(r + i0 + 16 * lane);
+                    }
                 for (int lg0 = warp; lg0 < NGl; lg0 += NW * PF) {
                     double d[PF];
                     bool ok[PF];
@@ -1517,6 +1528,11 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
         bool have_terms = false;
         double ymv = INFINITY;
         int ymi = -1;
+        if (cold && lane < 4)
+            for (int lg = warp + NW * PF; lg < NGl; lg += NW) {
+                const int z0 = (lg * kLcCtas + rank) << 5;
+                lc::prefetch_l2((lane < 2 ? rowx : rowy) + z0 + 16 * (lane & 1));
+            }
         for (int lg0 = warp; lg0 < NGl; lg0 += NW * PF) {
             double dx[PF], dy[PF];
             bool live[PF];
@@ -1576,7 +1592,11 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
         const Top part = warp_top(ymi >= 0 ? ymv : INFINITY, ymi, ymi >= 0 ? 1 : 0);
         double v2;
         const Top t = warp_rows_top2(x, y, v2);
+#if defined(SD_LC_FENCE_CLUSTER)
+        asm volatile("fence.acq_rel.cluster;" ::: "memory");  // experiment: every consumer is in this cluster
+#else
         __threadfence();  // the sweep's stores are visible device-wide before any peer can see this publish
+#endif
         publish(par, t, v2, part.i >= 0 ? part.v : INFINITY, part.i, y, false);
         t0 = clock64();
         c_work += t0 - t1;

@@ -239,25 +239,113 @@ SD_HD int tw_table_source(int e) {  // returns r*20 + k1 of the value stored at 
     return r * 20 + k1;
 }
 
-// phase 1 with the window (wtab[20*n1 + r]) in a shared table and the twiddles behind a per-thread base pointer
-// (the table holds the pair (w, w) so that the two frames are windowed by one packed multiply)
-SD_HD void stft_phase1_tab(const float* sig, int fa_off, int fb_off, const float2* wtab, const float2* twp, int g, int r,
-                           float2* xchg) {
-    float2 v[20];
-#pragma unroll
-    for (int n1 = 0; n1 < 20; ++n1) {
-        const int o = 20 * n1 + r;
-        const float2 w = wtab[o];
-        v[n1] = cmul_elem(make_float2(sig[fa_off + o + sig_pad_even(n1)], sig[fb_off + o + sig_pad_odd(n1)]), w);
-    }
-    dft20(v);
-    float2* dst = xchg + g * kGroupStride + r;
+// Multiply the phase-1 outputs by W400^(r*k1), k1 = 0..19, and write them to the transpose buffer.
+// The shared-memory pipe is the kernel's busiest unit, so only the five twiddles W^(r*{1,2,4,8,16}) are read from the
+// table and the other fourteen are products of at most three of them (<= 3 roundings on a unit-modulus value:
+// ~2e-7 relative, far inside the 1e-4 bar): 5 instead of 19 eight-byte shared loads per thread and tile.
+// Each product is formed when its bin is reached, while the registers of the bins already stored are free again.
+SD_HD void twiddle_store(const float2 (&v)[20], const float2* twp, float2* dst) {
+#if defined(SD_TWIDDLE_TABLE_ONLY)
 #pragma unroll
     for (int k1 = 0; k1 < 20; ++k1) {
         float2 y = v[dft20_slot(k1)];
         if (k1 > 0) y = cmul(y, twp[k1 * kTwRow]);
         dst[k1 * kXchgRow] = y;
     }
+#else
+    dst[0] = v[dft20_slot(0)];
+    const float2 t1 = twp[1 * kTwRow], t2 = twp[2 * kTwRow];
+    const float2 t3 = cmul(t1, t2);
+    dst[1 * kXchgRow] = cmul(v[dft20_slot(1)], t1);
+    dst[2 * kXchgRow] = cmul(v[dft20_slot(2)], t2);
+    dst[3 * kXchgRow] = cmul(v[dft20_slot(3)], t3);
+    const float2 t4 = twp[4 * kTwRow];
+    dst[4 * kXchgRow] = cmul(v[dft20_slot(4)], t4);
+    dst[5 * kXchgRow] = cmul(v[dft20_slot(5)], cmul(t4, t1));
+    dst[6 * kXchgRow] = cmul(v[dft20_slot(6)], cmul(t4, t2));
+    dst[7 * kXchgRow] = cmul(v[dft20_slot(7)], cmul(t4, t3));
+    const float2 t8 = twp[8 * kTwRow];
+    const float2 t12 = cmul(t8, t4);
+    dst[8 * kXchgRow] = cmul(v[dft20_slot(8)], t8);
+    dst[9 * kXchgRow] = cmul(v[dft20_slot(9)], cmul(t8, t1));
+    dst[10 * kXchgRow] = cmul(v[dft20_slot(10)], cmul(t8, t2));
+    dst[11 * kXchgRow] = cmul(v[dft20_slot(11)], cmul(t8, t3));
+    dst[12 * kXchgRow] = cmul(v[dft20_slot(12)], t12);
+    dst[13 * kXchgRow] = cmul(v[dft20_slot(13)], cmul(t12, t1));
+    dst[14 * kXchgRow] = cmul(v[dft20_slot(14)], cmul(t12, t2));
+    dst[15 * kXchgRow] = cmul(v[dft20_slot(15)], cmul(t12, t3));
+    const float2 t16 = twp[16 * kTwRow];
+    dst[16 * kXchgRow] = cmul(v[dft20_slot(16)], t16);
+    dst[17 * kXchgRow] = cmul(v[dft20_slot(17)], cmul(t16, t1));
+    dst[18 * kXchgRow] = cmul(v[dft20_slot(18)], cmul(t16, t2));
+    dst[19 * kXchgRow] = cmul(v[dft20_slot(19)], cmul(t16, t3));
+#endif
+}
+
+// phase 1 with the window (wtab[20*n1 + r]) in a shared table and the twiddles behind a per-thread base pointer
+// Window table element: the plain value, or (SD_WINDOW_PAIRS) the pair (w, w) so that the two frames are windowed by
+// one packed multiply at the price of 8-byte table reads.
+#if defined(SD_WINDOW_PAIRS)
+typedef float2 wtab_t;
+SD_HD wtab_t wtab_make(float w) { return make_float2(w, w); }
+SD_HD float wtab_value(wtab_t w) { return w.x; }
+SD_HD float2 wtab_apply(float a, float b, wtab_t w) { return cmul_elem(make_float2(a, b), w); }
+#else
+typedef float wtab_t;
+SD_HD wtab_t wtab_make(float w) { return w; }
+SD_HD float wtab_value(wtab_t w) { return w; }
+SD_HD float2 wtab_apply(float a, float b, wtab_t w) { return make_float2(a * w, b * w); }
+#endif
+
+SD_HD void stft_phase1_tab(const float* sig, int fa_off, int fb_off, const wtab_t* wtab, const float2* twp, int g, int r,
+                           float2* xchg) {
+    // Frame B starts one hop (160 = 8 * 20 samples) after frame A, so B's sample n1 IS A's sample n1 + 8 (the same
+    // staged float) for n1 < 12: 28 shared-memory loads instead of 40.
+    float a[20], b[8];
+#pragma unroll
+    for (int n1 = 0; n1 < 20; ++n1) a[n1] = sig[fa_off + 20 * n1 + r + sig_pad_even(n1)];
+#pragma unroll
+    for (int n1 = 12; n1 < 20; ++n1) b[n1 - 12] = sig[fb_off + 20 * n1 + r + sig_pad_odd(n1)];
+    float2 v[20];
+#pragma unroll
+    for (int n1 = 0; n1 < 20; ++n1) v[n1] = wtab_apply(a[n1], n1 < 12 ? a[n1 + 8] : b[n1 - 12], wtab[20 * n1 + r]);
+    dft20(v);
+    twiddle_store(v, twp, xchg + g * kGroupStride + r);
+}
+
+// phase 1 for the reference's window (periodic Hamming, pre-scaled by 1/2) without a window table:
+//   w[n] / 2 = 0.27 - 0.23 cos(2 pi n / 400),  n = 20 n1 + r  =>  cos(theta_r + n1 pi/10) = cr C[n1] - sr S[n1]
+// with (cr, sr) = (cos, sin)(2 pi r / 400) in two registers of the thread and C, S compile-time constants: two FFMA per
+// sample instead of a shared-memory load (the shared-memory pipe is the kernel's limiter, the FMA pipe has room).
+// The values differ from at::hamming_window's fp32 table by a few ulp (~1e-7 relative), far inside the 1e-4 bar.
+SD_HD void stft_phase1_hamming(const float* sig, int fa_off, int fb_off, float cr, float sr, const float2* twp, int g,
+                               int r, float2* xchg) {
+    // -0.23 cos(n1 pi / 10) and 0.23 sin(n1 pi / 10), n1 = 0..19
+    constexpr float K1[20] = {-0.23f, -0.21874299874788533f, -0.1860739087062379f, -0.13519060802726882f,
+                              -0.0710739087062379f, 0.0f, 0.0710739087062379f, 0.13519060802726882f,
+                              0.1860739087062379f, 0.21874299874788533f, 0.23f, 0.21874299874788533f,
+                              0.1860739087062379f, 0.13519060802726882f, 0.0710739087062379f, 0.0f,
+                              -0.0710739087062379f, -0.13519060802726882f, -0.1860739087062379f,
+                              -0.21874299874788533f};
+    constexpr float K2[20] = {0.0f, 0.0710739087062379f, 0.13519060802726882f, 0.1860739087062379f,
+                              0.21874299874788533f, 0.23f, 0.21874299874788533f, 0.1860739087062379f,
+                              0.13519060802726882f, 0.0710739087062379f, 0.0f, -0.0710739087062379f,
+                              -0.13519060802726882f, -0.1860739087062379f, -0.21874299874788533f, -0.23f,
+                              -0.21874299874788533f, -0.1860739087062379f, -0.13519060802726882f,
+                              -0.0710739087062379f};
+    float a[20], b[8];
+#pragma unroll
+    for (int n1 = 0; n1 < 20; ++n1) a[n1] = sig[fa_off + 20 * n1 + r + sig_pad_even(n1)];
+#pragma unroll
+    for (int n1 = 12; n1 < 20; ++n1) b[n1 - 12] = sig[fb_off + 20 * n1 + r + sig_pad_odd(n1)];
+    float2 v[20];
+#pragma unroll
+    for (int n1 = 0; n1 < 20; ++n1) {
+        const float w = fmaf(K1[n1], cr, fmaf(K2[n1], sr, 0.27f));
+        v[n1] = make_float2(a[n1] * w, (n1 < 12 ? a[n1 + 8] : b[n1 - 12]) * w);
+    }
+    dft20(v);
+    twiddle_store(v, twp, xchg + g * kGroupStride + r);
 }
 
 // ---- Kaldi-compatible per-frame conditioning (north_star bullet 1) -------------------------------------------------
@@ -281,13 +369,13 @@ SD_HD float2 stft_frame_partial_sums(const float* sig, int fa_off, int fb_off, i
 }
 
 // phase 1 with pre-emphasis coefficient c and the per-frame offsets dc = (1 - c) * mean (zero when DC removal is off)
-SD_HD void stft_phase1_kaldi(const float* sig, int fa_off, int fb_off, const float2* wtab, const float2* twp, int g, int r,
+SD_HD void stft_phase1_kaldi(const float* sig, int fa_off, int fb_off, const wtab_t* wtab, const float2* twp, int g, int r,
                              float2* xchg, float c, float2 dc) {
     float2 v[20];
 #pragma unroll
     for (int n1 = 0; n1 < 20; ++n1) {
         const int o = 20 * n1 + r;
-        const float w = wtab[o].x;
+        const float w = wtab_value(wtab[o]);
         const int pa = fa_off + o + sig_pad_even(n1), pb = fb_off + o + sig_pad_odd(n1);
         // previous sample: one float to the left, except across a hop-segment boundary (r == 0 at n1 = 8, 16) and
         // at the start of the frame, where Kaldi uses the first sample itself
@@ -300,13 +388,7 @@ SD_HD void stft_phase1_kaldi(const float* sig, int fa_off, int fb_off, const flo
         v[n1] = make_float2(xa * w, xb * w);
     }
     dft20(v);
-    float2* dst = xchg + g * kGroupStride + r;
-#pragma unroll
-    for (int k1 = 0; k1 < 20; ++k1) {
-        float2 y = v[dft20_slot(k1)];
-        if (k1 > 0) y = cmul(y, twp[k1 * kTwRow]);
-        dst[k1 * kXchgRow] = y;
-    }
+    twiddle_store(v, twp, xchg + g * kGroupStride + r);
 }
 
 // phase 2 split in two so that the exchange buffer can be reused for the spectrum: load + transform ...

@@ -27,7 +27,7 @@ struct StftCfg {
     static constexpr int kSigPadded = sig_padded_size(kSigFloats) + 4;   // staged floats (hop segments padded 8 / 12)
     static constexpr size_t kSigBytes = (size_t)((kSigPadded + 3) / 4 * 4) * sizeof(float);
     static constexpr size_t kZBytes = (size_t)GROUPS * kZStride * sizeof(float2);
-    static constexpr size_t kTablesBytes = (size_t)GROUPS * kGroupStride * sizeof(float2) + kNfft * sizeof(float2) +
+    static constexpr size_t kTablesBytes = (size_t)GROUPS * kGroupStride * sizeof(float2) + kNfft * sizeof(wtab_t) +
                                            kTwTableUnits * sizeof(float2);
     // fbank kernel: the upper-spectrum buffer shares storage with the staged samples (dead after phase 1)
     static constexpr size_t kSmemBytes = (kSigBytes > kZBytes ? kSigBytes : kZBytes) + kTablesBytes;
@@ -154,7 +154,9 @@ __device__ __forceinline__ float2 frame_dc_offsets(const float* sig, int g, int 
     return make_float2(sa * f, sb * f);
 }
 
-template <int GROUPS, int MINB, bool KALDI>
+// KALDI: per-frame pre-emphasis / DC removal (table window).  HAMMING: the reference's periodic Hamming window computed
+// in registers instead of read from the shared table (only without KALDI).
+template <int GROUPS, int MINB, bool KALDI, bool HAMMING>
 __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     stft400_kernel(const float* __restrict__ wav, float* __restrict__ out, int L, int T, int tiles_per_item,
                    long total_tiles, const float* __restrict__ window, const float2* __restrict__ twiddle,
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xbuf = reinterpret_cast<float2*>(smem_raw);                 // phase 1 -> phase 2 transpose
     float2* twT = xbuf + GROUPS * kGroupStride;                         // twiddle table (see tw_thread_offset)
-    float2* wtab = twT + kTwTableUnits;                                 // window pairs (w, w), pre-scaled by 1/2
+    wtab_t* wtab = reinterpret_cast<wtab_t*>(twT + kTwTableUnits);      // window, pre-scaled by 1/2
     float* sig = reinterpret_cast<float*>(wtab + kNfft);                // padded samples of the tile
     float2* zup = xbuf;  // upper half of the spectrum: reuses the transpose buffer once phase 2 has loaded it
     __shared__ __align__(8) uint64_t bar;
@@ -171,10 +173,10 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
 
     const int g = threadIdx.x / kRadix;
     const int r = threadIdx.x - g * kRadix;
-    for (int i = threadIdx.x; i < kNfft; i += Cfg::kThreads) {
-        const float wv = 0.5f * window[i];  // exact scaling; lets phase 3 drop its multiplications
-        wtab[i] = make_float2(wv, wv);
-    }
+    float ham_c, ham_s;  // (cos, sin)(2 pi r / 400) for the table-free Hamming window
+    sincospif((float)r * (1.0f / 200.0f), &ham_s, &ham_c);
+    for (int i = threadIdx.x; i < kNfft; i += Cfg::kThreads)
+        wtab[i] = wtab_make(0.5f * window[i]);  // exact scaling; lets phase 3 drop its multiplications
     for (int e = threadIdx.x; e < kTwTableUnits; e += Cfg::kThreads) twT[e] = twiddle[tw_table_source(e)];
     const float2* twp = twT + tw_thread_offset(threadIdx.x);
     if (threadIdx.x == 0) {
@@ -229,6 +231,8 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
         if (KALDI) {
             const float2 dc = frame_dc_offsets<GROUPS>(sig, g, r, dc_part, ka);
             stft_phase1_kaldi(sig, sig_frame_off(2 * g), sig_frame_off(2 * g + 1), wtab, twp, g, r, xbuf, ka.preemph, dc);
+        } else if (HAMMING) {
+            stft_phase1_hamming(sig, sig_frame_off(2 * g), sig_frame_off(2 * g + 1), ham_c, ham_s, twp, g, r, xbuf);
         } else {
             stft_phase1_tab(sig, sig_frame_off(2 * g), sig_frame_off(2 * g + 1), wtab, twp, g, r, xbuf);
         }
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xbuf = reinterpret_cast<float2*>(smem_raw);
     float2* twT = xbuf + GROUPS * kGroupStride;
-    float2* wtab = twT + kTwTableUnits;
+    wtab_t* wtab = reinterpret_cast<wtab_t*>(twT + kTwTableUnits);
     float* sig = reinterpret_cast<float*>(wtab + kNfft);
     float2* zup = reinterpret_cast<float2*>(sig);
     float* pw = reinterpret_cast<float*>(xbuf);  // power spectra [frame][201], aliases the transpose buffer
@@ -308,10 +312,7 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
 
     const int g = threadIdx.x / kRadix;
     const int r = threadIdx.x - g * kRadix;
-    for (int i = threadIdx.x; i < kNfft; i += Cfg::kThreads) {
-        const float wv = 0.5f * window[i];
-        wtab[i] = make_float2(wv, wv);
-    }
+    for (int i = threadIdx.x; i < kNfft; i += Cfg::kThreads) wtab[i] = wtab_make(0.5f * window[i]);
     for (int e = threadIdx.x; e < kTwTableUnits; e += Cfg::kThreads) twT[e] = twiddle[tw_table_source(e)];
     for (int i = threadIdx.x; i < (int)(sizeof(MelTable) / 4); i += Cfg::kThreads)
         reinterpret_cast<int*>(&smel)[i] = reinterpret_cast<const int*>(mel)[i];
@@ -568,10 +569,10 @@ static int frame_geometry(const sd_stft_params* p, int L, FrameGeom* fg) {
 }
 static bool kaldi_conditioning(const sd_stft_params* p) { return p->preemph != 0.f || p->remove_dc_offset != 0; }
 
-template <int GROUPS, int MINB, bool KALDI>
+template <int GROUPS, int MINB, bool KALDI, bool HAMMING>
 static int launch_cfg(sd_ctx* ctx, const float* d_wav, int B, int L, int T, float* d_out, FrameGeom fg, KaldiArgs ka) {
     using Cfg = StftCfg<GROUPS>;
-    const int blocks_per_sm = kernel_setup(ctx, stft400_kernel<GROUPS, MINB, KALDI>, (int)Cfg::kSmemBytesStft,
+    const int blocks_per_sm = kernel_setup(ctx, stft400_kernel<GROUPS, MINB, KALDI, HAMMING>, (int)Cfg::kSmemBytesStft,
                                            Cfg::kThreads, Cfg::kSmemBytesStft);
     if (blocks_per_sm < 0) return SD_ERR_CUDA;
     const int tiles_per_item = (T + Cfg::kTileFrames - 1) / Cfg::kTileFrames;
@@ -579,7 +580,7 @@ static int launch_cfg(sd_ctx* ctx, const float* d_wav, int B, int L, int T, floa
     long grid = (long)ctx->num_sms * blocks_per_sm;
     if (grid > total) grid = total;
     const int aligned = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_wav) & 15) == 0);
-    stft400_kernel<GROUPS, MINB, KALDI><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytesStft, ctx->stream>>>(
+    stft400_kernel<GROUPS, MINB, KALDI, HAMMING><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytesStft, ctx->stream>>>(
         d_wav, d_out, L, T, tiles_per_item, total, ctx->d_window, reinterpret_cast<const float2*>(ctx->d_twiddle),
         aligned, fg, ka);
     SD_LAUNCH_CHECK(ctx);
@@ -601,11 +602,17 @@ int stft_launch(sd_ctx* ctx, const float* d_wav, int B, int L, const sd_stft_par
     if (T < 1) return ctx->fail(SD_ERR_INVALID, "sd_stft: %d samples give no frame in this frame_mode", L);
     if (fg.reflect && L < kNfft) return ctx->fail(SD_ERR_INVALID, "sd_stft: reflection needs at least n_fft samples");
     const KaldiArgs ka{p->preemph, p->remove_dc_offset};
+    // stft_variant (tuning hook): 0 = Hamming window in registers when the window is the reference's, 4 CTAs/SM;
+    // 1 = 3 CTAs/SM; 2 = always the window table
+    const bool hamming = p->window_kind == SD_WINDOW_HAMMING_PERIODIC && ctx->stft_variant != 2;
     if (kaldi_conditioning(p))
-        rc = launch_cfg<8, 3, true>(ctx, d_wav, B, L, T, d_out, fg, ka);
+        rc = launch_cfg<8, 3, true, false>(ctx, d_wav, B, L, T, d_out, fg, ka);
+    else if (ctx->stft_variant == 1)
+        rc = launch_cfg<8, 3, false, false>(ctx, d_wav, B, L, T, d_out, fg, ka);
+    else if (hamming)
+        rc = launch_cfg<8, 4, false, true>(ctx, d_wav, B, L, T, d_out, fg, ka);
     else
-        rc = ctx->stft_variant == 1 ? launch_cfg<8, 3, false>(ctx, d_wav, B, L, T, d_out, fg, ka)
-                                    : launch_cfg<8, 4, false>(ctx, d_wav, B, L, T, d_out, fg, ka);
+        rc = launch_cfg<8, 4, false, false>(ctx, d_wav, B, L, T, d_out, fg, ka);
     if (rc) return rc;
     if (p->pad_batch_to > B) {  // _infer: rows beyond the real batch are zeros (speakerDiarizer.cpp:1904)
         size_t row = (size_t)T * kBins * 2 * sizeof(float);

@@ -33,5 +33,9 @@ for name, N, D, k in (("cfg2", 1773, 192, 4), ("cfg3", 10773, 192, 6), ("cfg5", 
     c = ctx.debug_counters().astype(float)
     print("%s N=%d D=%d: linkage (pdist + merges) %.1f ms = %.2f us/merge; %.2f revalidations/merge, refills %d, "
           "fallbacks %d" % (name, N, D, ms, ms * 1e3 / (N - 1), c[0] / max(c[7], 1), int(c[1]), int(c[2])), flush=True)
+    m = max(c[7], 1)  # counters accumulate over the two repetitions, and so does the merge count
+    print("    cycles per merge (control warp view): decide %.0f, revalidation %.0f, sweep+fence+publish %.0f, "
+          "mbarrier wait %.0f; stage times: pdist %.2f ms, merges %.2f ms"
+          % (c[3] / m, c[4] / m, c[5] / m, c[6] / m, *ctx.linkage_stage_ms()), flush=True)
     ctx.free(d_x)
     ctx.free(d_Z)

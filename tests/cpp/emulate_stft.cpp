@@ -38,8 +38,8 @@ int main() {
     }
     // variant B (the kernel's): padded staging, shared window / twiddle tables, one exchange buffer
     std::vector<float> sigp(sig_padded_size(nsig) + 8, 0.f), out2(frames * kBins * 2, 0.f);
-    std::vector<float2> wtab(w.size());  // (w/2, w/2): the kernel folds the 1/2 of the real-pair split into the window
-    for (size_t i = 0; i < w.size(); ++i) wtab[i] = make_float2(0.5f * w[i], 0.5f * w[i]);
+    std::vector<wtab_t> wtab(w.size());  // w/2: the kernel folds the 1/2 of the real-pair split into the window
+    for (size_t i = 0; i < w.size(); ++i) wtab[i] = wtab_make(0.5f * w[i]);
     for (int j = 0; j < nsig; ++j) sigp[sig_pos(j)] = sig[j];
     std::vector<float2> twT(kTwTableUnits), xb(groups * kGroupStride);
     for (int e = 0; e < kTwTableUnits; ++e) {
@@ -94,9 +94,11 @@ int main() {
         stft_split_store<true, true>(v, zup.data(), g, t % kRadix, &out2[(2 * g) * kBins * 2], &out2[(2 * g + 1) * kBins * 2],
                                      kGroupStride);
     }
+    // the kernel's phase 1 composes fourteen of its nineteen twiddles from five table entries (twiddle_store): the
+    // two variants agree to rounding, not bit for bit
     for (size_t i = 0; i < out.size(); ++i)
-        if (out[i] != out2[i] && !(out[i] == 0.f && out2[i] == 0.f)) {
-            printf("variant mismatch at %zu\n", i);
+        if (fabs((double)out[i] - (double)out2[i]) > 2e-5) {
+            printf("variant mismatch at %zu: %g vs %g\n", i, out[i], out2[i]);
             return 2;
         }
     double maxerr = 0, maxabs = 0;
@@ -110,6 +112,7 @@ int main() {
                 im += x * sin(a);
             }
             maxerr = fmax(maxerr, fmax(fabs(re - out[(f * kBins + k) * 2]), fabs(im - out[(f * kBins + k) * 2 + 1])));
+            maxerr = fmax(maxerr, fmax(fabs(re - out2[(f * kBins + k) * 2]), fabs(im - out2[(f * kBins + k) * 2 + 1])));
             maxabs = fmax(maxabs, fmax(fabs(re), fabs(im)));
         }
     printf("max|X| %.3f  max abs err %.3e\n", maxabs, maxerr);
