@@ -91,11 +91,14 @@ __global__ void row_valid_kernel(const double* __restrict__ emb, int R, int D, u
 constexpr int PD_TILE = 64;
 constexpr int PD_KC = 16;
 
-// Dm[i][j] = sqrt(sum_k (x_ik - x_jk)^2), k ascending, mul then add, no FMA.  Full square (both triangles
-// are produced by identical arithmetic since (a-b)^2 == (b-a)^2 bit for bit).
+// Dm[i][j] = sqrt(sum_k (x_ik - x_jk)^2), k ascending, mul then add, no FMA.  The output is the full symmetric
+// square, but only the tiles on and above the diagonal are computed: (a-b)^2 == (b-a)^2 bit for bit, so a tile below
+// the diagonal would repeat the arithmetic of its mirror image -- each value is written to both places instead
+// (the mirrored stores are whole 32-byte sectors: a thread holds four consecutive rows of a column).
 __global__ void __launch_bounds__(256)
     pdist_f64_kernel(const double* __restrict__ x, int N, int D, double* __restrict__ Dm, long ld,
                      const int* __restrict__ run_flag) {
+    if (blockIdx.x < blockIdx.y) return;  // mirror image of tile (x, y)
     if (run_flag && !*run_flag) return;
     __shared__ double A[PD_KC][PD_TILE + 1];
     __shared__ double B[PD_KC][PD_TILE + 1];
@@ -133,6 +136,7 @@ __global__ void __launch_bounds__(256)
         }
         __syncthreads();
     }
+    const bool mirror = blockIdx.x != blockIdx.y;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         const int gi = bi + ty * 4 + p;
@@ -140,7 +144,11 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int gj = bj + tx * 4 + q;
-            if (gj < N) Dm[(size_t)gi * ld + gj] = __dsqrt_rn(acc[p][q]);
+            if (gj < N) {
+                const double d = __dsqrt_rn(acc[p][q]);
+                Dm[(size_t)gi * ld + gj] = d;
+                if (mirror) Dm[(size_t)gj * ld + gi] = d;
+            }
         }
     }
 }
