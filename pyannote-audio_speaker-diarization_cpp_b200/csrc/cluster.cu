@@ -1623,6 +1623,424 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
 }
 
 // ------------------------------------------------------------------------------------------------
+// linkage_wide_kernel: the heap-free merge loop spread over the whole GPU (large N)
+// ------------------------------------------------------------------------------------------------
+// One 8-CTA cluster streams a matrix that no longer fits L2 through 8 SMs: 11 us per merge at N = 10 773, 25 us at
+// N = 50 000.  Here G co-resident CTAs (one per SM, cooperative launch) share the rows, 32-row groups dealt round
+// robin, and the per-round exchange goes through a global-memory mailbox instead of DSMEM:
+//   * every round each CTA publishes one 64-byte box -- the smallest bound among its own live rows (value, row,
+//     multiplicity), that row's cached candidate (cur, nbr), its share of the recomputed row's new nearest neighbour,
+//     and, from the owner, the old state of the recomputed row -- then raises its flag (fence + store);
+//   * G threads of every CTA poll one flag each (ld.acquire.gpu) and read one box each; two block reductions later
+//     every CTA has reached the same decision, exactly as in linkage_cluster_kernel: nothing is broadcast;
+//   * a round executes ONE request: revalidate a stale candidate (every thread scans its rows of that matrix row) or
+//     merge (Lance-Williams sweep over the own rows, both D[y][z] and D[z][y] written).  The row whose bound the
+//     request recomputes (x after a rescan, the survivor y after a merge) is "pending": its owner leaves it out of the
+//     published minimum and everybody derives its new state from the partial results of the next exchange.
+// Same algorithm, same uniqueness argument and the same hand-over to the exact heap kernel on a tied minimum as the
+// other two heap-free kernels, so Z is the reference's bit for bit.  Cluster size / id replicas are private to each
+// CTA (global memory, L1-cacheable since nobody else touches them).
+// Measured (profiles/r02_cluster_sizes_wide*.log): a round costs ~7 us (flag + box round trips through L2, the
+// per-thread fences, four block barriers, the skew of 148 CTAs) and a merge needs ~3 rounds (one per revalidation):
+// 20.4 us per merge at N = 10 773, 25.5 us at N = 50 000 -- slower than the cluster kernel at the first size, level
+// at the second.  Kept as an opt-in (SD_OPT_LINKAGE_WIDE), bit-exact (tests/test_gpu_linkage_wide.py); what it
+// shows is that the round count, not the width, is what a faster large-N merge loop has to attack.
+constexpr int LW_T = 256;
+constexpr int LW_NW = LW_T / 32;
+constexpr int LW_MAX_CTAS = 160;
+
+struct __align__(16) WideBox {
+    uint4 A;  // v1 (double), i1, c1
+    uint4 B;  // cur[i1] (double), nbr[i1], -
+    uint4 C;  // partial value (double), partial row, old nbr of the pending row (owner only)
+    uint4 D;  // old lb, old cur of the pending row (owner only)
+};
+
+__host__ __device__ inline size_t linkwide_global_bytes(int n, int ctas) {
+    const size_t N32 = (size_t)(n + 31) / 32 * 32;
+    return (size_t)ctas * N32 * 8 + 2 * (size_t)ctas * sizeof(WideBox) + (size_t)LW_MAX_CTAS * LW_MAX_CTAS * 4 + 512;
+}
+
+namespace lw {
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint4 ld_cg16(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 packd(double a, int b, int c) {
+    uint4 r;
+    r.x = (unsigned)__double2loint(a);
+    r.y = (unsigned)__double2hiint(a);
+    r.z = (unsigned)b;
+    r.w = (unsigned)c;
+    return r;
+}
+__device__ __forceinline__ double lod(const uint4& v) { return __hiloint2double((int)v.y, (int)v.x); }
+__device__ __forceinline__ double hid(const uint4& v) { return __hiloint2double((int)v.w, (int)v.z); }
+}  // namespace lw
+
+__global__ void __launch_bounds__(LW_T)
+    linkage_wide_kernel(const LinkWork* __restrict__ works, const int* ns, int* __restrict__ need_exact) {
+    const LinkWork w = works[0];
+    const int n = ns[0];
+    const int G = (int)gridDim.x, cta = (int)blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    extern __shared__ __align__(16) unsigned char lw_smem[];
+    __shared__ double s_tv[LW_NW], s_pv[LW_NW];
+    __shared__ int s_ti[LW_NW], s_tc[LW_NW], s_pi[LW_NW];
+    __shared__ double s_xcur, s_plb, s_pcur;
+    __shared__ int s_xnbr, s_pnbr;
+    const bool scribe = cta == 0 && tid == 0;
+    if (scribe) need_exact[0] = 0;
+    if (n < 2) return;
+
+    const int NG = (n + 31) / 32;
+    const int NGl = NG > cta ? (NG - cta + G - 1) / G : 0;  // groups of this CTA: g = lg * G + cta
+    const int NGmax = (NG + G - 1) / G;
+    double* lb = reinterpret_cast<double*>(lw_smem);
+    double* cur = lb + (size_t)NGmax * 32;
+    int* nbr = reinterpret_cast<int*>(cur + (size_t)NGmax * 32);
+    int* alive = nbr + (size_t)NGmax * 32;
+    // global scratch: private size / id replicas, the two box arrays, the flags
+    const size_t N32 = (size_t)NG * 32;
+    int* rsize = reinterpret_cast<int*>(w.fast_scratch) + (size_t)cta * 2 * N32;
+    int* rcid = rsize + N32;
+    WideBox* boxes = reinterpret_cast<WideBox*>(reinterpret_cast<char*>(w.fast_scratch) + (size_t)G * N32 * 8);
+    int* flags = reinterpret_cast<int*>(boxes + 2 * (size_t)G);
+
+    auto row_of = [&](int lg) { return ((lg * G + cta) << 5) + lane; };
+    auto owner_cta = [&](int z) { return (z >> 5) % G; };
+    auto owner_lg = [&](int z) { return (z >> 5) / G; };
+    auto mine = [&](int z) { return z >= 0 && owner_cta(z) == cta && owner_lg(z) % LW_NW == warp && (z & 31) == lane; };
+
+    for (int lg = warp; lg < NGl; lg += LW_NW) {
+        const int z = row_of(lg), s = lg * 32 + lane;
+        nbr[s] = z < n - 1 ? w.nbr[z] : -1;
+        lb[s] = z < n - 1 ? w.lb[z] : INFINITY;
+        cur[s] = lb[s];
+        alive[s] = z < n ? 1 : 0;
+    }
+    for (int i = tid; i < (int)N32; i += LW_T) {
+        rsize[i] = i < n ? 1 : 0;
+        rcid[i] = i;
+    }
+    __syncthreads();
+
+    // smallest bound among this CTA's live heap rows, `skip` left out; result in every thread of warp 0 ... and,
+    // through shared memory, published by thread 0
+    auto local_top = [&](int skip) -> Top {
+        Top m;
+        m.v = INFINITY;
+        m.i = -1;
+        m.c = 0;
+        for (int lg = warp; lg < NGl; lg += LW_NW) {
+            const int z = row_of(lg), s = lg * 32 + lane;
+            if (z < n - 1 && z != skip && alive[s] != 0) {
+                const double v = lb[s];
+                if (m.c == 0 || v < m.v) {
+                    m.v = v;
+                    m.i = z;
+                    m.c = 1;
+                } else if (v == m.v)
+                    ++m.c;  // rows ascend within a lane: the stored row stays the lowest
+            }
+        }
+        return warp_top(m.c ? m.v : INFINITY, m.i, m.c);
+    };
+    // combine the per-warp results left in shared memory (every thread, redundantly)
+    auto combine_tops = [&]() -> Top {
+        Top t;
+        t.v = INFINITY;
+        t.i = -1;
+        t.c = 0;
+#pragma unroll
+        for (int q = 0; q < LW_NW; ++q) {
+            const int c = s_tc[q];
+            if (c == 0) continue;
+            const double v = s_tv[q];
+            const int i = s_ti[q];
+            if (t.c == 0 || v < t.v) {
+                t.v = v;
+                t.i = i;
+                t.c = c;
+            } else if (v == t.v) {
+                t.c += c;
+                t.i = i < t.i ? i : t.i;
+            }
+        }
+        return t;
+    };
+    auto combine_parts = [&](double& pv, int& pi) {
+        pv = INFINITY;
+        pi = -1;
+#pragma unroll
+        for (int q = 0; q < LW_NW; ++q) {
+            const int i = s_pi[q];
+            if (i < 0) continue;
+            const double v = s_pv[q];
+            if (pi < 0 || v < pv || (v == pv && i < pi)) {
+                pv = v;
+                pi = i;
+            }
+        }
+    };
+    // publish this CTA's box of round `round` (thread 0, after a block barrier that follows every thread's fence)
+    auto publish = [&](int round, const Top& t, double pv, int pi, int pend) {
+        WideBox* b = boxes + (size_t)(round & 1) * G + cta;
+        double t_cur = 0.0;
+        int t_nbr = -1;
+        if (t.i >= 0) {
+            const int s = owner_lg(t.i) * 32 + (t.i & 31);
+            t_cur = cur[s];
+            t_nbr = nbr[s];
+        }
+        double q_lb = 0.0, q_cur = 0.0;
+        int q_nbr = -1;
+        if (pend >= 0 && owner_cta(pend) == cta) {
+            const int s = owner_lg(pend) * 32 + (pend & 31);
+            q_lb = lb[s];
+            q_cur = cur[s];
+            q_nbr = nbr[s];
+        }
+        b->A = lw::packd(t.v, t.i, t.c);
+        b->B = lw::packd(t_cur, t_nbr, 0);
+        b->C = lw::packd(pv, pi, q_nbr);
+        uint4 d;
+        d.x = (unsigned)__double2loint(q_lb);
+        d.y = (unsigned)__double2hiint(q_lb);
+        d.z = (unsigned)__double2loint(q_cur);
+        d.w = (unsigned)__double2hiint(q_cur);
+        b->D = d;
+        __threadfence();  // the box is visible before any of the flags that the other threads raise after the barrier
+    };
+    // every reader polls its own copy of the flags (flags[reader][writer]): one hot line per reader instead of five
+    // lines polled by all G * G threads of the grid
+    auto raise_flags = [&](int round) {
+        if (tid < G) lw::st_release(flags + (size_t)tid * G + cta, round);
+    };
+
+    int round = 1;
+    int pending = -1;       // row whose bound the previous request recomputed
+    bool pend_merge = false;  // it was a merge (the survivor keeps its old state when no partial exists)
+    {
+        const Top wt = local_top(-1);
+        if (lane == 0) {
+            s_tv[warp] = wt.v;
+            s_ti[warp] = wt.i;
+            s_tc[warp] = wt.c;
+        }
+        __syncthreads();
+        if (tid == 0) publish(round, combine_tops(), INFINITY, -1, -1);
+        __syncthreads();
+        raise_flags(round);
+    }
+    int k = 0, tries = 0;
+    unsigned long long rescans = 0;
+    for (;;) {
+        // ---------------- exchange: wait for every CTA's box of this round, reduce ----------------
+        Top bt;
+        bt.v = INFINITY;
+        bt.i = -1;
+        bt.c = 0;
+        double bpv = INFINITY;
+        int bpi = -1;
+        uint4 bB = make_uint4(0, 0, 0, 0), bC = bB, bD = bB;
+        if (tid < G) {
+            while (lw::ld_acquire(flags + (size_t)cta * G + tid) < round) {
+            }
+            const WideBox* b = boxes + (size_t)(round & 1) * G + tid;
+            const uint4 a = lw::ld_cg16(&b->A);
+            bB = lw::ld_cg16(&b->B);
+            bC = lw::ld_cg16(&b->C);
+            bD = lw::ld_cg16(&b->D);
+            bt.v = lw::lod(a);
+            bt.i = (int)a.z;
+            bt.c = (int)a.w;
+            if (bt.c == 0) {
+                bt.v = INFINITY;
+                bt.i = -1;
+            }
+            bpi = (int)bC.z;
+            bpv = bpi >= 0 ? lw::lod(bC) : INFINITY;
+        }
+        {
+            const Top wt = warp_top(bt.c ? bt.v : INFINITY, bt.i, bt.c);
+            const Top wp = warp_top(bpi >= 0 ? bpv : INFINITY, bpi, bpi >= 0 ? 1 : 0);
+            if (lane == 0) {
+                s_tv[warp] = wt.v;
+                s_ti[warp] = wt.i;
+                s_tc[warp] = wt.c;
+                s_pv[warp] = wp.v;
+                s_pi[warp] = wp.i;
+            }
+        }
+        if (pending >= 0 && tid == owner_cta(pending)) {  // the owner's box carries the pending row's old state
+            s_plb = lw::lod(bD);
+            s_pcur = lw::hid(bD);
+            s_pnbr = (int)bC.w;
+        }
+        __syncthreads();  // S1
+        Top top = combine_tops();
+        double pv;
+        int pi;
+        combine_parts(pv, pi);
+        // new state of the pending row (clustering.cpp:395-404 after a merge, 259-276 after a rescan)
+        double p_lb = INFINITY, p_cur = INFINITY;
+        int p_nbr = -1;
+        bool p_cand = false;
+        if (pending >= 0) {
+            if (pi >= 0) {
+                p_lb = pv;
+                p_cur = pv;
+                p_nbr = pi;
+            } else if (pend_merge) {
+                p_lb = s_plb;
+                p_cur = s_pcur;
+                p_nbr = s_pnbr;
+            }
+            if (mine(pending)) {
+                const int s = owner_lg(pending) * 32 + lane;
+                lb[s] = p_lb;
+                cur[s] = p_cur;
+                nbr[s] = p_nbr;
+            }
+            p_cand = pending < n - 1;
+            if (p_cand) {  // it was left out of its owner's published minimum
+                if (top.c == 0 || p_lb < top.v) {
+                    top.v = p_lb;
+                    top.i = pending;
+                    top.c = 1;
+                } else if (p_lb == top.v) {
+                    top.c += 1;
+                    top.i = pending < top.i ? pending : top.i;
+                }
+            }
+        }
+        if (k >= n - 1) break;
+        const int x = top.i;
+        const double dist = top.v;
+        if (top.c != 1 || x < 0 || tries >= n - k) {  // tied minimum: the heap order would matter
+            if (scribe) need_exact[0] = 1;
+            break;
+        }
+        // cached candidate of row x: from the pending state or from the box that published x
+        if (x != pending && tid < G && bt.c > 0 && bt.i == x) {
+            s_xcur = lw::lod(bB);
+            s_xnbr = (int)bB.z;
+        }
+        __syncthreads();  // S2 (also: every thread has consumed s_tv.. before the request reuses them)
+        const double x_cur = x == pending ? p_cur : s_xcur;
+        const int y = x == pending ? p_nbr : s_xnbr;
+        const bool valid = y >= 0 && dist == x_cur;  // clustering.cpp:329
+        ++round;
+        double part_v = INFINITY;
+        int part_i = -1;
+        if (!valid) {
+            // ---------------- revalidate: find_min_dist(x) over live i > x ----------------
+            const double* r = w.D + (size_t)x * w.ld;
+            for (int lg = warp; lg < NGl; lg += LW_NW) {
+                const int i = row_of(lg);
+                if (i > x && i < n && alive[lg * 32 + lane] != 0) {
+                    const double d = __ldcg(r + i);
+                    if (d < part_v) {  // rows ascend within a lane: first minimum in index order
+                        part_v = d;
+                        part_i = i;
+                    }
+                }
+            }
+            pending = x;
+            pend_merge = false;
+            ++tries;
+            ++rescans;
+        } else {
+            // ---------------- merge x into y (clustering.cpp:347-404) ----------------
+            const int nx = rsize[x], ny = rsize[y], ix = rcid[x], iy = rcid[y];
+            if (scribe) {
+                double* z = w.Z + 4 * (size_t)k;
+                z[0] = ix < iy ? ix : iy;
+                z[1] = ix < iy ? iy : ix;
+                z[2] = dist;
+                z[3] = nx + ny;
+            }
+            const double* rowx = w.D + (size_t)x * w.ld;
+            double* rowy = w.D + (size_t)y * w.ld;
+            const double fx = (double)nx, fy = (double)ny, fs = (double)(nx + ny);
+            const double t3 = __ddiv_rn(__dmul_rn(__dmul_rn((double)(nx * ny), dist), dist), fs);
+            const double rs = __drcp_rn(fs);
+            for (int lg = warp; lg < NGl; lg += LW_NW) {
+                const int z = row_of(lg), s = lg * 32 + lane;
+                if (z == x) alive[s] = 0;
+                if (z < n && z != x && z != y && alive[s] != 0) {
+                    const double dx = __ldcg(rowx + z), dy = __ldcg(rowy + z);
+                    const double t1q = __dmul_rn(__dmul_rn(fx, dx), dx);
+                    const double t2q = __dmul_rn(__dmul_rn(fy, dy), dy);
+                    const double nd = __dsqrt_rn(div_by(__dsub_rn(__dadd_rn(t1q, t2q), t3), fs, rs));
+                    __stcg(rowy + z, nd);
+                    __stcg(w.D + (size_t)z * w.ld + y, nd);
+                    if (z < y) {
+                        int nb = nbr[s];
+                        const double lbz = lb[s];
+                        if (z < x && nb == x) nb = y;  // clustering.cpp:374-378
+                        if (nd < lbz) {                // clustering.cpp:381-392
+                            nb = y;
+                            lb[s] = nd;
+                        }
+                        if (nb == y) cur[s] = nd;  // cur mirrors D[z][nbr[z]]
+                        nbr[s] = nb;
+                    } else if (nd < part_v) {  // rows ascend within a lane: first strict minimum
+                        part_v = nd;
+                        part_i = z;
+                    }
+                }
+            }
+            if (tid == 0) {  // private replicas follow the merge
+                rsize[x] = 0;
+                rsize[y] = nx + ny;
+                rcid[y] = n + k;
+            }
+            pending = y;
+            pend_merge = true;
+            ++k;
+            tries = 0;
+            __threadfence();  // this thread's matrix stores are visible device-wide before the CTA's flag goes up
+        }
+        // ---------------- publish: own minimum without the pending row, own share of its new neighbour ----------
+        {
+            const Top wt = local_top(pending);
+            const Top wp = warp_top(part_i >= 0 ? part_v : INFINITY, part_i, part_i >= 0 ? 1 : 0);
+            if (lane == 0) {
+                s_tv[warp] = wt.v;
+                s_ti[warp] = wt.i;
+                s_tc[warp] = wt.c;
+                s_pv[warp] = wp.v;
+                s_pi[warp] = wp.i;
+            }
+        }
+        __syncthreads();  // S3
+        if (tid == 0) {
+            double pv2;
+            int pi2;
+            combine_parts(pv2, pi2);
+            publish(round, combine_tops(), pv2, pi2, pending);
+        }
+        __syncthreads();  // S4: the box is out and fenced; shared scratch is free again
+        raise_flags(round);
+    }
+    if (scribe && w.stats) {
+        w.stats[0] += rescans;
+        w.stats[7] += (unsigned long long)(n - 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // fcluster (criterion "distance")
 // ------------------------------------------------------------------------------------------------
 
@@ -2221,7 +2639,8 @@ static LinkLayout link_layout(int N) {
     L.off_n = o;
     o += 256;
     L.off_fast = o;
-    o += align_up(std::max(linkfast_smem_bytes(N), linkcluster_global_bytes(N)), 256);
+    o += align_up(std::max(std::max(linkfast_smem_bytes(N), linkcluster_global_bytes(N)),
+                           linkwide_global_bytes(N, LW_MAX_CTAS)), 256);
     L.total = o;
     return L;
 }
@@ -2293,8 +2712,31 @@ static int linkage_cluster_launch(sd_ctx* ctx, const LinkWork* d_works, const in
     return SD_OK;
 }
 
+// The whole-GPU merge loop: G = one CTA per SM, cooperative launch (all CTAs must be co-resident: they wait for each
+// other's flags).  `fast_scratch` = base of the problem's scratch area (replicas, boxes, flags).
+static int linkage_wide_launch(sd_ctx* ctx, const LinkWork* d_works, const int* d_ns, int max_n, int* d_need_exact,
+                               char* fast_scratch) {
+    const int G = std::min(ctx->num_sms, LW_MAX_CTAS);
+    const size_t N32 = (size_t)(max_n + 31) / 32 * 32;
+    const size_t ngmax = (N32 / 32 + G - 1) / G;
+    const size_t smem = ngmax * 32 * (8 + 8 + 4 + 4) + 64;
+    if (kernel_setup(ctx, linkage_wide_kernel, (int)std::max(smem, (size_t)48 * 1024)) < 0) return SD_ERR_CUDA;
+    int* d_flags = reinterpret_cast<int*>(fast_scratch + (size_t)G * N32 * 8 + 2 * (size_t)G * sizeof(WideBox));
+    SD_CUDA(ctx, cudaMemsetAsync(d_flags, 0, (size_t)G * G * sizeof(int), ctx->stream));
+    void* args[] = {(void*)&d_works, (void*)&d_ns, (void*)&d_need_exact};
+    SD_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)linkage_wide_kernel, dim3((unsigned)G), dim3(LW_T), args, smem,
+                                             ctx->stream));
+    ctx->launches++;
+    return SD_OK;
+}
+
 static int linkage_fast_dispatch(sd_ctx* ctx, const LinkWork* d_works, const int* d_ns, int problems, int max_n,
-                                 int* d_need_exact) {
+                                 int* d_need_exact, char* fast_scratch) {
+    // Opt-in (SD_OPT_LINKAGE_WIDE): measured 20.4 us per merge at N = 10 773 and 25.5 us at N = 50 000 against 11.4 /
+    // 26.5 us for the cluster kernel -- a round through the global-memory mailbox costs ~7 us and a merge needs ~3 of
+    // them, so it only breaks even at the largest size
+    if (problems == 1 && fast_scratch && (ctx->linkage_wide == 2 || (ctx->linkage_wide == 1 && max_n >= 32768)))
+        return linkage_wide_launch(ctx, d_works, d_ns, max_n, d_need_exact, fast_scratch);
     constexpr size_t kClusterSmem = (size_t)180 * 1024;
     if (ctx->linkage_cluster && linkcluster_smem_bytes(max_n, false) <= kClusterSmem) {
         const int t = ctx->linkage_threads ? ctx->linkage_threads : (max_n <= 4096 ? 128 : 256);
@@ -2341,7 +2783,7 @@ static int linkage_on_square(sd_ctx* ctx, char* base, const LinkLayout& L, const
     rowmin_init_kernel<<<rm_grid, 256, 0, ctx->stream>>>(w, N, nullptr);
     SD_LAUNCH_CHECK(ctx);
     if (!ctx->force_exact_linkage) {
-        rc = linkage_fast_dispatch(ctx, d_work, d_n, 1, N, d_need_exact);
+        rc = linkage_fast_dispatch(ctx, d_work, d_n, 1, N, d_need_exact, base + L.off_fast);
         if (rc) return rc;
         // exact chain, skipped on the device unless the fast kernel met a tied minimum
         dim3 grid((N + PD_TILE - 1) / PD_TILE, (N + PD_TILE - 1) / PD_TILE);
