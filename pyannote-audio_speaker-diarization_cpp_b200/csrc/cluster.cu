@@ -1077,11 +1077,15 @@ struct __align__(16) ClusterXch {
 // revalidation costs one L2 round trip and one block barrier instead of a DSMEM round.  To keep deciding after
 // a row of some warp has been revalidated, every warp also publishes the value of its second smallest bound:
 // as long as the running minimum stays strictly below it, the rows that warp did not publish cannot matter.
-template <int T, bool GREPL>
+// PRE (used from 512 threads per CTA on): the warps of a CTA first reduce their entries through shared memory (one
+// block barrier) and warp 0 publishes ONE entry per CTA, so that the exchange and the redundant decide work on 8
+// entries whatever the thread count is -- that is what lets large problems use 512 threads per CTA (fewer sequential
+// load rounds per thread in the sweep and the rescans) without the decide growing with the number of warps.
+template <int T, bool GREPL, bool PRE>
 __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
     linkage_cluster_kernel(const LinkWork* __restrict__ works, const int* ns, int* __restrict__ need_exact) {
     constexpr int NW = T / 32;
-    constexpr int E = kLcCtas * NW;
+    constexpr int E = PRE ? kLcCtas : kLcCtas * NW;
     constexpr int EPL = (E + 31) / 32;  // exchange entries per lane
     constexpr int PF = 4;               // sweep / rescan groups in flight per warp
     constexpr int LOOSE = 4;            // rows revalidated since the last exchange that every warp tracks
@@ -1095,6 +1099,11 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
     __shared__ ClusterXch<E> xch[2];
     __shared__ __align__(16) uint4 rx[2][E];  // revalidation exchange: (partial value, partial row) per warp
     __shared__ __align__(8) unsigned long long mbar[2], rbar[2];
+    // PRE: per-warp entries of this CTA, combined by warp 0 before they leave the CTA
+    constexpr int PW = PRE ? NW : 1;
+    __shared__ double pre_v[PW], pre_v2[PW], pre_cur[PW], pre_pv[PW], prx_v[PW];
+    __shared__ int pre_i[PW], pre_c[PW], pre_nbr[PW], pre_pi[PW], prx_i[PW];
+    __shared__ __align__(16) uint4 pre_pend[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool scribe = rank == 0 && tid == 0;  // writes Z / flags / counters
     if (scribe) need_exact[prob] = 0;
@@ -1139,17 +1148,17 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
         const uint4* base = piece == 0 ? xch[b].A : piece == 1 ? xch[b].B : piece == 2 ? xch[b].C : xch[b].D;
-        dst_piece[b] = lc::mapa(lc::smem_u32(base + (rank * NW + warp)), dst_rank);
+        dst_piece[b] = lc::mapa(lc::smem_u32(base + (PRE ? rank : rank * NW + warp)), dst_rank);
         dst_pend[b] = lc::mapa(lc::smem_u32(&xch[b].P[piece & 1]), dst_rank);
         dst_bar[b] = lc::mapa(bar_local[b], dst_rank);
-        dst_rx[b] = lc::mapa(lc::smem_u32(&rx[b][rank * NW + warp]), dst_rank);
+        dst_rx[b] = lc::mapa(lc::smem_u32(&rx[b][PRE ? rank : rank * NW + warp]), dst_rank);
         dst_rbar[b] = lc::mapa(rbar_local[b], dst_rank);
     }
 
     auto row_of = [&](int lg) { return ((lg * kLcCtas + rank) << 5) + lane; };
     auto owner_rank = [&](int z) { return (z >> 5) % kLcCtas; };
     auto owner_lg = [&](int z) { return (z >> 5) / kLcCtas; };
-    auto entry_of = [&](int z) { return owner_rank(z) * NW + owner_lg(z) % NW; };
+    auto entry_of = [&](int z) { return PRE ? owner_rank(z) : owner_rank(z) * NW + owner_lg(z) % NW; };
     auto mine = [&](int z) { return z >= 0 && owner_rank(z) == rank && owner_lg(z) % NW == warp && (z & 31) == lane; };
 
     for (int lg = warp; lg < NGl; lg += NW) {
@@ -1211,9 +1220,67 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
             d_cur = __shfl_sync(0xffffffffu, me ? cur[s] : 0.0, src);
             d_nbr = __shfl_sync(0xffffffffu, me ? nbr[s] : 0, src);
         }
+        const bool own_pend = pend >= 0 ? (owner_rank(pend) == rank && owner_lg(pend) % NW == warp) : false;
+        uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+        if (own_pend) {
+            const int src = pend & 31, s = owner_lg(pend) * 32 + src;
+            const bool me = lane == src;
+            const double q_lb = __shfl_sync(0xffffffffu, me ? lb[s] : 0.0, src);
+            const double q_cur = __shfl_sync(0xffffffffu, me ? cur[s] : 0.0, src);
+            q0.x = (unsigned)__double2loint(q_lb);
+            q0.y = (unsigned)__double2hiint(q_lb);
+            q0.z = (unsigned)__double2loint(q_cur);
+            q0.w = (unsigned)__double2hiint(q_cur);
+            q1.x = (unsigned)__shfl_sync(0xffffffffu, me ? nbr[s] : 0, src);
+        }
+        Top pt = t;
+        bool send_pend = own_pend || (pend < 0 && dummy_pend);
+        if (PRE) {
+            // per-warp entries -> shared memory -> warp 0 combines them into the CTA's one entry
+            if (lane == 0) {
+                pre_v[warp] = t.v;
+                pre_i[warp] = t.i;
+                pre_c[warp] = t.c;
+                pre_cur[warp] = d_cur;
+                pre_nbr[warp] = d_nbr;
+                pre_v2[warp] = v2;
+                pre_pv[warp] = pv;
+                pre_pi[warp] = pi;
+                if (own_pend) {
+                    pre_pend[0] = q0;
+                    pre_pend[1] = q1;
+                }
+            }
+            __syncthreads();
+            if (warp != 0) return;
+            const bool has = lane < NW;
+            const double ev = has && pre_c[lane] > 0 ? pre_v[lane] : INFINITY;
+            pt = warp_top(ev, has ? pre_i[lane] : -1, has ? pre_c[lane] : 0);
+            // second smallest bound of the CTA: the winner's own second, everybody else's first
+            const bool winner = has && pre_c[lane] > 0 && pre_i[lane] == pt.i;
+            v2 = warp_top(has ? (winner ? pre_v2[lane] : ev) : INFINITY, 0, 1).v;
+            const unsigned wb = __ballot_sync(0xffffffffu, winner);
+            const int wsrc = wb ? __ffs(wb) - 1 : 0;
+            d_cur = __shfl_sync(0xffffffffu, has ? pre_cur[lane] : 0.0, wsrc);
+            d_nbr = __shfl_sync(0xffffffffu, has ? pre_nbr[lane] : -1, wsrc);
+            if (!wb) {
+                d_cur = 0.0;
+                d_nbr = -1;
+            }
+            const int ppi = has ? pre_pi[lane] : -1;
+            const Top pp = warp_top(ppi >= 0 ? pre_pv[lane] : INFINITY, ppi, ppi >= 0 ? 1 : 0);
+            pv = pp.i >= 0 ? pp.v : INFINITY;
+            pi = pp.i;
+            if (pend >= 0) {
+                send_pend = owner_rank(pend) == rank;
+                q0 = pre_pend[0];
+                q1 = pre_pend[1];
+            } else
+                send_pend = dummy_pend;
+        }
         uint4 v;
         if (piece == 0)
-            v = lc::pack(t.v, t.i, t.c);
+            v = lc::pack(pt.v, pt.i, pt.c);
         else if (piece == 1)
             v = lc::pack(d_cur, d_nbr, 0);
         else if (piece == 2)
@@ -1221,22 +1288,7 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
         else
             v = lc::pack(pv, pi, 0);
         lc::st_async16(dst_piece[b], dst_bar[b], v);
-        const bool own_pend = pend >= 0 ? (owner_rank(pend) == rank && owner_lg(pend) % NW == warp) : dummy_pend;
-        if (own_pend) {
-            uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
-            if (pend >= 0) {
-                const int src = pend & 31, s = owner_lg(pend) * 32 + src;
-                const bool me = lane == src;
-                const double q_lb = __shfl_sync(0xffffffffu, me ? lb[s] : 0.0, src);
-                const double q_cur = __shfl_sync(0xffffffffu, me ? cur[s] : 0.0, src);
-                q0.x = (unsigned)__double2loint(q_lb);
-                q0.y = (unsigned)__double2hiint(q_lb);
-                q0.z = (unsigned)__double2loint(q_cur);
-                q0.w = (unsigned)__double2hiint(q_cur);
-                q1.x = (unsigned)__shfl_sync(0xffffffffu, me ? nbr[s] : 0, src);
-            }
-            if (piece < 2) lc::st_async16(dst_pend[b], dst_bar[b], piece == 0 ? q0 : q1);
-        }
+        if (send_pend && piece < 2) lc::st_async16(dst_pend[b], dst_bar[b], piece == 0 ? q0 : q1);
     };
 
     int par = 0;
@@ -1440,8 +1492,22 @@ __global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
                             bi = row_of(lg0 + u * NW);
                         }
                 }
-                const Top part = warp_top(bi >= 0 ? bv : INFINITY, bi, bi >= 0 ? 1 : 0);
-                if (lane < kLcCtas) lc::st_async16(dst_rx[rpar], dst_rbar[rpar], lc::pack(part.i >= 0 ? part.v : INFINITY, part.i, 0));
+                Top part = warp_top(bi >= 0 ? bv : INFINITY, bi, bi >= 0 ? 1 : 0);
+                bool sender = true;
+                if (PRE) {  // one partial per CTA
+                    if (lane == 0) {
+                        prx_v[warp] = part.v;
+                        prx_i[warp] = part.i;
+                    }
+                    __syncthreads();
+                    sender = warp == 0;
+                    if (sender) {
+                        const int qi_ = lane < NW ? prx_i[lane] : -1;
+                        part = warp_top(qi_ >= 0 ? prx_v[lane] : INFINITY, qi_, qi_ >= 0 ? 1 : 0);
+                    }
+                }
+                if (sender && lane < kLcCtas)
+                    lc::st_async16(dst_rx[rpar], dst_rbar[rpar], lc::pack(part.i >= 0 ? part.v : INFINITY, part.i, 0));
                 lc::mbar_wait(rbar_local[rpar], rphase[rpar] & 1u);
                 ++rphase[rpar];
                 if (tid == 0) lc::mbar_expect_tx(rbar_local[rpar], kRxBytes);  // re-arm for the revalidation after next
@@ -2702,12 +2768,12 @@ static int linkage_fast_launch_mode(sd_ctx* ctx, const LinkWork* d_works, const 
     return SD_OK;
 }
 
-template <int T, bool GREPL>
+template <int T, bool GREPL, bool PRE>
 static int linkage_cluster_launch(sd_ctx* ctx, const LinkWork* d_works, const int* d_ns, int problems, int max_n,
                                   int* d_need_exact) {
     const size_t smem = linkcluster_smem_bytes(max_n, GREPL);
-    if (kernel_setup(ctx, linkage_cluster_kernel<T, GREPL>, 200 * 1024) < 0) return SD_ERR_CUDA;
-    linkage_cluster_kernel<T, GREPL><<<problems * kLcCtas, T, smem, ctx->stream>>>(d_works, d_ns, d_need_exact);
+    if (kernel_setup(ctx, linkage_cluster_kernel<T, GREPL, PRE>, 200 * 1024) < 0) return SD_ERR_CUDA;
+    linkage_cluster_kernel<T, GREPL, PRE><<<problems * kLcCtas, T, smem, ctx->stream>>>(d_works, d_ns, d_need_exact);
     SD_LAUNCH_CHECK(ctx);
     return SD_OK;
 }
@@ -2739,13 +2805,18 @@ static int linkage_fast_dispatch(sd_ctx* ctx, const LinkWork* d_works, const int
         return linkage_wide_launch(ctx, d_works, d_ns, max_n, d_need_exact, fast_scratch);
     constexpr size_t kClusterSmem = (size_t)180 * 1024;
     if (ctx->linkage_cluster && linkcluster_smem_bytes(max_n, false) <= kClusterSmem) {
-        const int t = ctx->linkage_threads ? ctx->linkage_threads : (max_n <= 4096 ? 128 : 256);
-        if (t <= 128) return linkage_cluster_launch<128, false>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
-        if (t <= 256) return linkage_cluster_launch<256, false>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
-        return linkage_cluster_launch<512, false>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
+        // SD_OPT_LINKAGE_THREADS: 128 / 256 = one exchange entry per warp, 512 = pre-reduced to one entry per CTA,
+        // 1024 = 512 threads with one entry per warp (the round-1 form, kept for comparison)
+        const int t = ctx->linkage_threads ? ctx->linkage_threads : (max_n <= 4096 ? 128 : 512);
+        if (t <= 128) return linkage_cluster_launch<128, false, false>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
+        if (t <= 256) return linkage_cluster_launch<256, false, false>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
+        if (t <= 512) return linkage_cluster_launch<512, false, true>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
+        return linkage_cluster_launch<512, false, false>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
     }
     if (ctx->linkage_cluster && linkcluster_smem_bytes(max_n, true) <= kClusterSmem)  // replicas in global memory
-        return linkage_cluster_launch<512, true>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
+        return ctx->linkage_threads == 1024
+                   ? linkage_cluster_launch<512, true, false>(ctx, d_works, d_ns, problems, max_n, d_need_exact)
+                   : linkage_cluster_launch<512, true, true>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
     const bool fits = linkfast_smem_bytes(max_n) <= (size_t)220 * 1024;
     const int threads = ctx->linkage_threads ? ctx->linkage_threads : (max_n <= 4096 ? 512 : 1024);
     if (fits && threads == 512) return linkage_fast_launch_mode<LF_SMEM, 512>(ctx, d_works, d_ns, problems, max_n, d_need_exact);
