@@ -310,7 +310,8 @@ int sd_crop_chunks_dev(sd_ctx* ctx, const float* d_wave, int64_t num_samples, co
  * scratch) driven by a library-owned host thread that runs the per-file sequence of speakerDiarization()
  * (SD:2937-3234) over the hot path: STFT of the C*S embedding items -> binarize -> speaker_count -> clustering (with
  * the inactive-speaker mask) -> skip-average aggregate of the diarization scores.  A stage runs when both its input
- * and its output pointer are set.  One thread submits; file i of a batch runs on worker i % workers, in order.
+ * and its output pointer are set (so one long file can be split by chunk range: STFT + binarize per range, then one
+ * sd_file with `binarized` as an input for the stages that need every chunk; shard.split_chunk_range).  One thread submits; file i of a batch runs on worker i % workers, in order.
  * Pointers are HOST (pinned recommended; H2D/D2H inside, overlapped across the files in flight) or DEVICE.
  * Multi-GPU: one sd_batch per GPU (one process per GPU, or one batch per device in a process); files are assigned
  * to GPUs by the caller (shard.assign_files: longest-processing-time first). */

@@ -64,7 +64,7 @@ int run_file(sd_batch* b, sd_ctx* ctx, sd_file* f, int pointers) {
                    : sd_speaker_count(ctx, f->binarized, f->C, f->F, f->S, &f->chunks, &f->frames, f->count, f->count_cap,
                                       &f->n_count, &f->count_frames));
     if (f->embeddings && f->hard) {
-        const double* bin = f->segmentations && f->binarized ? f->binarized : nullptr;
+        const double* bin = f->binarized;  // computed above or supplied by the caller (chunk-range splits); may be NULL
         SD_TRY(dev ? sd_clustering_dev(ctx, f->embeddings, f->C, f->S, f->D, &b->cp, bin, f->F, f->hard, nullptr, 0,
                                        &f->num_clusters)
                    : sd_clustering(ctx, f->embeddings, f->C, f->S, f->D, &b->cp, bin, f->F, f->hard, nullptr, 0,

@@ -52,3 +52,19 @@ def gather_results(local_packed, max_files_per_rank, device="cpu"):
             if row[0] >= 0:
                 res[int(row[0])] = row[2:2 + int(row[1])].copy()
     return res
+
+
+def split_chunk_range(num_chunks, parts):
+    """Chunk-range split of ONE long file (the per-chunk loops of speakerDiarization(),
+    speakerDiarizer.cpp:3047-3105, have no dependence between chunks): contiguous ranges [c0, c1) of nearly equal size.
+    The STFT items and the binarize rows of a range are independent of the other ranges, so each range can be
+    submitted as its own sd_file (STFT + binarize stages only) on any GPU; speaker_count / clustering / the
+    diarization aggregate need every chunk and stay on one GPU (they are the cheap or the sequential stages)."""
+    parts = max(1, min(int(parts), int(num_chunks)))
+    base, extra = divmod(int(num_chunks), parts)
+    out, c0 = [], 0
+    for p in range(parts):
+        c1 = c0 + base + (1 if p < extra else 0)
+        out.append((c0, c1))
+        c0 = c1
+    return out

@@ -47,6 +47,15 @@ def test_assign_files_balanced():
     assert shard.assign_files([5.0], 3) == [[0], [], []]
 
 
+def test_split_chunk_range():
+    shard = _load_shard()
+    assert shard.split_chunk_range(10, 3) == [(0, 4), (4, 7), (7, 10)]
+    assert shard.split_chunk_range(3591, 8)[-1][1] == 3591 and len(shard.split_chunk_range(3591, 8)) == 8
+    assert shard.split_chunk_range(2, 8) == [(0, 1), (1, 2)]
+    r = shard.split_chunk_range(591, 4)
+    assert all(a[1] == b[0] for a, b in zip(r, r[1:])) and max(c1 - c0 for c0, c1 in r) - min(c1 - c0 for c0, c1 in r) <= 1
+
+
 def test_gather_world_size_2(tmp_path):
     durations = [300.0, 120.0, 600.0, 60.0, 300.0]
     port = 29500 + (os.getpid() % 2000)

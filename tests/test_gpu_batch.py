@@ -115,3 +115,38 @@ def test_batch_reports_the_failing_file(pkg, synth):
         b.run((pkg.SdFile * 1)(files[1]))  # the batch stays usable
     finally:
         b.close()
+
+
+def test_one_long_file_split_by_chunk_range(pkg, synth, oracle):
+    """inside one long file the STFT items and binarize rows of a chunk range are independent, so the
+    range can run as its own sd_file (here three ranges on three workers; on a multi-GPU box: on three GPUs), while
+    count / clustering / aggregate run once over all chunks.  Results equal the unsplit file's."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("sdb200_shard", os.path.join(os.path.dirname(pkg.__file__), "shard.py"))
+    shard = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(shard)
+    x = make_inputs(synth, 55, 41)
+    want = expected(oracle, x)
+    f_all, out = host_file(pkg, x)
+    ranges = shard.split_chunk_range(x["C"], 3)
+    assert ranges == [(0, 14), (14, 28), (28, 41)]
+    parts = []
+    S, L, F = x["S"], x["L"], x["F"]
+    for c0, c1 in ranges:
+        parts.append(pkg.make_file(c1 - c0, F, S, L, x["D"], x["chunks"], wav_items=x["wav"][c0 * S:c1 * S],
+                                   segmentations=x["seg"][c0:c1], stft=out["stft"][c0 * S:c1 * S],
+                                   binarized=out["binarized"][c0:c1]))
+    b = pkg.Batch(0, 3)
+    try:
+        b.run((pkg.SdFile * 3)(*parts))  # front-end stages, range by range
+        assert np.abs(out["stft"] - want["stft"]).max() < 1e-4 and np.array_equal(out["binarized"], want["binarized"])
+        rest = pkg.make_file(x["C"], F, S, L, x["D"], x["chunks"], Kd=x["Kd"], embeddings=x["emb"], diar_scores=x["diar"],
+                             binarized=out["binarized"], count=out["count"], count_cap=out["count"].size,
+                             hard=out["hard"], diar=out["diar"])
+        arr = (pkg.SdFile * 1)(rest)
+        b.run(arr)  # the stages that need every chunk
+        assert arr[0].n_count == want["count"].size and np.array_equal(out["count"][:arr[0].n_count], want["count"])
+        assert np.array_equal(out["hard"], want["hard"]) and np.array_equal(out["diar"], want["diar"])
+    finally:
+        b.close()
