@@ -289,6 +289,10 @@ int sd_ctx_set_option(sd_ctx* ctx, int option, int value) {
         case SD_OPT_LINKAGE_CLUSTER:
             ctx->linkage_cluster = value != 0;
             return SD_OK;
+        case SD_OPT_STFT_WAVES:
+            if (value < 1 || value > 64) return ctx->fail(SD_ERR_INVALID, "SD_OPT_STFT_WAVES must be 1..64");
+            ctx->stft_waves = value;
+            return SD_OK;
         case SD_OPT_LINKAGE_WIDE:
             if (value < 0 || value > 2) return ctx->fail(SD_ERR_INVALID, "SD_OPT_LINKAGE_WIDE must be 0, 1 or 2");
             ctx->linkage_wide = value;

@@ -132,6 +132,20 @@ int sd_batch_create(int device, int workers, sd_batch** out) {
             return rc;  // no device: no CPU fallback
         }
     }
+    // experiment hooks: SDB_BATCH_OPTS="option=value,..." is applied to every worker context (sd_ctx_set_option)
+    if (const char* opts = std::getenv("SDB_BATCH_OPTS")) {
+        std::string s(opts);
+        size_t pos = 0;
+        while (pos < s.size()) {
+            const size_t comma = s.find(',', pos), eq = s.find('=', pos);
+            const size_t end = comma == std::string::npos ? s.size() : comma;
+            if (eq != std::string::npos && eq < end) {
+                const int o = std::atoi(s.substr(pos, eq - pos).c_str()), v = std::atoi(s.substr(eq + 1, end - eq - 1).c_str());
+                for (auto& w : b->workers) sd_ctx_set_option(w.ctx, o, v);
+            }
+            pos = end + 1;
+        }
+    }
     for (int i = 0; i < workers; ++i) b->workers[i].th = std::thread(worker_loop, b, i);
     *out = b;
     return SD_OK;

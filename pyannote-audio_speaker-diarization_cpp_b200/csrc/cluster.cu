@@ -1081,8 +1081,12 @@ struct __align__(16) ClusterXch {
 // block barrier) and warp 0 publishes ONE entry per CTA, so that the exchange and the redundant decide work on 8
 // entries whatever the thread count is -- that is what lets large problems use 512 threads per CTA (fewer sequential
 // load rounds per thread in the sweep and the rescans) without the decide growing with the number of warps.
+// Register budget of the 128-thread form (the one every file of a batch runs): capped at 128 per thread = 16 K per CTA.
+// An SM has 64 K registers and an STFT CTA takes 15.4 K (96 x 160): next to an uncapped merge-loop CTA (167 registers,
+// 21 K) only two STFT CTAs fit, next to a capped one three -- and with 16 files in flight the merge loops sit on 128
+// of the 148 SMs, so this decides how fast the bandwidth-bound STFTs of the other files run underneath them.
 template <int T, bool GREPL, bool PRE>
-__global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T)
+__global__ void __cluster_dims__(kLcCtas, 1, 1) __launch_bounds__(T, T == 128 ? 4 : 1)
     linkage_cluster_kernel(const LinkWork* __restrict__ works, const int* ns, int* __restrict__ need_exact) {
     constexpr int NW = T / 32;
     constexpr int E = PRE ? kLcCtas : kLcCtas * NW;

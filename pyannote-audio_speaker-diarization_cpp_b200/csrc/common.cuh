@@ -92,6 +92,7 @@ struct sd_ctx {
     int linkage_cluster = 1;                // 1 = spread the merge loop over an 8-CTA cluster when the state fits
     int linkage_wide = 0;                   // whole-GPU merge loop: 0 never (default), 1 for N >= 32768, 2 always
     int stft_variant = 0;                   // tuning hook: 0 = 4 CTAs/SM (<=102 regs), 1 = 3 CTAs/SM
+    int stft_waves = 1;                     // CTAs per resident slot of the STFT grid (1 = persistent)
     cudaEvent_t ev_lk[3] = {};              // around pdist / the merge loop of the last linkage (sd_linkage_stage_ms)
     void* extra = nullptr;                  // api.cu's CtxExtra (pinned upload ring, copy streams), owned by the context
 

@@ -577,7 +577,9 @@ static int launch_cfg(sd_ctx* ctx, const float* d_wav, int B, int L, int T, floa
     if (blocks_per_sm < 0) return SD_ERR_CUDA;
     const int tiles_per_item = (T + Cfg::kTileFrames - 1) / Cfg::kTileFrames;
     const long total = (long)B * tiles_per_item;
-    long grid = (long)ctx->num_sms * blocks_per_sm;
+    // stft_waves > 1: that many CTAs per resident slot, each looping over proportionally fewer tiles, so that slots
+    // are handed back every 1 / waves of the kernel instead of at its end (other streams' small kernels get in)
+    long grid = (long)ctx->num_sms * blocks_per_sm * (ctx->stft_waves > 1 ? ctx->stft_waves : 1);
     if (grid > total) grid = total;
     const int aligned = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_wav) & 15) == 0);
     stft400_kernel<GROUPS, MINB, KALDI, HAMMING><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytesStft, ctx->stream>>>(
