@@ -3,7 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl reference]
 
-A "step" is one pass of the hot path over a batch of `--files` (default 16) synthetic 10-minute files per GPU, each
+A "step" is one pass of the hot path over a batch of `--files` (default 24) synthetic 10-minute files per GPU, each
 at BASELINE.json configs[1]
 (10 s chunks / 1 s step -> 591 chunks x 589 frames x 3 local speakers, 1 773 STFT items of 160 000 samples,
 1 773 embeddings of dimension 192): STFT of every (chunk, speaker) item, hysteresis binarisation, speaker
@@ -297,6 +297,7 @@ def run_product(args, rank, world):
     # and are gathered over the ranks with ONE all_gather at the end of the timed region (shard.gather_results) -- the
     # only collective on the path (KBs).
     batch = pkg.Batch(local, workers)
+    batch_cfg = batch.config()
     files = (pkg.SdFile * nfiles)(*[j.sd_file() for j in jobs])
 
     def run_batch(nsteps):
@@ -406,6 +407,7 @@ def run_product(args, rank, world):
                    "concurrency": "sd_batch_* (native): one library-owned host thread + sd_ctx + CUDA stream per file "
                                   "in flight, all steps queued at once; files assigned to ranks by shard.assign_files "
                                   "(LPT); one all_gather of the labels at the end of the timed region",
+                   "batch_config": batch_cfg,
                    "host_wait": sched or "spin (driver default)",
                    "parallelism": "file-sharded x%d" % world},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * e2e_files,
@@ -643,9 +645,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--files", type=int, default=16,
-                    help="files per step per GPU, all in flight at once (16: 345 k audio-s/s on one B200, 8: 268 k, "
-                         "24-32: 360-375 k at twice the memory; profiles/r02_bench_v2_*.json)")
+    ap.add_argument("--files", type=int, default=24,
+                    help="files per step per GPU, all in flight at once (4 GB of device memory each; 16: ~390 k "
+                         "audio-s/s on one B200, 24: ~490 k, 32: ~500 k; profiles/r02_batch_sweep.md)")
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS),
                     help="cfg2 (default): BASELINE configs[1], --files 10-min files per GPU per step (weak scaling); "
                          "cfg4: BASELINE configs[3], 64 five-minute files sharded over the GPUs (strong scaling)")

@@ -345,7 +345,29 @@ typedef struct sd_file {
     int status;        /* sd_status of this file */
     sd_window count_frames;
 } sd_file;
-int sd_batch_create(int device, int workers, sd_batch** out);
+int sd_batch_create(int device, int workers, sd_batch** out); /* = sd_batch_create_ex with cfg == NULL */
+/* How the files in flight share the GPU (every field: -1 = automatic).
+ *   stft_chain      k > 0: the STFT launch of a file waits (on the device, through an event) for the k-th most recent
+ *                   STFT launch of the batch, so the persistent STFT grids run first in, first out instead of sharing the
+ *                   SMs and finishing together; the merge loops that follow then start staggered and run under the other
+ *                   files' STFTs.  0 = unordered.  Automatic: 1.
+ *   linkage_cluster 1: merge loop on an 8-CTA cluster (lowest latency for one file: 8.7 ms at 1 683 embeddings);
+ *                   0: merge loop in one CTA (11.6 ms, but it holds one SM's registers instead of eight, which is what
+ *                   the bandwidth-bound STFTs of the other files lose).  Automatic: 1 up to 16 workers, 0 beyond.
+ *   narrow_sms      n > 0: partition the GPU with CUDA green contexts -- the STFT runs on (SMs - n) SMs, every other
+ *                   stage of a file on the remaining n (a multiple of 8 on sm_100).  Isolates the stages from each other
+ *                   (the STFT then runs at its stand-alone rate per SM); measured slower overall than sharing all SMs
+ *                   for the benchmark mix, so automatic = 0 (no partition).  Falls back to 0 if the driver refuses.
+ * Results are identical whatever the configuration.  The environment variables SDB_BATCH_STFT_CHAIN,
+ * SDB_BATCH_LINKAGE_CLUSTER and SDB_BATCH_NARROW_SMS override the structure (experiments); SDB_BATCH_TRACE=<path>
+ * writes a device-side timeline of every file (one %globaltimer stamp per stage) when the batch is destroyed. */
+typedef struct sd_batch_config {
+    int stft_chain;
+    int linkage_cluster;
+    int narrow_sms;
+} sd_batch_config;
+int sd_batch_create_ex(int device, int workers, const sd_batch_config* cfg, sd_batch** out);
+int sd_batch_get_config(const sd_batch* b, sd_batch_config* out); /* the values in effect (narrow_sms as granted) */
 void sd_batch_destroy(sd_batch* b);
 int sd_batch_set_params(sd_batch* b, const sd_stft_params* stft, const sd_cluster_params* cluster); /* NULL = keep */
 int sd_batch_workers(const sd_batch* b);

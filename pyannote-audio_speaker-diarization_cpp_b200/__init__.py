@@ -93,7 +93,7 @@ EXPORTS = [
     "sd_crop_chunks_dev", "sd_clustering_async_dev", "sd_status_reset", "sd_status_check",
     "sd_clustering_ex", "sd_binarize_rows_stages", "sd_trim_sum", "sd_mask_interpolate", "sd_clustered_segmentations",
     "sd_to_diarization", "sd_stft_kaldi_params", "sd_stft_num_frames_mode", "sd_fbank_kaldi_params",
-    "sd_batch_create", "sd_batch_destroy", "sd_batch_set_params", "sd_batch_workers", "sd_batch_stream",
+    "sd_batch_create", "sd_batch_create_ex", "sd_batch_get_config", "sd_batch_destroy", "sd_batch_set_params", "sd_batch_workers", "sd_batch_stream",
     "sd_batch_submit", "sd_batch_wait", "sd_batch_last_error", "sd_batch_launch_count", "sd_linkage_stage_ms",
 ]
 
@@ -191,6 +191,8 @@ def lib():
         "sd_clustered_segmentations": (i, [vp, vp, i, i, i, vp, i, vp]),
         "sd_to_diarization": (i, [vp, vp, i64, i, W, vp, i64, W, vp, i64, c_lp, W, vp, c_lp]),
         "sd_batch_create": (i, [i, i, C.POINTER(vp)]),
+        "sd_batch_create_ex": (i, [i, i, C.POINTER(SdBatchConfig), C.POINTER(vp)]),
+        "sd_batch_get_config": (i, [vp, C.POINTER(SdBatchConfig)]),
         "sd_batch_destroy": (None, [vp]),
         "sd_batch_set_params": (i, [vp, C.POINTER(StftParams), C.POINTER(ClusterParams)]),
         "sd_batch_workers": (i, [vp]),
@@ -222,17 +224,29 @@ def _win(w):
 FRAMES = (0.0, FRAME_STEP, FRAME_DURATION, 0)
 
 
+class SdBatchConfig(C.Structure):
+    _fields_ = [("stft_chain", C.c_int), ("linkage_cluster", C.c_int), ("narrow_sms", C.c_int)]
+
+
 class Batch:
     """sd_batch: `workers` files in flight on one GPU, driven by library-owned host threads."""
 
-    def __init__(self, device=0, workers=8):
+    def __init__(self, device=0, workers=8, stft_chain=-1, linkage_cluster=-1, narrow_sms=-1):
+        """-1 = automatic (sd_batch_config, include/sdb200.h)."""
         self.L = lib()
         h = C.c_void_p()
-        rc = self.L.sd_batch_create(device, workers, C.byref(h))
+        cfg = SdBatchConfig(stft_chain, linkage_cluster, narrow_sms)
+        rc = self.L.sd_batch_create_ex(device, workers, C.byref(cfg), C.byref(h))
         if rc != SD_OK:
             raise SdError(rc, "sd_batch_create(device=%d) failed: no usable CUDA device (no CPU fallback exists)" % device)
         self.h = h
         self.workers = workers
+
+    def config(self):
+        """The configuration in effect (narrow_sms as granted by the driver, 0 = no partition)."""
+        cfg = SdBatchConfig()
+        self.L.sd_batch_get_config(self.h, C.byref(cfg))
+        return dict(stft_chain=cfg.stft_chain, linkage_cluster=cfg.linkage_cluster, narrow_sms=cfg.narrow_sms)
 
     def close(self):
         if self.h:

@@ -2899,9 +2899,11 @@ int linkage_launch(sd_ctx* ctx, const double* d_x, int N, int D, double* d_Z, in
     int rc = pdist_square(ctx, d_x, N, D, mode, &base, &L);
     if (rc) return rc;
     SD_CUDA(ctx, cudaEventRecord(ctx->ev_lk[1], ctx->stream));
+    trace_stamp(ctx, 3);
     rc = linkage_on_square(ctx, base, L, d_x, N, D, d_Z);
     if (rc) return rc;
     SD_CUDA(ctx, cudaEventRecord(ctx->ev_lk[2], ctx->stream));
+    trace_stamp(ctx, 4);
     return SD_OK;
 }
 

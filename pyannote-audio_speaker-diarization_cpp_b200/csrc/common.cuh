@@ -95,6 +95,10 @@ struct sd_ctx {
     int stft_waves = 1;                     // CTAs per resident slot of the STFT grid (1 = persistent)
     cudaEvent_t ev_lk[3] = {};              // around pdist / the merge loop of the last linkage (sd_linkage_stage_ms)
     void* extra = nullptr;                  // api.cu's CtxExtra (pinned upload ring, copy streams), owned by the context
+    // batch timeline (SDB_BATCH_TRACE, batch.cu): %globaltimer stamps written by one-thread kernels on the stream
+    unsigned long long* d_trace = nullptr;
+    int trace_cap = 0;
+    std::vector<int> trace_tags;            // tag of stamp i (host side)
 
     int fail(int code, const char* fmt, ...) {
         char b[512];
@@ -203,6 +207,9 @@ int clean_launch(sd_ctx* ctx, const double* d_bin, int64_t rows, int K, double* 
 
 // latched device status word -> sd_status + message (api.cu)
 int status_message(sd_ctx* ctx, int st);
+
+// batch timeline: no-op unless the context has a trace buffer (batch.cu)
+void trace_stamp(sd_ctx* ctx, int tag);
 
 // host-side scalar helpers shared by several translation units
 int np_rint_host(double v);

@@ -160,7 +160,7 @@ template <int GROUPS, int MINB, bool KALDI, bool HAMMING>
 __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     stft400_kernel(const float* __restrict__ wav, float* __restrict__ out, int L, int T, int tiles_per_item,
                    long total_tiles, const float* __restrict__ window, const float2* __restrict__ twiddle,
-                   int aligned16, FrameGeom fg, KaldiArgs ka) {
+                   int aligned16, FrameGeom fg, KaldiArgs ka, unsigned long long* __restrict__ tile_ctr) {
     using Cfg = StftCfg<GROUPS>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xbuf = reinterpret_cast<float2*>(smem_raw);                 // phase 1 -> phase 2 transpose
@@ -169,8 +169,18 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     float* sig = reinterpret_cast<float*>(wtab + kNfft);                // padded samples of the tile
     float2* zup = xbuf;  // upper half of the spectrum: reuses the transpose buffer once phase 2 has loaded it
     __shared__ __align__(8) uint64_t bar;
+    __shared__ long s_next;
     __shared__ float2 dc_part[KALDI ? GROUPS * kRadix : 1];
 
+    // Tiles are handed out dynamically: the first one is the CTA's own index, every further one comes from a global
+    // counter.  A static stride would assume that every CTA of the grid is resident at once; when other kernels hold
+    // SM resources (the merge loops of other files of a batch: one register-heavy CTA on most SMs), some CTAs only
+    // start when others exit and the kernel takes two waves -- measured 1.55 ms instead of 0.93 ms per launch under
+    // eight concurrent merge loops.  With the counter a late CTA just finds less work.  Thread 0 fetches the index
+    // one tile ahead of its use, so the round trip of the atomic is off the critical path.
+    unsigned long long nxt_raw = 0;  // counter value; the tile index is gridDim.x + this (added at the point of use, so
+                                     // that nothing waits for the atomic's round trip before the next iteration)
+    if (threadIdx.x == 0) nxt_raw = atomicAdd(tile_ctr, 1ull);
     const int g = threadIdx.x / kRadix;
     const int r = threadIdx.x - g * kRadix;
     float ham_c, ham_s;  // (cos, sin)(2 pi r / 400) for the table-free Hamming window
@@ -221,7 +231,7 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
         fetched = true;
         __syncthreads();
     }
-    for (; tile < total_tiles; tile += gridDim.x) {
+    while (tile < total_tiles) {
         if (!fetched) {
             stage_tile<GROUPS>(sig, wav, L, tile, tiles_per_item, aligned16 != 0, fg);
             cp_async_commit();
@@ -238,12 +248,17 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
         }
         __syncthreads();  // the transpose is complete and sig is free: the next tile's samples may land already,
                           // under the shadow of phase 2 and the stores
-        const long next = tile + gridDim.x;
-        fetched = next < total_tiles && interior(next);
-        if (fetched && threadIdx.x == 0) issue_bulk(next);
+        if (threadIdx.x == 0) {
+            const long nxt = (long)gridDim.x + (long)nxt_raw;
+            s_next = nxt;  // read by everybody after the next barrier
+            if (nxt < total_tiles && interior(nxt)) issue_bulk(nxt);
+            nxt_raw = atomicAdd(tile_ctr, 1ull);  // used one iteration from now
+        }
         float2 v[20];
         stft_phase2_load(xbuf, g, r, v);
         __syncthreads();  // every row of the transpose buffer is in registers: it now receives the upper halves
+        const long next = s_next;
+        fetched = next < total_tiles && interior(next);
         stft_publish_upper(v, g, r, zup, kGroupStride);
         __syncthreads();  // upper halves are visible
 
@@ -260,6 +275,16 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
             parity ^= 1;
         }
         __syncthreads();  // zup (the transpose buffer) is consumed: the next tile's phase 1 may overwrite it
+        tile = next;
+    }
+    // the last CTA to leave zeroes the counters for the next launch on this context (launches of a context are
+    // stream-ordered; contexts do not share counters)
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(tile_ctr + 1, 1ull) == (unsigned long long)gridDim.x - 1) {
+            tile_ctr[0] = 0;
+            tile_ctr[1] = 0;
+        }
     }
 }
 
@@ -584,7 +609,7 @@ static int launch_cfg(sd_ctx* ctx, const float* d_wav, int B, int L, int T, floa
     const int aligned = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_wav) & 15) == 0);
     stft400_kernel<GROUPS, MINB, KALDI, HAMMING><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytesStft, ctx->stream>>>(
         d_wav, d_out, L, T, tiles_per_item, total, ctx->d_window, reinterpret_cast<const float2*>(ctx->d_twiddle),
-        aligned, fg, ka);
+        aligned, fg, ka, ctx->d_stats + 8);
     SD_LAUNCH_CHECK(ctx);
     return SD_OK;
 }

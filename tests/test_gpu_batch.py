@@ -150,3 +150,50 @@ def test_one_long_file_split_by_chunk_range(pkg, synth, oracle):
         assert np.array_equal(out["hard"], want["hard"]) and np.array_equal(out["diar"], want["diar"])
     finally:
         b.close()
+
+
+@pytest.mark.parametrize("cfg", [dict(stft_chain=0, linkage_cluster=1), dict(stft_chain=2, linkage_cluster=0),
+                                 dict(narrow_sms=16), dict(narrow_sms=24, linkage_cluster=0, stft_chain=0)])
+def test_batch_configurations_give_identical_results(pkg, synth, oracle, cfg):
+    """sd_batch_config (STFT launch order, merge-loop kernel, SM partition through green contexts) changes how the
+    files share the GPU, never what they compute: every configuration equals the oracle, with host and device
+    pointers mixed over two submissions."""
+    xs = [make_inputs(synth, 300 + 10 * i, 18 + 9 * i) for i in range(6)]
+    wants = [expected(oracle, x) for x in xs]
+    pairs = [host_file(pkg, x) for x in xs]
+    files = (pkg.SdFile * len(pairs))(*[p[0] for p in pairs])
+    b = pkg.Batch(0, 4, **cfg)
+    try:
+        got = b.config()
+        for k, v in cfg.items():
+            if k == "narrow_sms":
+                assert got[k] in (0, v) or got[k] >= v  # granted size (rounded up), or 0 if the driver refused
+            else:
+                assert got[k] == v
+        for _ in range(2):
+            for _, out in pairs:
+                out["hard"][...] = -7
+                out["stft"][...] = 0
+            b.run(files, pkg.SD_BATCH_HOST)
+            for i, (_, out) in enumerate(pairs):
+                check(files[i], out, wants[i])
+    finally:
+        b.close()
+
+
+def test_batch_trace_writes_a_timeline(pkg, synth, tmp_path, monkeypatch):
+    """SDB_BATCH_TRACE: one line per file with the seven %globaltimer stamps in order."""
+    path = tmp_path / "trace.csv"
+    monkeypatch.setenv("SDB_BATCH_TRACE", str(path))
+    xs = [make_inputs(synth, 400 + i, 15) for i in range(3)]
+    pairs = [host_file(pkg, x) for x in xs]
+    b = pkg.Batch(0, 2)
+    try:
+        b.run((pkg.SdFile * 3)(*[p[0] for p in pairs]))
+    finally:
+        b.close()
+    rows = path.read_text().strip().splitlines()
+    assert rows[0].startswith("worker,start,stft_done") and len(rows) == 4
+    for line in rows[1:]:
+        t = [float(v) for v in line.split(",")[1:]]
+        assert all(a <= b_ for a, b_ in zip(t, t[1:])), line
