@@ -353,7 +353,8 @@ int sd_batch_create(int device, int workers, sd_batch** out); /* = sd_batch_crea
  *                   files' STFTs.  0 = unordered.  Automatic: 1.
  *   linkage_cluster 1: merge loop on an 8-CTA cluster (lowest latency for one file: 8.7 ms at 1 683 embeddings);
  *                   0: merge loop in one CTA (11.6 ms, but it holds one SM's registers instead of eight, which is what
- *                   the bandwidth-bound STFTs of the other files lose).  Automatic: 1 up to 16 workers, 0 beyond.
+ *                   the bandwidth-bound STFTs of the other files lose: 413 k against 378 k audio-s/s at 16 files in
+ *                   flight).  Automatic: 1 up to 8 workers, 0 beyond.
  *   narrow_sms      n > 0: partition the GPU with CUDA green contexts -- the STFT runs on (SMs - n) SMs, every other
  *                   stage of a file on the remaining n (a multiple of 8 on sm_100).  Isolates the stages from each other
  *                   (the STFT then runs at its stand-alone rate per SM); measured slower overall than sharing all SMs

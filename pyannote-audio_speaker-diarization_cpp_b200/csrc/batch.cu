@@ -306,7 +306,7 @@ int sd_batch_create_ex(int device, int workers, const sd_batch_config* cfg, sd_b
     env_int("SDB_BATCH_LINKAGE_CLUSTER", &c.linkage_cluster);
     env_int("SDB_BATCH_NARROW_SMS", &c.narrow_sms);
     b->stft_chain = c.stft_chain < 0 ? 1 : c.stft_chain;
-    b->linkage_cluster = c.linkage_cluster < 0 ? (workers <= 16 ? 1 : 0) : (c.linkage_cluster != 0);
+    b->linkage_cluster = c.linkage_cluster < 0 ? (workers <= 8 ? 1 : 0) : (c.linkage_cluster != 0);
     int narrow = c.narrow_sms < 0 ? 0 : c.narrow_sms;
     b->workers.resize((size_t)workers);
     for (int i = 0; i < workers; ++i) {

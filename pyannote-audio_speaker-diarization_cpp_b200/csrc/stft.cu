@@ -317,7 +317,7 @@ __host__ __device__ __forceinline__ float float_from_order_key(int k) {
 #endif
 }
 
-template <int GROUPS, int MINB, bool KALDI>
+template <int GROUPS, int MINB, bool KALDI, bool HAMMING>
 __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     fbank400_kernel(const float* __restrict__ wav, float* __restrict__ out, int L, int T, int tiles_per_item,
                     long total_tiles, const float* __restrict__ window, const float2* __restrict__ twiddle,
@@ -337,6 +337,8 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
 
     const int g = threadIdx.x / kRadix;
     const int r = threadIdx.x - g * kRadix;
+    float ham_c, ham_s;  // (cos, sin)(2 pi r / 400) for the table-free Hamming window (stft400_kernel)
+    sincospif((float)r * (1.0f / 200.0f), &ham_s, &ham_c);
     for (int i = threadIdx.x; i < kNfft; i += Cfg::kThreads) wtab[i] = wtab_make(0.5f * window[i]);
     for (int e = threadIdx.x; e < kTwTableUnits; e += Cfg::kThreads) twT[e] = twiddle[tw_table_source(e)];
     for (int i = threadIdx.x; i < (int)(sizeof(MelTable) / 4); i += Cfg::kThreads)
@@ -392,6 +394,8 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
         if (KALDI) {
             const float2 dc = frame_dc_offsets<GROUPS>(sig, g, r, dc_part, ka);
             stft_phase1_kaldi(sig, sig_frame_off(2 * g), sig_frame_off(2 * g + 1), wtab, twp, g, r, xbuf, ka.preemph, dc);
+        } else if (HAMMING) {
+            stft_phase1_hamming(sig, sig_frame_off(2 * g), sig_frame_off(2 * g + 1), ham_c, ham_s, twp, g, r, xbuf);
         } else {
             stft_phase1_tab(sig, sig_frame_off(2 * g), sig_frame_off(2 * g + 1), wtab, twp, g, r, xbuf);
         }
@@ -425,15 +429,22 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
         fetched = next < total_tiles && interior(next);
         if (fetched && threadIdx.x == 0) issue_bulk(next);
 
-        // mel projection + dB.  Thread -> one mel filter (fastest index, so stores are coalesced) and one half of the
-        // tile's frames: the filter's weights are read once and reused for every frame.
+        // mel projection + dB.  Thread -> one mel filter and one half of the tile's frames: the filter's weights are
+        // read once and reused for every frame.  A warp takes as long as its widest filter (1 bin at the bottom of the
+        // mel scale, 13 at the top), so with 160 threads and 80 filters warp w gets filters 16 (4 - w) .. + 15 for both
+        // halves: similar widths share a warp (issue slots 240 instead of 320 per tile, the widest warp starts first);
+        // 16 consecutive filters are still one 64-byte run of a row.
         const int b = (int)(tile / tiles_per_item);
         const int ti = (int)(tile - (long)b * tiles_per_item);
         const int t0 = ti * Cfg::kTileFrames;
         float vmax = -INFINITY;
         constexpr int kFramesPerPass = Cfg::kThreads / 80 > 0 ? Cfg::kThreads / 80 : 1;  // frame slots per pass
         for (int m0 = 0; m0 < n_mels; m0 += 80) {
-            const int m = m0 + (int)(threadIdx.x % 80), slot = threadIdx.x / 80;
+            int m = m0 + (int)(threadIdx.x % 80), slot = threadIdx.x / 80;
+            if (Cfg::kThreads == 160) {
+                m = m0 + 16 * (4 - (int)(threadIdx.x >> 5)) + (int)(threadIdx.x & 15);
+                slot = (threadIdx.x >> 4) & 1;
+            }
             if (m < n_mels && slot < kFramesPerPass) {
                 const int lo = smel.lo[m], cnt = smel.cnt[m];
                 const float* wq = smel.w + smel.off[m];
@@ -755,23 +766,25 @@ int fbank_launch(sd_ctx* ctx, const float* d_wav, int B, int L, const float* d_l
     fill_int_kernel2<<<(B + 255) / 256, 256, 0, ctx->stream>>>(d_max, B, (int)0x80000000);  // below every key
     SD_LAUNCH_CHECK(ctx);
     using Cfg = StftCfg<8>;
-    const int blocks_per_sm =
-        kaldi ? kernel_setup(ctx, fbank400_kernel<8, 3, true>, (int)Cfg::kSmemBytes, Cfg::kThreads, Cfg::kSmemBytes)
-              : kernel_setup(ctx, fbank400_kernel<8, 3, false>, (int)Cfg::kSmemBytes, Cfg::kThreads, Cfg::kSmemBytes);
-    if (blocks_per_sm < 0) return SD_ERR_CUDA;
-    const int tiles_per_item = (T + Cfg::kTileFrames - 1) / Cfg::kTileFrames;
-    const long total = (long)B * tiles_per_item;
-    long grid = (long)ctx->num_sms * blocks_per_sm;
-    if (grid > total) grid = total;
-    const int aligned = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_wav) & 15) == 0);
-    if (kaldi)
-        fbank400_kernel<8, 3, true><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream>>>(
+    // the reference's window is computed in registers (two FFMA per sample instead of a table read) -- stft400_kernel
+    const bool hamming = !kaldi && sp->window_kind == SD_WINDOW_HAMMING_PERIODIC && ctx->stft_variant != 2;
+    auto launch = [&](auto kernel) -> int {
+        const int blocks_per_sm = kernel_setup(ctx, kernel, (int)Cfg::kSmemBytes, Cfg::kThreads, Cfg::kSmemBytes);
+        if (blocks_per_sm < 0) return SD_ERR_CUDA;
+        const int tiles_per_item = (T + Cfg::kTileFrames - 1) / Cfg::kTileFrames;
+        const long total = (long)B * tiles_per_item;
+        long grid = (long)ctx->num_sms * blocks_per_sm;
+        if (grid > total) grid = total;
+        const int aligned = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_wav) & 15) == 0);
+        kernel<<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream>>>(
             d_wav, d_out, L, T, tiles_per_item, total, ctx->d_window, reinterpret_cast<const float2*>(ctx->d_twiddle),
             aligned, reinterpret_cast<const MelTable*>(ctx->d_mel), p->n_mels, p->amin, log_scale, d_max, fg, ka);
-    else
-        fbank400_kernel<8, 3, false><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream>>>(
-            d_wav, d_out, L, T, tiles_per_item, total, ctx->d_window, reinterpret_cast<const float2*>(ctx->d_twiddle),
-            aligned, reinterpret_cast<const MelTable*>(ctx->d_mel), p->n_mels, p->amin, log_scale, d_max, fg, ka);
+        return SD_OK;
+    };
+    // 96 registers (4 CTAs per SM) without spills for the plain front-end; the Kaldi conditioning needs 128 (3 per SM)
+    rc = kaldi ? launch(fbank400_kernel<8, 3, true, false>)
+               : hamming ? launch(fbank400_kernel<8, 4, false, true>) : launch(fbank400_kernel<8, 4, false, false>);
+    if (rc) return rc;
     SD_LAUNCH_CHECK(ctx);
     const int total_e = T * p->n_mels;
     const size_t nsm = sizeof(double) * (size_t)FN_THREADS;
