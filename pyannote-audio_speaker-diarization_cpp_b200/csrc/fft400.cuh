@@ -40,6 +40,16 @@ constexpr int kRadix = 20;          // threads per frame pair, points per thread
 constexpr int kXchgRow = 21;        // padded row stride (float2 units) of the phase-1 -> phase-2 transpose
 constexpr int kGroupStride = 436;   // float2 units per group in either exchange buffer (436 - 20 = 26 * 16)
 
+// Phase-2 roles.  The real-pair split needs Z[k] and Z[400 - k]; with k = k1 + 20 k2 the partner of role k1 is role
+// 20 - k1 of the same group (roles 0 and 10 are their own partners).  Phase 2 therefore hands the roles out so that
+// partners sit in ADJACENT lanes -- slot s = tid % 20 plays role pair_role(s): (0, 10), (1, 19), (2, 18), ... -- and a
+// group starts at an even thread index, so a pair never straddles a warp: the second exchange is one shfl.xor(1) per
+// value instead of a trip through shared memory behind two block barriers.  Phase 1 keeps slot == n2 (its sample and
+// twiddle accesses stay as they were); only the ROW it writes for output k1 moves to pair_slot(k1), the slot that reads
+// it back, so both transposes keep their lane -> address patterns (and their conflict-free paddings).
+SD_HD constexpr int pair_role(int s) { return (s & 1) == 0 ? s / 2 : (s == 1 ? 10 : 20 - s / 2); }
+SD_HD constexpr int pair_slot(int k1) { return k1 == 0 ? 0 : k1 == 10 ? 1 : k1 < 10 ? 2 * k1 : 2 * (20 - k1) + 1; }
+
 SD_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 SD_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 SD_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
@@ -250,35 +260,35 @@ SD_HD void twiddle_store(const float2 (&v)[20], const float2* twp, float2* dst) 
     for (int k1 = 0; k1 < 20; ++k1) {
         float2 y = v[dft20_slot(k1)];
         if (k1 > 0) y = cmul(y, twp[k1 * kTwRow]);
-        dst[k1 * kXchgRow] = y;
+        dst[pair_slot(k1) * kXchgRow] = y;
     }
 #else
-    dst[0] = v[dft20_slot(0)];
+    dst[pair_slot(0) * kXchgRow] = v[dft20_slot(0)];
     const float2 t1 = twp[1 * kTwRow], t2 = twp[2 * kTwRow];
     const float2 t3 = cmul(t1, t2);
-    dst[1 * kXchgRow] = cmul(v[dft20_slot(1)], t1);
-    dst[2 * kXchgRow] = cmul(v[dft20_slot(2)], t2);
-    dst[3 * kXchgRow] = cmul(v[dft20_slot(3)], t3);
+    dst[pair_slot(1) * kXchgRow] = cmul(v[dft20_slot(1)], t1);
+    dst[pair_slot(2) * kXchgRow] = cmul(v[dft20_slot(2)], t2);
+    dst[pair_slot(3) * kXchgRow] = cmul(v[dft20_slot(3)], t3);
     const float2 t4 = twp[4 * kTwRow];
-    dst[4 * kXchgRow] = cmul(v[dft20_slot(4)], t4);
-    dst[5 * kXchgRow] = cmul(v[dft20_slot(5)], cmul(t4, t1));
-    dst[6 * kXchgRow] = cmul(v[dft20_slot(6)], cmul(t4, t2));
-    dst[7 * kXchgRow] = cmul(v[dft20_slot(7)], cmul(t4, t3));
+    dst[pair_slot(4) * kXchgRow] = cmul(v[dft20_slot(4)], t4);
+    dst[pair_slot(5) * kXchgRow] = cmul(v[dft20_slot(5)], cmul(t4, t1));
+    dst[pair_slot(6) * kXchgRow] = cmul(v[dft20_slot(6)], cmul(t4, t2));
+    dst[pair_slot(7) * kXchgRow] = cmul(v[dft20_slot(7)], cmul(t4, t3));
     const float2 t8 = twp[8 * kTwRow];
     const float2 t12 = cmul(t8, t4);
-    dst[8 * kXchgRow] = cmul(v[dft20_slot(8)], t8);
-    dst[9 * kXchgRow] = cmul(v[dft20_slot(9)], cmul(t8, t1));
-    dst[10 * kXchgRow] = cmul(v[dft20_slot(10)], cmul(t8, t2));
-    dst[11 * kXchgRow] = cmul(v[dft20_slot(11)], cmul(t8, t3));
-    dst[12 * kXchgRow] = cmul(v[dft20_slot(12)], t12);
-    dst[13 * kXchgRow] = cmul(v[dft20_slot(13)], cmul(t12, t1));
-    dst[14 * kXchgRow] = cmul(v[dft20_slot(14)], cmul(t12, t2));
-    dst[15 * kXchgRow] = cmul(v[dft20_slot(15)], cmul(t12, t3));
+    dst[pair_slot(8) * kXchgRow] = cmul(v[dft20_slot(8)], t8);
+    dst[pair_slot(9) * kXchgRow] = cmul(v[dft20_slot(9)], cmul(t8, t1));
+    dst[pair_slot(10) * kXchgRow] = cmul(v[dft20_slot(10)], cmul(t8, t2));
+    dst[pair_slot(11) * kXchgRow] = cmul(v[dft20_slot(11)], cmul(t8, t3));
+    dst[pair_slot(12) * kXchgRow] = cmul(v[dft20_slot(12)], t12);
+    dst[pair_slot(13) * kXchgRow] = cmul(v[dft20_slot(13)], cmul(t12, t1));
+    dst[pair_slot(14) * kXchgRow] = cmul(v[dft20_slot(14)], cmul(t12, t2));
+    dst[pair_slot(15) * kXchgRow] = cmul(v[dft20_slot(15)], cmul(t12, t3));
     const float2 t16 = twp[16 * kTwRow];
-    dst[16 * kXchgRow] = cmul(v[dft20_slot(16)], t16);
-    dst[17 * kXchgRow] = cmul(v[dft20_slot(17)], cmul(t16, t1));
-    dst[18 * kXchgRow] = cmul(v[dft20_slot(18)], cmul(t16, t2));
-    dst[19 * kXchgRow] = cmul(v[dft20_slot(19)], cmul(t16, t3));
+    dst[pair_slot(16) * kXchgRow] = cmul(v[dft20_slot(16)], t16);
+    dst[pair_slot(17) * kXchgRow] = cmul(v[dft20_slot(17)], cmul(t16, t1));
+    dst[pair_slot(18) * kXchgRow] = cmul(v[dft20_slot(18)], cmul(t16, t2));
+    dst[pair_slot(19) * kXchgRow] = cmul(v[dft20_slot(19)], cmul(t16, t3));
 #endif
 }
 
@@ -391,7 +401,8 @@ SD_HD void stft_phase1_kaldi(const float* sig, int fa_off, int fb_off, const wta
     twiddle_store(v, twp, xchg + g * kGroupStride + r);
 }
 
-// phase 2 split in two so that the exchange buffer can be reused for the spectrum: load + transform ...
+// phase 2 of the kernels: slot r reads the row that phase 1 wrote for output k1 = pair_role(r) and transforms it:
+// afterwards v[dft20_slot(k2)] = Z[pair_role(r) + 20 k2]
 SD_HD void stft_phase2_load(const float2* xchg, int g, int r, float2 (&v)[20]) {
     const float2* src = xchg + g * kGroupStride + r * kXchgRow;
 #pragma unroll
@@ -499,5 +510,65 @@ SD_HD void stft_split_store(const float2 (&v)[20], const float2* zup, int g, int
         if (HAS_B) ob[200] = make_float2(a.y + a.y, 0.f);
     }
 }
+
+// ---- second exchange between pair lanes -------------------------------------------------------------------
+// Slot s (role k1 = pair_role(s)) owns bins k = k1 + 20 m, m = 0..9 (plus k = 200 for role 0).  Z[400 - k] is the
+// pair lane's k2 = 19 - m value -- the same register index on both sides, so both lanes send v[dft20_slot(19 - m)] and
+// receive the other's.  `partner(value, index)` returns the pair lane's v[index]: a shfl.xor(1) on the device, an array
+// access in the host emulation.  Roles 0 and 10 are their own partners (role 0: Z[400 - 20 m] = own k2 = 20 - m).
+// Spectrum scaled by 1/2 (folded into the window): A[k] = Z[k] + conj Z[400-k], B[k] = -i (Z[k] - conj Z[400-k]).
+// okA / okB: whether the frame exists (predicated stores: the exchange itself must run in every lane).
+template <typename Partner>
+SD_HD void stft_split_store_pair(const float2 (&v)[20], int s, float* outA, float* outB, bool okA, bool okB,
+                                 Partner partner) {
+    const int k1 = pair_role(s);
+    float2* oa = reinterpret_cast<float2*>(outA);
+    float2* ob = reinterpret_cast<float2*>(outB);
+#pragma unroll
+    for (int m = 0; m < 10; ++m) {
+        const float2 a = v[dft20_slot(m)];
+        const float2 mine = v[dft20_slot(19 - m)];
+        float2 b = partner(mine, dft20_slot(19 - m));
+        if (s == 1) b = mine;
+        if (s == 0) b = v[dft20_slot((20 - m) % 20)];
+        if (okA) oa[k1 + 20 * m] = split_a(a, b);
+        if (okB) ob[k1 + 20 * m] = split_b(a, b);
+    }
+    if (s == 0) {  // k = 200: partner of Z[200] is itself
+        const float2 a = v[dft20_slot(10)];
+        if (okA) oa[200] = make_float2(a.x + a.x, 0.f);
+        if (okB) ob[200] = make_float2(a.y + a.y, 0.f);
+    }
+}
+
+// |A[k]|^2 and |B[k]|^2 of the slot's bins into pa / pb (fbank front-end), same exchange
+template <typename Partner>
+SD_HD void stft_split_power_pair(const float2 (&v)[20], int s, float* pa, float* pb, Partner partner) {
+    const int k1 = pair_role(s);
+#pragma unroll
+    for (int m = 0; m < 10; ++m) {
+        const float2 a = v[dft20_slot(m)];
+        const float2 mine = v[dft20_slot(19 - m)];
+        float2 c = partner(mine, dft20_slot(19 - m));
+        if (s == 1) c = mine;
+        if (s == 0) c = v[dft20_slot((20 - m) % 20)];
+        const float ar = a.x + c.x, ai = a.y - c.y, br = a.y + c.y, bi = c.x - a.x;
+        pa[k1 + 20 * m] = ar * ar + ai * ai;
+        pb[k1 + 20 * m] = br * br + bi * bi;
+    }
+    if (s == 0) {
+        const float2 a = v[dft20_slot(10)];
+        pa[200] = 4.f * a.x * a.x;
+        pb[200] = 4.f * a.y * a.y;
+    }
+}
+
+#if defined(__CUDACC__)
+struct PairShuffle {  // the pair lane's copy of a register, through the warp
+    __device__ __forceinline__ float2 operator()(float2 mine, int) const {
+        return make_float2(__shfl_xor_sync(0xffffffffu, mine.x, 1), __shfl_xor_sync(0xffffffffu, mine.y, 1));
+    }
+};
+#endif
 
 }  // namespace sdb

@@ -167,7 +167,6 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     float2* twT = xbuf + GROUPS * kGroupStride;                         // twiddle table (see tw_thread_offset)
     wtab_t* wtab = reinterpret_cast<wtab_t*>(twT + kTwTableUnits);      // window, pre-scaled by 1/2
     float* sig = reinterpret_cast<float*>(wtab + kNfft);                // padded samples of the tile
-    float2* zup = xbuf;  // upper half of the spectrum: reuses the transpose buffer once phase 2 has loaded it
     __shared__ __align__(8) uint64_t bar;
     __shared__ long s_next;
     __shared__ float2 dc_part[KALDI ? GROUPS * kRadix : 1];
@@ -248,33 +247,30 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
         }
         __syncthreads();  // the transpose is complete and sig is free: the next tile's samples may land already,
                           // under the shadow of phase 2 and the stores
+        bool wait_next = false;  // thread 0: a bulk load is in flight
         if (threadIdx.x == 0) {
             const long nxt = (long)gridDim.x + (long)nxt_raw;
-            s_next = nxt;  // read by everybody after the next barrier
-            if (nxt < total_tiles && interior(nxt)) issue_bulk(nxt);
+            s_next = nxt;  // read by everybody after the barrier at the end of the tile
+            wait_next = nxt < total_tiles && interior(nxt);
+            if (wait_next) issue_bulk(nxt);
             nxt_raw = atomicAdd(tile_ctr, 1ull);  // used one iteration from now
         }
         float2 v[20];
-        stft_phase2_load(xbuf, g, r, v);
-        __syncthreads();  // every row of the transpose buffer is in registers: it now receives the upper halves
-        const long next = s_next;
-        fetched = next < total_tiles && interior(next);
-        stft_publish_upper(v, g, r, zup, kGroupStride);
-        __syncthreads();  // upper halves are visible
+        stft_phase2_load(xbuf, g, r, v);  // slot r plays role pair_role(r) from here on
 
+        // The real-pair split: Z[400 - k] lives in the adjacent lane (fft400.cuh), so the second exchange is a
+        // shuffle -- no shared-memory round trip and no block barrier around it (two barriers per tile instead of four).
         const int b = (int)(tile / tiles_per_item);
         const int ti = (int)(tile - (long)b * tiles_per_item);
         const int tA = ti * Cfg::kTileFrames + 2 * g;
         float* rowA = out + ((size_t)b * T + tA) * (kBins * 2);
-        if (tA + 1 < T)
-            stft_split_store<true, true>(v, zup, g, r, rowA, rowA + kBins * 2, kGroupStride);
-        else if (tA < T)
-            stft_split_store<true, false>(v, zup, g, r, rowA, nullptr, kGroupStride);
-        if (fetched) {
-            if (threadIdx.x == 0) mbar_wait(&bar, parity);  // the next tile's samples have landed
-            parity ^= 1;
-        }
-        __syncthreads();  // zup (the transpose buffer) is consumed: the next tile's phase 1 may overwrite it
+        stft_split_store_pair(v, r, rowA, rowA + kBins * 2, tA < T, tA + 1 < T, PairShuffle());
+        if (wait_next) mbar_wait(&bar, parity);  // thread 0: the next tile's samples have landed
+        __syncthreads();  // every phase-2 load of the transpose buffer is done: the next tile's phase 1 may overwrite
+                          // it; s_next and the landed samples are visible to everybody
+        const long next = s_next;  // (rewritten only after the next tile's first barrier)
+        fetched = next < total_tiles && interior(next);
+        if (fetched) parity ^= 1;
         tile = next;
     }
     // the last CTA to leave zeroes the counters for the next launch on this context (launches of a context are
@@ -329,7 +325,6 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     float2* twT = xbuf + GROUPS * kGroupStride;
     wtab_t* wtab = reinterpret_cast<wtab_t*>(twT + kTwTableUnits);
     float* sig = reinterpret_cast<float*>(wtab + kNfft);
-    float2* zup = reinterpret_cast<float2*>(sig);
     float* pw = reinterpret_cast<float*>(xbuf);  // power spectra [frame][201], aliases the transpose buffer
     __shared__ __align__(8) uint64_t bar;
     __shared__ MelTable smel;
@@ -399,35 +394,17 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
         } else {
             stft_phase1_tab(sig, sig_frame_off(2 * g), sig_frame_off(2 * g + 1), wtab, twp, g, r, xbuf);
         }
-        __syncthreads();
-        float2 v[20];
-        stft_phase2_load(xbuf, g, r, v);
-        stft_publish_upper(v, g, r, zup);
-        __syncthreads();  // xbuf is dead from here: it receives the power spectra
-
-        // |X|^2 of both frames of the pair into pw[frame][bin]
-        {
-            float* pa = pw + (2 * g) * kBins;
-            float* pb = pa + kBins;
-            const float2* zm = zup + g * kZStride + 200 - r;
-#pragma unroll
-            for (int m = 0; m < 10; ++m) {
-                const float2 a = v[dft20_slot(m)];
-                const float2 c = zm[-20 * m];
-                const float ar = a.x + c.x, ai = a.y - c.y, br = a.y + c.y, bi = c.x - a.x;
-                pa[r + 20 * m] = ar * ar + ai * ai;
-                pb[r + 20 * m] = br * br + bi * bi;
-            }
-            if (r == 0) {
-                const float2 a = v[dft20_slot(10)];
-                pa[200] = 4.f * a.x * a.x;
-                pb[200] = 4.f * a.y * a.y;
-            }
-        }
-        __syncthreads();  // power spectra complete; zup (aliasing sig) is consumed
+        __syncthreads();  // the transpose is complete and sig is free: the next tile's samples may land from here on
         const long next = tile + gridDim.x;
         fetched = next < total_tiles && interior(next);
         if (fetched && threadIdx.x == 0) issue_bulk(next);
+        float2 v[20];
+        stft_phase2_load(xbuf, g, r, v);  // slot r plays role pair_role(r) from here on
+        __syncthreads();  // xbuf is dead from here: it receives the power spectra
+
+        // |X|^2 of both frames of the pair into pw[frame][bin]; Z[400 - k] comes from the adjacent lane (fft400.cuh)
+        stft_split_power_pair(v, r, pw + (2 * g) * kBins, pw + (2 * g + 1) * kBins, PairShuffle());
+        __syncthreads();  // power spectra complete
 
         // mel projection + dB.  Thread -> one mel filter and one half of the tile's frames: the filter's weights are
         // read once and reused for every frame.  A warp takes as long as its widest filter (1 bin at the bottom of the

@@ -36,7 +36,8 @@ int main() {
         int g = t / kRadix;
         stft_phase3(zbuf.data(), g, t % kRadix, &out[(2 * g) * kBins * 2], &out[(2 * g + 1) * kBins * 2]);
     }
-    // variant B (the kernel's): padded staging, shared window / twiddle tables, one exchange buffer
+    // variant B (the kernel's): padded staging, shared window / twiddle tables, one transpose through shared memory, the
+    // real-pair split between adjacent lanes
     std::vector<float> sigp(sig_padded_size(nsig) + 8, 0.f), out2(frames * kBins * 2, 0.f);
     std::vector<wtab_t> wtab(w.size());  // w/2: the kernel folds the 1/2 of the real-pair split into the window
     for (size_t i = 0; i < w.size(); ++i) wtab[i] = wtab_make(0.5f * w[i]);
@@ -81,18 +82,41 @@ int main() {
         stft_phase2_load(xb.data(), t / kRadix, t % kRadix, v);
         for (int i = 0; i < 20; ++i) regs[t][i] = v[i];
     }
-    std::vector<float2> zup(groups * kGroupStride);  // the kernel reuses the transpose buffer (stride kGroupStride)
-    for (int t = 0; t < nthreads; ++t) {  // compact second exchange: only Z[200..400] crosses threads
-        float2 v[20];
-        for (int i = 0; i < 20; ++i) v[i] = regs[t][i];
-        stft_publish_upper(v, t / kRadix, t % kRadix, zup.data(), kGroupStride);
+    // second exchange: slot s plays role pair_role(s) in phase 2 and Z[400 - k] sits in the pair lane t ^ 1 (on the
+    // device: shfl.xor 1; here: the other thread's register array).  Pairs must not straddle a warp.
+    for (int t = 0; t < nthreads; ++t) {
+        if ((t ^ 1) / 32 != t / 32 || (t ^ 1) / kRadix != t / kRadix) { printf("pair lanes straddle at %d\n", t); return 5; }
+        const int s = t % kRadix;
+        if (pair_slot(pair_role(s)) != s) { printf("pair_slot is not the inverse of pair_role at %d\n", s); return 5; }
+        if (s >= 2 && pair_role(s) + pair_role(s ^ 1) != 20) { printf("lanes %d and %d are not partners\n", s, s ^ 1); return 5; }
     }
     for (int t = 0; t < nthreads; ++t) {
         int g = t / kRadix;
         float2 v[20];
         for (int i = 0; i < 20; ++i) v[i] = regs[t][i];
-        stft_split_store<true, true>(v, zup.data(), g, t % kRadix, &out2[(2 * g) * kBins * 2], &out2[(2 * g + 1) * kBins * 2],
-                                     kGroupStride);
+        const std::vector<float2>& pv = regs[t ^ 1];
+        stft_split_store_pair(v, t % kRadix, &out2[(2 * g) * kBins * 2], &out2[(2 * g + 1) * kBins * 2], true, true,
+                              [&](float2, int idx) { return pv[idx]; });
+    }
+    // the fbank front-end's variant of the same exchange: |A|^2, |B|^2
+    {
+        std::vector<float> pw(frames * kBins, -1.f);
+        for (int t = 0; t < nthreads; ++t) {
+            int g = t / kRadix;
+            float2 v[20];
+            for (int i = 0; i < 20; ++i) v[i] = regs[t][i];
+            const std::vector<float2>& pv = regs[t ^ 1];
+            stft_split_power_pair(v, t % kRadix, &pw[(2 * g) * kBins], &pw[(2 * g + 1) * kBins],
+                                  [&](float2, int idx) { return pv[idx]; });
+        }
+        for (int f = 0; f < frames; ++f)
+            for (int k = 0; k < kBins; ++k) {
+                const double re = out2[(f * kBins + k) * 2], im = out2[(f * kBins + k) * 2 + 1];
+                if (fabs(re * re + im * im - (double)pw[f * kBins + k]) > 1e-4 * (1.0 + re * re + im * im)) {
+                    printf("power mismatch at frame %d bin %d\n", f, k);
+                    return 6;
+                }
+            }
     }
     // the kernel's phase 1 composes fourteen of its nineteen twiddles from five table entries (twiddle_store): the
     // two variants agree to rounding, not bit for bit
