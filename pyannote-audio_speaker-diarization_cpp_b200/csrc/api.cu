@@ -130,8 +130,9 @@ int sd_ctx_create(int device, sd_ctx** out) {
     if (cudaMalloc(&ctx->d_status, sizeof(int)) != cudaSuccess ||
         cudaMemset(ctx->d_status, 0, sizeof(int)) != cudaSuccess ||
         cudaHostAlloc(&ctx->h_status, sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
-        cudaMalloc(&ctx->d_stats, 16 * sizeof(unsigned long long)) != cudaSuccess ||  // [8], [9]: STFT tile counters
-        cudaMemset(ctx->d_stats, 0, 16 * sizeof(unsigned long long)) != cudaSuccess) {
+        // [8], [9]: STFT tile counters; [16..]: scratch row for the frames past the end of an item (stft400_kernel)
+        cudaMalloc(&ctx->d_stats, (16 + 256) * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(ctx->d_stats, 0, (16 + 256) * sizeof(unsigned long long)) != cudaSuccess) {
         cudaGetLastError();
         sd_ctx_destroy(ctx);
         return SD_ERR_CUDA;

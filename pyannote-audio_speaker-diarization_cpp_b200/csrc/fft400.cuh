@@ -228,25 +228,26 @@ SD_HD constexpr int sig_pad_odd(int n1) { return (20 * n1) / kHop == 0 ? 0 : (20
 // floats needed to stage n samples
 SD_HD constexpr int sig_padded_size(int n) { return sig_pos(n - 1) + 1; }
 
-// Twiddle table layout.  A row of 20 float2 does not fit the 16 eight-byte banks: in a half-warp that holds
-// lanes r = a..19 of one group and r' = 0..a-5 of the next, roles 16..19 would alias roles 0..3.  So roles 0..15
-// read T0[k1*16 + r] and roles 16..19 read one of four copies T1[k1*16 + 4c + (r-16)], c = (a-4)/4, placed on
-// exactly the four banks their half-warp leaves free.  kTwRow = 16 for both, so each thread just keeps a base
-// pointer and indexes it with k1 * kTwRow.
+// Twiddle table layout.  Only the five rows k1 = 1, 2, 4, 8, 16 are stored (twiddle_store composes the rest).  A row
+// of 20 float2 does not fit the 16 eight-byte banks: in a half-warp that holds lanes r = a..19 of one group and
+// r' = 0..a-5 of the next, roles 16..19 would alias roles 0..3.  So roles 0..15 read T0[row*16 + r] and roles 16..19
+// read one of four copies T1[row*16 + 4c + (r-16)], c = (a-4)/4, placed on exactly the four banks their half-warp
+// leaves free.  kTwRow = 16 for both, so each thread just keeps a base pointer and indexes it with row * kTwRow.
 constexpr int kTwRow = 16;
-constexpr int kTwTableUnits = 2 * 20 * kTwRow;  // T0 then T1
+constexpr int kTwRows = 5;                            // row j holds k1 = 1 << j
+constexpr int kTwTableUnits = 2 * kTwRows * kTwRow;   // T0 then T1: 160 float2 = 1 280 bytes
 SD_HD int tw_thread_offset(int tid) {  // float2 units from the start of the table for thread `tid` of the CTA
     const int g = tid / kRadix, r = tid - g * kRadix;
     if (r < 16) return r;
     const int a = 16 * (tid >> 4) - 20 * g;  // first role of this group inside the thread's half-warp (4, 8, 12, 16)
-    return 20 * kTwRow + (a - 4) + (r - 16);
+    return kTwRows * kTwRow + (a - 4) + (r - 16);
 }
 // fills the table from tw[r*20 + k1] = exp(-2 pi i r k1 / 400); entry index e in [0, kTwTableUnits)
 SD_HD int tw_table_source(int e) {  // returns r*20 + k1 of the value stored at table entry e
-    const int half = e / (20 * kTwRow), rem = e - half * 20 * kTwRow;
-    const int k1 = rem / kTwRow, c = rem - k1 * kTwRow;
+    const int half = e / (kTwRows * kTwRow), rem = e - half * kTwRows * kTwRow;
+    const int row = rem / kTwRow, c = rem - row * kTwRow;
     const int r = half == 0 ? c : 16 + (c & 3);
-    return r * 20 + k1;
+    return r * 20 + (1 << row);
 }
 
 // Multiply the phase-1 outputs by W400^(r*k1), k1 = 0..19, and write them to the transpose buffer.
@@ -255,26 +256,18 @@ SD_HD int tw_table_source(int e) {  // returns r*20 + k1 of the value stored at 
 // ~2e-7 relative, far inside the 1e-4 bar): 5 instead of 19 eight-byte shared loads per thread and tile.
 // Each product is formed when its bin is reached, while the registers of the bins already stored are free again.
 SD_HD void twiddle_store(const float2 (&v)[20], const float2* twp, float2* dst) {
-#if defined(SD_TWIDDLE_TABLE_ONLY)
-#pragma unroll
-    for (int k1 = 0; k1 < 20; ++k1) {
-        float2 y = v[dft20_slot(k1)];
-        if (k1 > 0) y = cmul(y, twp[k1 * kTwRow]);
-        dst[pair_slot(k1) * kXchgRow] = y;
-    }
-#else
     dst[pair_slot(0) * kXchgRow] = v[dft20_slot(0)];
-    const float2 t1 = twp[1 * kTwRow], t2 = twp[2 * kTwRow];
+    const float2 t1 = twp[0 * kTwRow], t2 = twp[1 * kTwRow];
     const float2 t3 = cmul(t1, t2);
     dst[pair_slot(1) * kXchgRow] = cmul(v[dft20_slot(1)], t1);
     dst[pair_slot(2) * kXchgRow] = cmul(v[dft20_slot(2)], t2);
     dst[pair_slot(3) * kXchgRow] = cmul(v[dft20_slot(3)], t3);
-    const float2 t4 = twp[4 * kTwRow];
+    const float2 t4 = twp[2 * kTwRow];
     dst[pair_slot(4) * kXchgRow] = cmul(v[dft20_slot(4)], t4);
     dst[pair_slot(5) * kXchgRow] = cmul(v[dft20_slot(5)], cmul(t4, t1));
     dst[pair_slot(6) * kXchgRow] = cmul(v[dft20_slot(6)], cmul(t4, t2));
     dst[pair_slot(7) * kXchgRow] = cmul(v[dft20_slot(7)], cmul(t4, t3));
-    const float2 t8 = twp[8 * kTwRow];
+    const float2 t8 = twp[3 * kTwRow];
     const float2 t12 = cmul(t8, t4);
     dst[pair_slot(8) * kXchgRow] = cmul(v[dft20_slot(8)], t8);
     dst[pair_slot(9) * kXchgRow] = cmul(v[dft20_slot(9)], cmul(t8, t1));
@@ -284,12 +277,11 @@ SD_HD void twiddle_store(const float2 (&v)[20], const float2* twp, float2* dst) 
     dst[pair_slot(13) * kXchgRow] = cmul(v[dft20_slot(13)], cmul(t12, t1));
     dst[pair_slot(14) * kXchgRow] = cmul(v[dft20_slot(14)], cmul(t12, t2));
     dst[pair_slot(15) * kXchgRow] = cmul(v[dft20_slot(15)], cmul(t12, t3));
-    const float2 t16 = twp[16 * kTwRow];
+    const float2 t16 = twp[4 * kTwRow];
     dst[pair_slot(16) * kXchgRow] = cmul(v[dft20_slot(16)], t16);
     dst[pair_slot(17) * kXchgRow] = cmul(v[dft20_slot(17)], cmul(t16, t1));
     dst[pair_slot(18) * kXchgRow] = cmul(v[dft20_slot(18)], cmul(t16, t2));
     dst[pair_slot(19) * kXchgRow] = cmul(v[dft20_slot(19)], cmul(t16, t3));
-#endif
 }
 
 // phase 1 with the window (wtab[20*n1 + r]) in a shared table and the twiddles behind a per-thread base pointer
@@ -514,30 +506,30 @@ SD_HD void stft_split_store(const float2 (&v)[20], const float2* zup, int g, int
 // ---- second exchange between pair lanes -------------------------------------------------------------------
 // Slot s (role k1 = pair_role(s)) owns bins k = k1 + 20 m, m = 0..9 (plus k = 200 for role 0).  Z[400 - k] is the
 // pair lane's k2 = 19 - m value -- the same register index on both sides, so both lanes send v[dft20_slot(19 - m)] and
-// receive the other's.  `partner(value, index)` returns the pair lane's v[index]: a shfl.xor(1) on the device, an array
-// access in the host emulation.  Roles 0 and 10 are their own partners (role 0: Z[400 - 20 m] = own k2 = 20 - m).
+// receive the other's.  Roles 0 and 10 are their own partners: role 10 needs its own k2 = 19 - m value, role 0 its own
+// k2 = 20 - m (Z[400 - 20 m]); both "receive from themselves" (role 0 after selecting the other register).
+// `partner(mine, index)` returns `mine` in the self-paired slots (s < 2) and the pair lane's v[index] otherwise: one
+// indexed shuffle on the device (source lane = own lane or lane ^ 1), an array access in the host emulation.
 // Spectrum scaled by 1/2 (folded into the window): A[k] = Z[k] + conj Z[400-k], B[k] = -i (Z[k] - conj Z[400-k]).
-// okA / okB: whether the frame exists (predicated stores: the exchange itself must run in every lane).
+// outA / outB must both be writable (frames past the end of the item go to a scratch row): the exchange has to run in
+// every lane, and unconditional stores keep the loop free of branches.
 template <typename Partner>
-SD_HD void stft_split_store_pair(const float2 (&v)[20], int s, float* outA, float* outB, bool okA, bool okB,
-                                 Partner partner) {
+SD_HD void stft_split_store_pair(const float2 (&v)[20], int s, float* outA, float* outB, Partner partner) {
     const int k1 = pair_role(s);
     float2* oa = reinterpret_cast<float2*>(outA);
     float2* ob = reinterpret_cast<float2*>(outB);
 #pragma unroll
     for (int m = 0; m < 10; ++m) {
         const float2 a = v[dft20_slot(m)];
-        const float2 mine = v[dft20_slot(19 - m)];
-        float2 b = partner(mine, dft20_slot(19 - m));
-        if (s == 1) b = mine;
-        if (s == 0) b = v[dft20_slot((20 - m) % 20)];
-        if (okA) oa[k1 + 20 * m] = split_a(a, b);
-        if (okB) ob[k1 + 20 * m] = split_b(a, b);
+        const float2 mine = s == 0 ? v[dft20_slot((20 - m) % 20)] : v[dft20_slot(19 - m)];
+        const float2 b = partner(mine, dft20_slot(19 - m));
+        oa[k1 + 20 * m] = split_a(a, b);
+        ob[k1 + 20 * m] = split_b(a, b);
     }
     if (s == 0) {  // k = 200: partner of Z[200] is itself
         const float2 a = v[dft20_slot(10)];
-        if (okA) oa[200] = make_float2(a.x + a.x, 0.f);
-        if (okB) ob[200] = make_float2(a.y + a.y, 0.f);
+        oa[200] = make_float2(a.x + a.x, 0.f);
+        ob[200] = make_float2(a.y + a.y, 0.f);
     }
 }
 
@@ -548,10 +540,8 @@ SD_HD void stft_split_power_pair(const float2 (&v)[20], int s, float* pa, float*
 #pragma unroll
     for (int m = 0; m < 10; ++m) {
         const float2 a = v[dft20_slot(m)];
-        const float2 mine = v[dft20_slot(19 - m)];
-        float2 c = partner(mine, dft20_slot(19 - m));
-        if (s == 1) c = mine;
-        if (s == 0) c = v[dft20_slot((20 - m) % 20)];
+        const float2 mine = s == 0 ? v[dft20_slot((20 - m) % 20)] : v[dft20_slot(19 - m)];
+        const float2 c = partner(mine, dft20_slot(19 - m));
         const float ar = a.x + c.x, ai = a.y - c.y, br = a.y + c.y, bi = c.x - a.x;
         pa[k1 + 20 * m] = ar * ar + ai * ai;
         pb[k1 + 20 * m] = br * br + bi * bi;
@@ -564,9 +554,14 @@ SD_HD void stft_split_power_pair(const float2 (&v)[20], int s, float* pa, float*
 }
 
 #if defined(__CUDACC__)
-struct PairShuffle {  // the pair lane's copy of a register, through the warp
+struct PairShuffle {  // the pair lane's copy of a register through the warp; self-paired slots read their own lane
+    int src;
+    __device__ __forceinline__ explicit PairShuffle(int s) {
+        const int lane = (int)(threadIdx.x & 31);
+        src = s < 2 ? lane : lane ^ 1;
+    }
     __device__ __forceinline__ float2 operator()(float2 mine, int) const {
-        return make_float2(__shfl_xor_sync(0xffffffffu, mine.x, 1), __shfl_xor_sync(0xffffffffu, mine.y, 1));
+        return make_float2(__shfl_sync(0xffffffffu, mine.x, src), __shfl_sync(0xffffffffu, mine.y, src));
     }
 };
 #endif

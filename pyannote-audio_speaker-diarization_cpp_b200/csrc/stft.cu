@@ -31,8 +31,10 @@ struct StftCfg {
                                            kTwTableUnits * sizeof(float2);
     // fbank kernel: the upper-spectrum buffer shares storage with the staged samples (dead after phase 1)
     static constexpr size_t kSmemBytes = (kSigBytes > kZBytes ? kSigBytes : kZBytes) + kTablesBytes;
-    // STFT kernel: the upper spectrum goes into the (dead) transpose buffer, the sample buffer is not aliased
+    // STFT kernel: nothing aliases the sample buffer (the next tile's samples land while phase 2 runs); the variant
+    // that computes the Hamming window in registers has no window table: 41.1 KB, five CTAs per SM fit
     static constexpr size_t kSmemBytesStft = kSigBytes + kTablesBytes;
+    static constexpr size_t kSmemBytesStftNoWindow = kSmemBytesStft - kNfft * sizeof(wtab_t);
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -67,11 +69,9 @@ __device__ __forceinline__ float edge_sample(const float* __restrict__ src, long
 // the tile (item index t0*hop - lead + j) goes to sig[sig_pos(j)].  Out-of-range samples are zeros or the
 // mirrored signal (FrameGeom).  16-byte pieces never straddle a hop boundary.
 template <int GROUPS>
-__device__ __forceinline__ void stage_tile(float* sig, const float* __restrict__ wav, int L, long tile,
-                                           int tiles_per_item, bool aligned16, FrameGeom fg) {
+__device__ __forceinline__ void stage_tile(float* sig, const float* __restrict__ wav, int L, int b, int ti,
+                                           bool aligned16, FrameGeom fg) {
     using Cfg = StftCfg<GROUPS>;
-    const int b = (int)(tile / tiles_per_item);
-    const int ti = (int)(tile - (long)b * tiles_per_item);
     const long s0 = (long)ti * Cfg::kTileFrames * kHop - fg.lead;
     const float* src = wav + (size_t)b * L;
     if (aligned16) {
@@ -160,15 +160,18 @@ template <int GROUPS, int MINB, bool KALDI, bool HAMMING>
 __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     stft400_kernel(const float* __restrict__ wav, float* __restrict__ out, int L, int T, int tiles_per_item,
                    long total_tiles, const float* __restrict__ window, const float2* __restrict__ twiddle,
-                   int aligned16, FrameGeom fg, KaldiArgs ka, unsigned long long* __restrict__ tile_ctr) {
+                   int aligned16, FrameGeom fg, KaldiArgs ka, unsigned long long* __restrict__ tile_ctr,
+                   float* __restrict__ dump) {
     using Cfg = StftCfg<GROUPS>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* xbuf = reinterpret_cast<float2*>(smem_raw);                 // phase 1 -> phase 2 transpose
     float2* twT = xbuf + GROUPS * kGroupStride;                         // twiddle table (see tw_thread_offset)
-    wtab_t* wtab = reinterpret_cast<wtab_t*>(twT + kTwTableUnits);      // window, pre-scaled by 1/2
-    float* sig = reinterpret_cast<float*>(wtab + kNfft);                // padded samples of the tile
+    wtab_t* wtab = reinterpret_cast<wtab_t*>(twT + kTwTableUnits);      // window, pre-scaled by 1/2 (not with HAMMING)
+    float* sig = reinterpret_cast<float*>(wtab + (HAMMING ? 0 : kNfft));  // padded samples of the tile
     __shared__ __align__(8) uint64_t bar;
-    __shared__ long s_next;
+    // the next tile, worked out by thread 0 only (64-bit division and the interior test cost ~100 instructions, which
+    // every thread used to spend per tile): item, tile of the item, >= 0 when there is one; bulk-fetched or not
+    __shared__ int s_next_b, s_next_ti, s_next_fetched;
     __shared__ float2 dc_part[KALDI ? GROUPS * kRadix : 1];
 
     // Tiles are handed out dynamically: the first one is the CTA's own index, every further one comes from a global
@@ -182,10 +185,12 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     if (threadIdx.x == 0) nxt_raw = atomicAdd(tile_ctr, 1ull);
     const int g = threadIdx.x / kRadix;
     const int r = threadIdx.x - g * kRadix;
+    const PairShuffle pair_lane(r);
     float ham_c, ham_s;  // (cos, sin)(2 pi r / 400) for the table-free Hamming window
     sincospif((float)r * (1.0f / 200.0f), &ham_s, &ham_c);
-    for (int i = threadIdx.x; i < kNfft; i += Cfg::kThreads)
-        wtab[i] = wtab_make(0.5f * window[i]);  // exact scaling; lets phase 3 drop its multiplications
+    if (!HAMMING)
+        for (int i = threadIdx.x; i < kNfft; i += Cfg::kThreads)
+            wtab[i] = wtab_make(0.5f * window[i]);  // exact scaling; lets phase 3 drop its multiplications
     for (int e = threadIdx.x; e < kTwTableUnits; e += Cfg::kThreads) twT[e] = twiddle[tw_table_source(e)];
     const float2* twp = twT + tw_thread_offset(threadIdx.x);
     if (threadIdx.x == 0) {
@@ -196,14 +201,11 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
 
     // A tile is "interior" when all its samples exist: it is then fetched by one thread with bulk (TMA) copies,
     // one per hop-sized segment (the padded layout), completing on an mbarrier.
-    auto interior = [&](long tile) -> bool {
-        const int ti = (int)(tile % tiles_per_item);
+    auto interior = [&](int ti) -> bool {
         const long s0 = (long)ti * Cfg::kTileFrames * kHop - fg.lead;
         return aligned16 && s0 >= 0 && s0 + Cfg::kSigFloats <= L;
     };
-    auto issue_bulk = [&](long tile) {  // thread 0 only
-        const int b = (int)(tile / tiles_per_item);
-        const int ti = (int)(tile - (long)b * tiles_per_item);
+    auto issue_bulk = [&](int b, int ti) {  // thread 0 only
         const long s0 = (long)ti * Cfg::kTileFrames * kHop - fg.lead;
         const float* src = wav + (size_t)b * L + s0;
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // earlier generic reads of sig vs async writes
@@ -219,20 +221,24 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     // kernel's issued instructions were try_wait / branch / yield); the others learn about the arrival through the
     // block barrier that follows, which is the barrier the tile loop needs anyway.
     unsigned parity = 0;
-    long tile = blockIdx.x;
+    int b = -1, ti = 0;  // current tile: item and tile of the item (b < 0: none left)
     bool fetched = false;
-    if (tile < total_tiles && interior(tile)) {
-        if (threadIdx.x == 0) {
-            issue_bulk(tile);
-            mbar_wait(&bar, parity);
+    if ((long)blockIdx.x < total_tiles) {
+        b = (int)(blockIdx.x / (unsigned)tiles_per_item);
+        ti = (int)(blockIdx.x - (unsigned)b * (unsigned)tiles_per_item);
+        if (interior(ti)) {
+            if (threadIdx.x == 0) {
+                issue_bulk(b, ti);
+                mbar_wait(&bar, parity);
+            }
+            parity ^= 1;
+            fetched = true;
+            __syncthreads();
         }
-        parity ^= 1;
-        fetched = true;
-        __syncthreads();
     }
-    while (tile < total_tiles) {
+    while (b >= 0) {
         if (!fetched) {
-            stage_tile<GROUPS>(sig, wav, L, tile, tiles_per_item, aligned16 != 0, fg);
+            stage_tile<GROUPS>(sig, wav, L, b, ti, aligned16 != 0, fg);
             cp_async_commit();
             cp_async_wait<0>();
             __syncthreads();
@@ -249,29 +255,49 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
                           // under the shadow of phase 2 and the stores
         bool wait_next = false;  // thread 0: a bulk load is in flight
         if (threadIdx.x == 0) {
-            const long nxt = (long)gridDim.x + (long)nxt_raw;
-            s_next = nxt;  // read by everybody after the barrier at the end of the tile
-            wait_next = nxt < total_tiles && interior(nxt);
-            if (wait_next) issue_bulk(nxt);
+            const unsigned long long nxt = (unsigned long long)gridDim.x + nxt_raw;
+            int nb = -1, nti = 0;
+            if (nxt < (unsigned long long)total_tiles) {  // total_tiles < 2^31 (checked at launch): 32-bit division
+                nb = (int)((unsigned)nxt / (unsigned)tiles_per_item);
+                nti = (int)((unsigned)nxt - (unsigned)nb * (unsigned)tiles_per_item);
+                wait_next = interior(nti);
+                if (wait_next) issue_bulk(nb, nti);
+            }
+            s_next_b = nb;  // read by everybody after the barrier at the end of the tile
+            s_next_ti = nti;
+            s_next_fetched = wait_next;
             nxt_raw = atomicAdd(tile_ctr, 1ull);  // used one iteration from now
         }
         float2 v[20];
         stft_phase2_load(xbuf, g, r, v);  // slot r plays role pair_role(r) from here on
+#if defined(SD_STFT_BARRIER_EARLY)
+        __syncthreads();  // every phase-2 load of the transpose buffer is issued and consumed (dft20 ran): the next
+                          // tile's phase 1 may overwrite it; the next tile's coordinates are visible
+#endif
 
         // The real-pair split: Z[400 - k] lives in the adjacent lane (fft400.cuh), so the second exchange is a
         // shuffle -- no shared-memory round trip and no block barrier around it (two barriers per tile instead of four).
-        const int b = (int)(tile / tiles_per_item);
-        const int ti = (int)(tile - (long)b * tiles_per_item);
         const int tA = ti * Cfg::kTileFrames + 2 * g;
-        float* rowA = out + ((size_t)b * T + tA) * (kBins * 2);
-        stft_split_store_pair(v, r, rowA, rowA + kBins * 2, tA < T, tA + 1 < T, PairShuffle());
+        float* rowA = tA < T ? out + ((size_t)b * T + tA) * (kBins * 2) : dump;  // frames past the item's end: scratch row
+        float* rowB = tA + 1 < T ? out + ((size_t)b * T + tA + 1) * (kBins * 2) : dump;
+        stft_split_store_pair(v, r, rowA, rowB, pair_lane);
+#if defined(SD_STFT_BARRIER_EARLY)
+        b = s_next_b;  // (rewritten only after the next tile's first barrier)
+        ti = s_next_ti;
+        fetched = s_next_fetched != 0;
+        if (fetched) {  // every thread checks the arrival itself: the samples were requested a whole phase ago
+            mbar_wait(&bar, parity);
+            parity ^= 1;
+        }
+#else
         if (wait_next) mbar_wait(&bar, parity);  // thread 0: the next tile's samples have landed
         __syncthreads();  // every phase-2 load of the transpose buffer is done: the next tile's phase 1 may overwrite
-                          // it; s_next and the landed samples are visible to everybody
-        const long next = s_next;  // (rewritten only after the next tile's first barrier)
-        fetched = next < total_tiles && interior(next);
+                          // it; the next tile's coordinates and its landed samples are visible to everybody
+        b = s_next_b;  // (rewritten only after the next tile's first barrier)
+        ti = s_next_ti;
+        fetched = s_next_fetched != 0;
         if (fetched) parity ^= 1;
-        tile = next;
+#endif
     }
     // the last CTA to leave zeroes the counters for the next launch on this context (launches of a context are
     // stream-ordered; contexts do not share counters)
@@ -381,7 +407,7 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     }
     for (; tile < total_tiles; tile += gridDim.x) {
         if (!fetched) {
-            stage_tile<GROUPS>(sig, wav, L, tile, tiles_per_item, aligned16 != 0, fg);
+            stage_tile<GROUPS>(sig, wav, L, (int)(tile / tiles_per_item), (int)(tile % tiles_per_item), aligned16 != 0, fg);
             cp_async_commit();
             cp_async_wait<0>();
             __syncthreads();
@@ -403,7 +429,7 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
         __syncthreads();  // xbuf is dead from here: it receives the power spectra
 
         // |X|^2 of both frames of the pair into pw[frame][bin]; Z[400 - k] comes from the adjacent lane (fft400.cuh)
-        stft_split_power_pair(v, r, pw + (2 * g) * kBins, pw + (2 * g + 1) * kBins, PairShuffle());
+        stft_split_power_pair(v, r, pw + (2 * g) * kBins, pw + (2 * g + 1) * kBins, PairShuffle(r));
         __syncthreads();  // power spectra complete
 
         // mel projection + dB.  Thread -> one mel filter and one half of the tile's frames: the filter's weights are
@@ -585,19 +611,20 @@ static bool kaldi_conditioning(const sd_stft_params* p) { return p->preemph != 0
 template <int GROUPS, int MINB, bool KALDI, bool HAMMING>
 static int launch_cfg(sd_ctx* ctx, const float* d_wav, int B, int L, int T, float* d_out, FrameGeom fg, KaldiArgs ka) {
     using Cfg = StftCfg<GROUPS>;
-    const int blocks_per_sm = kernel_setup(ctx, stft400_kernel<GROUPS, MINB, KALDI, HAMMING>, (int)Cfg::kSmemBytesStft,
-                                           Cfg::kThreads, Cfg::kSmemBytesStft);
+    const size_t smem = HAMMING ? Cfg::kSmemBytesStftNoWindow : Cfg::kSmemBytesStft;
+    const int blocks_per_sm = kernel_setup(ctx, stft400_kernel<GROUPS, MINB, KALDI, HAMMING>, (int)smem, Cfg::kThreads, smem);
     if (blocks_per_sm < 0) return SD_ERR_CUDA;
     const int tiles_per_item = (T + Cfg::kTileFrames - 1) / Cfg::kTileFrames;
     const long total = (long)B * tiles_per_item;
+    if (total >= (1l << 31)) return ctx->fail(SD_ERR_INVALID, "sd_stft: %ld tiles in one call (limit 2^31)", total);
     // stft_waves > 1: that many CTAs per resident slot, each looping over proportionally fewer tiles, so that slots
     // are handed back every 1 / waves of the kernel instead of at its end (other streams' small kernels get in)
     long grid = (long)ctx->num_sms * blocks_per_sm * (ctx->stft_waves > 1 ? ctx->stft_waves : 1);
     if (grid > total) grid = total;
     const int aligned = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_wav) & 15) == 0);
-    stft400_kernel<GROUPS, MINB, KALDI, HAMMING><<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytesStft, ctx->stream>>>(
+    stft400_kernel<GROUPS, MINB, KALDI, HAMMING><<<(unsigned)grid, Cfg::kThreads, smem, ctx->stream>>>(
         d_wav, d_out, L, T, tiles_per_item, total, ctx->d_window, reinterpret_cast<const float2*>(ctx->d_twiddle),
-        aligned, fg, ka, ctx->d_stats + 8);
+        aligned, fg, ka, ctx->d_stats + 8, reinterpret_cast<float*>(ctx->d_stats + 16));
     SD_LAUNCH_CHECK(ctx);
     return SD_OK;
 }
@@ -624,6 +651,8 @@ int stft_launch(sd_ctx* ctx, const float* d_wav, int B, int L, const sd_stft_par
         rc = launch_cfg<8, 3, true, false>(ctx, d_wav, B, L, T, d_out, fg, ka);
     else if (ctx->stft_variant == 1)
         rc = launch_cfg<8, 3, false, false>(ctx, d_wav, B, L, T, d_out, fg, ka);
+    else if (hamming && ctx->stft_variant == 3)  // five CTAs per SM: 72 registers, 40 bytes of spills
+        rc = launch_cfg<8, 5, false, true>(ctx, d_wav, B, L, T, d_out, fg, ka);
     else if (hamming)
         rc = launch_cfg<8, 4, false, true>(ctx, d_wav, B, L, T, d_out, fg, ka);
     else

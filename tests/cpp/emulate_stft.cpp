@@ -95,8 +95,8 @@ int main() {
         float2 v[20];
         for (int i = 0; i < 20; ++i) v[i] = regs[t][i];
         const std::vector<float2>& pv = regs[t ^ 1];
-        stft_split_store_pair(v, t % kRadix, &out2[(2 * g) * kBins * 2], &out2[(2 * g + 1) * kBins * 2], true, true,
-                              [&](float2, int idx) { return pv[idx]; });
+        stft_split_store_pair(v, t % kRadix, &out2[(2 * g) * kBins * 2], &out2[(2 * g + 1) * kBins * 2],
+                              [&](float2 mine, int idx) { return t % kRadix < 2 ? mine : pv[idx]; });
     }
     // the fbank front-end's variant of the same exchange: |A|^2, |B|^2
     {
@@ -107,7 +107,7 @@ int main() {
             for (int i = 0; i < 20; ++i) v[i] = regs[t][i];
             const std::vector<float2>& pv = regs[t ^ 1];
             stft_split_power_pair(v, t % kRadix, &pw[(2 * g) * kBins], &pw[(2 * g + 1) * kBins],
-                                  [&](float2, int idx) { return pv[idx]; });
+                                  [&](float2 mine, int idx) { return t % kRadix < 2 ? mine : pv[idx]; });
         }
         for (int f = 0; f < frames; ++f)
             for (int k = 0; k < kBins; ++k) {
