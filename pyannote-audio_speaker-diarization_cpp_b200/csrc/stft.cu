@@ -644,17 +644,21 @@ int stft_launch(sd_ctx* ctx, const float* d_wav, int B, int L, const sd_stft_par
     if (T < 1) return ctx->fail(SD_ERR_INVALID, "sd_stft: %d samples give no frame in this frame_mode", L);
     if (fg.reflect && L < kNfft) return ctx->fail(SD_ERR_INVALID, "sd_stft: reflection needs at least n_fft samples");
     const KaldiArgs ka{p->preemph, p->remove_dc_offset};
-    // stft_variant (tuning hook): 0 = Hamming window in registers when the window is the reference's, 4 CTAs/SM;
-    // 1 = 3 CTAs/SM; 2 = always the window table
-    const bool hamming = p->window_kind == SD_WINDOW_HAMMING_PERIODIC && ctx->stft_variant != 2;
+    // stft_variant (tuning hook): 0 = the reference's Hamming window computed in registers, five CTAs per SM (72
+    // registers, 24 bytes of spills: 0.773 ms per 1 773-item launch against 0.786 ms with four CTAs at 96 registers);
+    // 1 = window table, 3 CTAs/SM; 2 = window table, 4 CTAs/SM; 4 = register window, 4 CTAs/SM; 5 = register window,
+    // 8-frame tiles in 80-thread CTAs
+    const bool hamming = p->window_kind == SD_WINDOW_HAMMING_PERIODIC && ctx->stft_variant != 2 && ctx->stft_variant != 1;
     if (kaldi_conditioning(p))
         rc = launch_cfg<8, 3, true, false>(ctx, d_wav, B, L, T, d_out, fg, ka);
     else if (ctx->stft_variant == 1)
         rc = launch_cfg<8, 3, false, false>(ctx, d_wav, B, L, T, d_out, fg, ka);
-    else if (hamming && ctx->stft_variant == 3)  // five CTAs per SM: 72 registers, 40 bytes of spills
-        rc = launch_cfg<8, 5, false, true>(ctx, d_wav, B, L, T, d_out, fg, ka);
-    else if (hamming)
+    else if (hamming && ctx->stft_variant == 4)
         rc = launch_cfg<8, 4, false, true>(ctx, d_wav, B, L, T, d_out, fg, ka);
+    else if (hamming && ctx->stft_variant == 5)
+        rc = launch_cfg<4, 9, false, true>(ctx, d_wav, B, L, T, d_out, fg, ka);
+    else if (hamming)
+        rc = launch_cfg<8, 5, false, true>(ctx, d_wav, B, L, T, d_out, fg, ka);
     else
         rc = launch_cfg<8, 4, false, false>(ctx, d_wav, B, L, T, d_out, fg, ka);
     if (rc) return rc;

@@ -37,6 +37,25 @@ def test_stft_vs_oracle(ctx, oracle, synth, B, L):
     assert np.abs(got - want).max() < STFT_TOL
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 5])
+def test_stft_kernel_variants_agree(pkg, oracle, synth, variant):
+    """SD_OPT_STFT_VARIANT selects other builds of the kernel (CTAs per SM, window table or registers, 8-frame tiles):
+    each one against the oracle, ragged lengths included (edge tiles, last tile of an item, scratch-row frames), and
+    again after a second launch on the same context (the tile counter must have been reset by the first)."""
+    c = pkg.Context(0)
+    try:
+        c.set_option(3, variant)
+        for B, L in ((37, 16000), (3, 80000), (2, 16003), (1, 400), (150, 4800)):
+            wav = synth.fbank_items(B + L + variant, B, L)
+            want = oracle.stft(wav)
+            for _ in range(2):
+                got = c.stft(wav)
+                assert got.shape == want.shape
+                assert np.abs(got - want).max() < STFT_TOL, (variant, B, L)
+    finally:
+        c.close()
+
+
 def test_stft_edge_signals(ctx, oracle):
     L = 8000
     wav = np.zeros((4, L), np.float32)
