@@ -343,7 +343,7 @@ def run_product(args, rank, world):
 
     # ---- e2e: the same batch API with HOST pointers (pinned buffers): every step copies each file's inputs to the
     # device and brings every result back, the files in flight overlapping their copies and kernels
-    e2e_files = min(nfiles, 3 if world == 1 else 2)  # 4 GB of pinned host memory per file in flight and rank
+    e2e_files = min(nfiles, int(os.environ.get("SDB_E2E_FILES", 3 if world == 1 else 2)))  # 4 GB of pinned host memory each
     hosts, keep = [], []
     for k in range(e2e_files):
         j = jobs[k]

@@ -344,7 +344,11 @@ SD_HD void stft_phase1_hamming(const float* sig, int fa_off, int fb_off, float c
 #pragma unroll
     for (int n1 = 0; n1 < 20; ++n1) {
         const float w = fmaf(K1[n1], cr, fmaf(K2[n1], sr, 0.27f));
+#if defined(SD_PACKED_F32) && defined(SD_WINDOW_MUL2)
+        v[n1] = mul2(make_float2(a[n1], n1 < 12 ? a[n1 + 8] : b[n1 - 12]), w, w);
+#else
         v[n1] = make_float2(a[n1] * w, (n1 < 12 ? a[n1 + 8] : b[n1 - 12]) * w);
+#endif
     }
     dft20(v);
     twiddle_store(v, twp, xchg + g * kGroupStride + r);

@@ -156,8 +156,17 @@ __device__ __forceinline__ float2 frame_dc_offsets(const float* sig, int g, int 
 
 // KALDI: per-frame pre-emphasis / DC removal (table window).  HAMMING: the reference's periodic Hamming window computed
 // in registers instead of read from the shared table (only without KALDI).
+// registers per thread that let MINB CTAs of GROUPS * 20 threads share an SM (64 K registers, allocated per warp in
+// units of 8 per thread); given to ptxas as __maxnreg__ because with a minimum-blocks launch bound it stops at 72 for
+// five CTAs although 80 fit
+constexpr int stft_max_regs(int groups, int minb) {
+    const int warps = (groups * kRadix + 31) / 32;
+    const int r = 65536 / (minb * warps * 32) / 8 * 8;
+    return r > 255 ? 255 : r;
+}
+
 template <int GROUPS, int MINB, bool KALDI, bool HAMMING>
-__global__ void __launch_bounds__(GROUPS* kRadix, MINB)
+__global__ void __launch_bounds__(GROUPS* kRadix) __maxnreg__(stft_max_regs(GROUPS, MINB))
     stft400_kernel(const float* __restrict__ wav, float* __restrict__ out, int L, int T, int tiles_per_item,
                    long total_tiles, const float* __restrict__ window, const float2* __restrict__ twiddle,
                    int aligned16, FrameGeom fg, KaldiArgs ka, unsigned long long* __restrict__ tile_ctr,
@@ -205,17 +214,23 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
         const long s0 = (long)ti * Cfg::kTileFrames * kHop - fg.lead;
         return aligned16 && s0 >= 0 && s0 + Cfg::kSigFloats <= L;
     };
-    auto issue_bulk = [&](int b, int ti) {  // thread 0 only
+    // Bulk (TMA) copies of a tile: lane 0 of warp 0 announces the bytes on the mbarrier, then lane j issues the copy
+    // of hop segment j -- one warp instruction instead of an 18-iteration loop in thread 0, whose warp every other
+    // warp of the CTA would wait for at the end-of-tile barrier.  Call with all lanes of warp 0.
+    auto issue_bulk = [&](int b, int ti) {
+        const int lane = (int)threadIdx.x;
         const long s0 = (long)ti * Cfg::kTileFrames * kHop - fg.lead;
         const float* src = wav + (size_t)b * L + s0;
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // earlier generic reads of sig vs async writes
-        mbar_expect_tx(&bar, Cfg::kSigFloats * sizeof(float));
-#pragma unroll 1
-        for (int j = 0; j < Cfg::kSigFloats; j += kHop) {
+        if (lane == 0) mbar_expect_tx(&bar, Cfg::kSigFloats * sizeof(float));
+        __syncwarp();
+        const int j = lane * kHop;
+        if (j < Cfg::kSigFloats) {
             const int n = (Cfg::kSigFloats - j) < kHop ? (Cfg::kSigFloats - j) : kHop;
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // earlier generic reads of sig vs async writes
             bulk_g2s(sig + sig_pos(j), src + j, n * sizeof(float), &bar);
         }
     };
+    static_assert((Cfg::kSigFloats + kHop - 1) / kHop <= 32, "one hop segment per lane of warp 0");
 
     // Only thread 0 polls the mbarrier (a polling warp burns issue slots: with every warp polling, 16 % of the
     // kernel's issued instructions were try_wait / branch / yield); the others learn about the arrival through the
@@ -227,9 +242,9 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
         b = (int)(blockIdx.x / (unsigned)tiles_per_item);
         ti = (int)(blockIdx.x - (unsigned)b * (unsigned)tiles_per_item);
         if (interior(ti)) {
-            if (threadIdx.x == 0) {
+            if (threadIdx.x < 32) {
                 issue_bulk(b, ti);
-                mbar_wait(&bar, parity);
+                if (threadIdx.x == 0) mbar_wait(&bar, parity);
             }
             parity ^= 1;
             fetched = true;
@@ -253,20 +268,24 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
         }
         __syncthreads();  // the transpose is complete and sig is free: the next tile's samples may land already,
                           // under the shadow of phase 2 and the stores
-        bool wait_next = false;  // thread 0: a bulk load is in flight
-        if (threadIdx.x == 0) {
-            const unsigned long long nxt = (unsigned long long)gridDim.x + nxt_raw;
-            int nb = -1, nti = 0;
-            if (nxt < (unsigned long long)total_tiles) {  // total_tiles < 2^31 (checked at launch): 32-bit division
-                nb = (int)((unsigned)nxt / (unsigned)tiles_per_item);
-                nti = (int)((unsigned)nxt - (unsigned)nb * (unsigned)tiles_per_item);
-                wait_next = interior(nti);
-                if (wait_next) issue_bulk(nb, nti);
+        bool wait_next = false;  // warp 0: a bulk load is in flight
+        if (threadIdx.x < 32) {
+            if (threadIdx.x == 0) {
+                int nb = -1, nti = 0;
+                const unsigned long long nxt = (unsigned long long)gridDim.x + nxt_raw;
+                if (nxt < (unsigned long long)total_tiles) {  // total_tiles < 2^31 (checked at launch): 32-bit division
+                    nb = (int)((unsigned)nxt / (unsigned)tiles_per_item);
+                    nti = (int)((unsigned)nxt - (unsigned)nb * (unsigned)tiles_per_item);
+                    wait_next = interior(nti);
+                }
+                s_next_b = nb;  // read by everybody after the barrier at the end of the tile
+                s_next_ti = nti;
+                s_next_fetched = wait_next;
+                nxt_raw = atomicAdd(tile_ctr, 1ull);  // used one iteration from now
             }
-            s_next_b = nb;  // read by everybody after the barrier at the end of the tile
-            s_next_ti = nti;
-            s_next_fetched = wait_next;
-            nxt_raw = atomicAdd(tile_ctr, 1ull);  // used one iteration from now
+            __syncwarp();  // lane 0's shared-memory writes are visible to its warp
+            wait_next = s_next_fetched != 0;
+            if (wait_next) issue_bulk(s_next_b, s_next_ti);
         }
         float2 v[20];
         stft_phase2_load(xbuf, g, r, v);  // slot r plays role pair_role(r) from here on
@@ -290,7 +309,7 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
             parity ^= 1;
         }
 #else
-        if (wait_next) mbar_wait(&bar, parity);  // thread 0: the next tile's samples have landed
+        if (wait_next && threadIdx.x == 0) mbar_wait(&bar, parity);  // the next tile's samples have landed
         __syncthreads();  // every phase-2 load of the transpose buffer is done: the next tile's phase 1 may overwrite
                           // it; the next tile's coordinates and its landed samples are visible to everybody
         b = s_next_b;  // (rewritten only after the next tile's first barrier)
