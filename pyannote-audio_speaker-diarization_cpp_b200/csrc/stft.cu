@@ -35,6 +35,7 @@ struct StftCfg {
     // that computes the Hamming window in registers has no window table: 41.1 KB, five CTAs per SM fit
     static constexpr size_t kSmemBytesStft = kSigBytes + kTablesBytes;
     static constexpr size_t kSmemBytesStftNoWindow = kSmemBytesStft - kNfft * sizeof(wtab_t);
+    static constexpr size_t kSmemBytesStftNoWindow2 = kSmemBytesStftNoWindow + kSigBytes;  // two sample buffers
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -165,7 +166,9 @@ constexpr int stft_max_regs(int groups, int minb) {
     return r > 255 ? 255 : r;
 }
 
-template <int GROUPS, int MINB, bool KALDI, bool HAMMING>
+// DEPTH: sample buffers.  1: the next tile's bulk load is issued once phase 1 has released the buffer and has phase 2 +
+// stores to land; 2: two buffers, the load of tile i + 1 is issued before phase 1 of tile i and has the whole tile.
+template <int GROUPS, int MINB, bool KALDI, bool HAMMING, int DEPTH>
 __global__ void __launch_bounds__(GROUPS* kRadix) __maxnreg__(stft_max_regs(GROUPS, MINB))
     stft400_kernel(const float* __restrict__ wav, float* __restrict__ out, int L, int T, int tiles_per_item,
                    long total_tiles, const float* __restrict__ window, const float2* __restrict__ twiddle,
@@ -176,8 +179,10 @@ __global__ void __launch_bounds__(GROUPS* kRadix) __maxnreg__(stft_max_regs(GROU
     float2* xbuf = reinterpret_cast<float2*>(smem_raw);                 // phase 1 -> phase 2 transpose
     float2* twT = xbuf + GROUPS * kGroupStride;                         // twiddle table (see tw_thread_offset)
     wtab_t* wtab = reinterpret_cast<wtab_t*>(twT + kTwTableUnits);      // window, pre-scaled by 1/2 (not with HAMMING)
-    float* sig = reinterpret_cast<float*>(wtab + (HAMMING ? 0 : kNfft));  // padded samples of the tile
-    __shared__ __align__(8) uint64_t bar;
+    float* sig0 = reinterpret_cast<float*>(wtab + (HAMMING ? 0 : kNfft));  // padded samples of the tile (x DEPTH)
+    constexpr int kSigStride = (int)(Cfg::kSigBytes / sizeof(float));
+    __shared__ __align__(8) uint64_t bar[2];
+    __shared__ int s_plan_b, s_plan_ti, s_plan_fetched;  // warp 0's copy of the next tile (DEPTH 2: known a phase earlier)
     // the next tile, worked out by thread 0 only (64-bit division and the interior test cost ~100 instructions, which
     // every thread used to spend per tile): item, tile of the item, >= 0 when there is one; bulk-fetched or not
     __shared__ int s_next_b, s_next_ti, s_next_fetched;
@@ -203,7 +208,8 @@ __global__ void __launch_bounds__(GROUPS* kRadix) __maxnreg__(stft_max_regs(GROU
     for (int e = threadIdx.x; e < kTwTableUnits; e += Cfg::kThreads) twT[e] = twiddle[tw_table_source(e)];
     const float2* twp = twT + tw_thread_offset(threadIdx.x);
     if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
     }
     __syncthreads();
@@ -217,34 +223,58 @@ __global__ void __launch_bounds__(GROUPS* kRadix) __maxnreg__(stft_max_regs(GROU
     // Bulk (TMA) copies of a tile: lane 0 of warp 0 announces the bytes on the mbarrier, then lane j issues the copy
     // of hop segment j -- one warp instruction instead of an 18-iteration loop in thread 0, whose warp every other
     // warp of the CTA would wait for at the end-of-tile barrier.  Call with all lanes of warp 0.
-    auto issue_bulk = [&](int b, int ti) {
+    auto issue_bulk = [&](int b, int ti, int k) {  // into sample buffer k, completing on bar[k]
         const int lane = (int)threadIdx.x;
         const long s0 = (long)ti * Cfg::kTileFrames * kHop - fg.lead;
         const float* src = wav + (size_t)b * L + s0;
-        if (lane == 0) mbar_expect_tx(&bar, Cfg::kSigFloats * sizeof(float));
+        float* sig = sig0 + k * kSigStride;
+        if (lane == 0) mbar_expect_tx(&bar[k], Cfg::kSigFloats * sizeof(float));
         __syncwarp();
         const int j = lane * kHop;
         if (j < Cfg::kSigFloats) {
             const int n = (Cfg::kSigFloats - j) < kHop ? (Cfg::kSigFloats - j) : kHop;
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // earlier generic reads of sig vs async writes
-            bulk_g2s(sig + sig_pos(j), src + j, n * sizeof(float), &bar);
+            bulk_g2s(sig + sig_pos(j), src + j, n * sizeof(float), &bar[k]);
         }
     };
     static_assert((Cfg::kSigFloats + kHop - 1) / kHop <= 32, "one hop segment per lane of warp 0");
+    // warp 0: work out the next tile (thread 0: counter value fetched one tile ago, 32-bit division, interior test),
+    // start its bulk load into buffer k, and ask the counter for the tile after it
+    auto plan_and_issue = [&](int k) -> bool {
+        if (threadIdx.x == 0) {
+            int nb = -1, nti = 0;
+            bool w = false;
+            const unsigned long long nxt = (unsigned long long)gridDim.x + nxt_raw;
+            if (nxt < (unsigned long long)total_tiles) {  // total_tiles < 2^31 (checked at launch)
+                nb = (int)((unsigned)nxt / (unsigned)tiles_per_item);
+                nti = (int)((unsigned)nxt - (unsigned)nb * (unsigned)tiles_per_item);
+                w = interior(nti);
+            }
+            s_plan_b = nb;
+            s_plan_ti = nti;
+            s_plan_fetched = w;
+            nxt_raw = atomicAdd(tile_ctr, 1ull);  // used one iteration from now
+        }
+        __syncwarp();  // lane 0's shared-memory writes are visible to its warp
+        const bool w = s_plan_fetched != 0;
+        if (w) issue_bulk(s_plan_b, s_plan_ti, k);
+        return w;
+    };
 
     // Only thread 0 polls the mbarrier (a polling warp burns issue slots: with every warp polling, 16 % of the
     // kernel's issued instructions were try_wait / branch / yield); the others learn about the arrival through the
     // block barrier that follows, which is the barrier the tile loop needs anyway.
-    unsigned parity = 0;
-    int b = -1, ti = 0;  // current tile: item and tile of the item (b < 0: none left)
+    unsigned parity = 0;  // bit k: phase of bar[k]
+    int cur = 0;          // sample buffer of the current tile
+    int b = -1, ti = 0;   // current tile: item and tile of the item (b < 0: none left)
     bool fetched = false;
     if ((long)blockIdx.x < total_tiles) {
         b = (int)(blockIdx.x / (unsigned)tiles_per_item);
         ti = (int)(blockIdx.x - (unsigned)b * (unsigned)tiles_per_item);
         if (interior(ti)) {
             if (threadIdx.x < 32) {
-                issue_bulk(b, ti);
-                if (threadIdx.x == 0) mbar_wait(&bar, parity);
+                issue_bulk(b, ti, 0);
+                if (threadIdx.x == 0) mbar_wait(&bar[0], 0);
             }
             parity ^= 1;
             fetched = true;
@@ -252,6 +282,10 @@ __global__ void __launch_bounds__(GROUPS* kRadix) __maxnreg__(stft_max_regs(GROU
         }
     }
     while (b >= 0) {
+        float* sig = sig0 + cur * kSigStride;
+        bool wait_next = false;  // warp 0: a bulk load is in flight
+        // DEPTH 2: the other buffer was released by the previous tile's phase 1 (two barriers ago)
+        if (DEPTH == 2 && threadIdx.x < 32) wait_next = plan_and_issue(cur ^ 1);
         if (!fetched) {
             stage_tile<GROUPS>(sig, wav, L, b, ti, aligned16 != 0, fg);
             cp_async_commit();
@@ -266,33 +300,16 @@ __global__ void __launch_bounds__(GROUPS* kRadix) __maxnreg__(stft_max_regs(GROU
         } else {
             stft_phase1_tab(sig, sig_frame_off(2 * g), sig_frame_off(2 * g + 1), wtab, twp, g, r, xbuf);
         }
-        __syncthreads();  // the transpose is complete and sig is free: the next tile's samples may land already,
-                          // under the shadow of phase 2 and the stores
-        bool wait_next = false;  // warp 0: a bulk load is in flight
-        if (threadIdx.x < 32) {
-            if (threadIdx.x == 0) {
-                int nb = -1, nti = 0;
-                const unsigned long long nxt = (unsigned long long)gridDim.x + nxt_raw;
-                if (nxt < (unsigned long long)total_tiles) {  // total_tiles < 2^31 (checked at launch): 32-bit division
-                    nb = (int)((unsigned)nxt / (unsigned)tiles_per_item);
-                    nti = (int)((unsigned)nxt - (unsigned)nb * (unsigned)tiles_per_item);
-                    wait_next = interior(nti);
-                }
-                s_next_b = nb;  // read by everybody after the barrier at the end of the tile
-                s_next_ti = nti;
-                s_next_fetched = wait_next;
-                nxt_raw = atomicAdd(tile_ctr, 1ull);  // used one iteration from now
-            }
-            __syncwarp();  // lane 0's shared-memory writes are visible to its warp
-            wait_next = s_next_fetched != 0;
-            if (wait_next) issue_bulk(s_next_b, s_next_ti);
+        __syncthreads();  // the transpose is complete and sig is free (DEPTH 1: the next tile's samples may land
+                          // already, under the shadow of phase 2 and the stores)
+        if (DEPTH == 1 && threadIdx.x < 32) wait_next = plan_and_issue(0);
+        if (threadIdx.x == 0) {  // for everybody, read after the barrier at the end of the tile
+            s_next_b = s_plan_b;
+            s_next_ti = s_plan_ti;
+            s_next_fetched = s_plan_fetched;
         }
         float2 v[20];
         stft_phase2_load(xbuf, g, r, v);  // slot r plays role pair_role(r) from here on
-#if defined(SD_STFT_BARRIER_EARLY)
-        __syncthreads();  // every phase-2 load of the transpose buffer is issued and consumed (dft20 ran): the next
-                          // tile's phase 1 may overwrite it; the next tile's coordinates are visible
-#endif
 
         // The real-pair split: Z[400 - k] lives in the adjacent lane (fft400.cuh), so the second exchange is a
         // shuffle -- no shared-memory round trip and no block barrier around it (two barriers per tile instead of four).
@@ -300,23 +317,15 @@ __global__ void __launch_bounds__(GROUPS* kRadix) __maxnreg__(stft_max_regs(GROU
         float* rowA = tA < T ? out + ((size_t)b * T + tA) * (kBins * 2) : dump;  // frames past the item's end: scratch row
         float* rowB = tA + 1 < T ? out + ((size_t)b * T + tA + 1) * (kBins * 2) : dump;
         stft_split_store_pair(v, r, rowA, rowB, pair_lane);
-#if defined(SD_STFT_BARRIER_EARLY)
-        b = s_next_b;  // (rewritten only after the next tile's first barrier)
-        ti = s_next_ti;
-        fetched = s_next_fetched != 0;
-        if (fetched) {  // every thread checks the arrival itself: the samples were requested a whole phase ago
-            mbar_wait(&bar, parity);
-            parity ^= 1;
-        }
-#else
-        if (wait_next && threadIdx.x == 0) mbar_wait(&bar, parity);  // the next tile's samples have landed
+        const int nk = DEPTH == 2 ? cur ^ 1 : 0;  // buffer (and mbarrier) of the next tile
+        if (wait_next && threadIdx.x == 0) mbar_wait(&bar[nk], (parity >> nk) & 1u);  // its samples have landed
         __syncthreads();  // every phase-2 load of the transpose buffer is done: the next tile's phase 1 may overwrite
                           // it; the next tile's coordinates and its landed samples are visible to everybody
         b = s_next_b;  // (rewritten only after the next tile's first barrier)
         ti = s_next_ti;
         fetched = s_next_fetched != 0;
-        if (fetched) parity ^= 1;
-#endif
+        if (fetched) parity ^= 1u << nk;
+        cur = nk;
     }
     // the last CTA to leave zeroes the counters for the next launch on this context (launches of a context are
     // stream-ordered; contexts do not share counters)
@@ -395,16 +404,18 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
         const long s0 = (long)ti * Cfg::kTileFrames * kHop - fg.lead;
         return aligned16 && s0 >= 0 && s0 + Cfg::kSigFloats <= L;
     };
-    auto issue_bulk = [&](long tile) {
+    auto issue_bulk = [&](long tile) {  // all lanes of warp 0: lane j copies hop segment j (see stft400_kernel)
+        const int lane = (int)threadIdx.x;
         const int b = (int)(tile / tiles_per_item);
         const int ti = (int)(tile - (long)b * tiles_per_item);
         const long s0 = (long)ti * Cfg::kTileFrames * kHop - fg.lead;
         const float* src = wav + (size_t)b * L + s0;
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        mbar_expect_tx(&bar, Cfg::kSigFloats * sizeof(float));
-#pragma unroll 1
-        for (int j = 0; j < Cfg::kSigFloats; j += kHop) {
+        if (lane == 0) mbar_expect_tx(&bar, Cfg::kSigFloats * sizeof(float));
+        __syncwarp();
+        const int j = lane * kHop;
+        if (j < Cfg::kSigFloats) {
             const int n = (Cfg::kSigFloats - j) < kHop ? (Cfg::kSigFloats - j) : kHop;
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
             bulk_g2s(sig + sig_pos(j), src + j, n * sizeof(float), &bar);
         }
     };
@@ -416,9 +427,9 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     long tile = blockIdx.x;
     bool fetched = false;
     if (tile < total_tiles && interior(tile)) {
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < 32) {
             issue_bulk(tile);
-            mbar_wait(&bar, parity);
+            if (threadIdx.x == 0) mbar_wait(&bar, parity);
         }
         parity ^= 1;
         fetched = true;
@@ -442,7 +453,7 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
         __syncthreads();  // the transpose is complete and sig is free: the next tile's samples may land from here on
         const long next = tile + gridDim.x;
         fetched = next < total_tiles && interior(next);
-        if (fetched && threadIdx.x == 0) issue_bulk(next);
+        if (fetched && threadIdx.x < 32) issue_bulk(next);
         float2 v[20];
         stft_phase2_load(xbuf, g, r, v);  // slot r plays role pair_role(r) from here on
         __syncthreads();  // xbuf is dead from here: it receives the power spectra
@@ -627,11 +638,12 @@ static int frame_geometry(const sd_stft_params* p, int L, FrameGeom* fg) {
 }
 static bool kaldi_conditioning(const sd_stft_params* p) { return p->preemph != 0.f || p->remove_dc_offset != 0; }
 
-template <int GROUPS, int MINB, bool KALDI, bool HAMMING>
+template <int GROUPS, int MINB, bool KALDI, bool HAMMING, int DEPTH = 1>
 static int launch_cfg(sd_ctx* ctx, const float* d_wav, int B, int L, int T, float* d_out, FrameGeom fg, KaldiArgs ka) {
     using Cfg = StftCfg<GROUPS>;
-    const size_t smem = HAMMING ? Cfg::kSmemBytesStftNoWindow : Cfg::kSmemBytesStft;
-    const int blocks_per_sm = kernel_setup(ctx, stft400_kernel<GROUPS, MINB, KALDI, HAMMING>, (int)smem, Cfg::kThreads, smem);
+    static_assert(DEPTH == 1 || HAMMING, "two sample buffers only in the register-window build");
+    const size_t smem = DEPTH == 2 ? Cfg::kSmemBytesStftNoWindow2 : HAMMING ? Cfg::kSmemBytesStftNoWindow : Cfg::kSmemBytesStft;
+    const int blocks_per_sm = kernel_setup(ctx, stft400_kernel<GROUPS, MINB, KALDI, HAMMING, DEPTH>, (int)smem, Cfg::kThreads, smem);
     if (blocks_per_sm < 0) return SD_ERR_CUDA;
     const int tiles_per_item = (T + Cfg::kTileFrames - 1) / Cfg::kTileFrames;
     const long total = (long)B * tiles_per_item;
@@ -641,7 +653,7 @@ static int launch_cfg(sd_ctx* ctx, const float* d_wav, int B, int L, int T, floa
     long grid = (long)ctx->num_sms * blocks_per_sm * (ctx->stft_waves > 1 ? ctx->stft_waves : 1);
     if (grid > total) grid = total;
     const int aligned = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_wav) & 15) == 0);
-    stft400_kernel<GROUPS, MINB, KALDI, HAMMING><<<(unsigned)grid, Cfg::kThreads, smem, ctx->stream>>>(
+    stft400_kernel<GROUPS, MINB, KALDI, HAMMING, DEPTH><<<(unsigned)grid, Cfg::kThreads, smem, ctx->stream>>>(
         d_wav, d_out, L, T, tiles_per_item, total, ctx->d_window, reinterpret_cast<const float2*>(ctx->d_twiddle),
         aligned, fg, ka, ctx->d_stats + 8, reinterpret_cast<float*>(ctx->d_stats + 16));
     SD_LAUNCH_CHECK(ctx);
@@ -663,21 +675,24 @@ int stft_launch(sd_ctx* ctx, const float* d_wav, int B, int L, const sd_stft_par
     if (T < 1) return ctx->fail(SD_ERR_INVALID, "sd_stft: %d samples give no frame in this frame_mode", L);
     if (fg.reflect && L < kNfft) return ctx->fail(SD_ERR_INVALID, "sd_stft: reflection needs at least n_fft samples");
     const KaldiArgs ka{p->preemph, p->remove_dc_offset};
-    // stft_variant (tuning hook): 0 = the reference's Hamming window computed in registers, five CTAs per SM (72
-    // registers, 24 bytes of spills: 0.773 ms per 1 773-item launch against 0.786 ms with four CTAs at 96 registers);
-    // 1 = window table, 3 CTAs/SM; 2 = window table, 4 CTAs/SM; 4 = register window, 4 CTAs/SM; 5 = register window,
-    // 8-frame tiles in 80-thread CTAs
+    // stft_variant (tuning hook; 1 773 items x 160 000 samples, profiles/r02_stft_v12.log): 0 = the reference's Hamming
+    // window computed in registers, four CTAs per SM at 96 registers, one sample buffer (0.747 ms); 3 = five CTAs per SM
+    // (80 registers, 8 bytes of spills: 0.767 ms); 6 = two sample buffers, the next tile's load issued a whole tile
+    // ahead (0.805 ms: warp 0 issues it before its own phase 1 and everybody waits for that warp); 5 = 8-frame tiles in
+    // 80-thread CTAs (0.786 ms); 1 = window table, 3 CTAs/SM; 2 = window table, 4 CTAs/SM
     const bool hamming = p->window_kind == SD_WINDOW_HAMMING_PERIODIC && ctx->stft_variant != 2 && ctx->stft_variant != 1;
     if (kaldi_conditioning(p))
         rc = launch_cfg<8, 3, true, false>(ctx, d_wav, B, L, T, d_out, fg, ka);
     else if (ctx->stft_variant == 1)
         rc = launch_cfg<8, 3, false, false>(ctx, d_wav, B, L, T, d_out, fg, ka);
-    else if (hamming && ctx->stft_variant == 4)
-        rc = launch_cfg<8, 4, false, true>(ctx, d_wav, B, L, T, d_out, fg, ka);
+    else if (hamming && ctx->stft_variant == 6)
+        rc = launch_cfg<8, 4, false, true, 2>(ctx, d_wav, B, L, T, d_out, fg, ka);
+    else if (hamming && ctx->stft_variant == 3)
+        rc = launch_cfg<8, 5, false, true>(ctx, d_wav, B, L, T, d_out, fg, ka);
     else if (hamming && ctx->stft_variant == 5)
         rc = launch_cfg<4, 9, false, true>(ctx, d_wav, B, L, T, d_out, fg, ka);
     else if (hamming)
-        rc = launch_cfg<8, 5, false, true>(ctx, d_wav, B, L, T, d_out, fg, ka);
+        rc = launch_cfg<8, 4, false, true>(ctx, d_wav, B, L, T, d_out, fg, ka);
     else
         rc = launch_cfg<8, 4, false, false>(ctx, d_wav, B, L, T, d_out, fg, ka);
     if (rc) return rc;
