@@ -1,0 +1,11 @@
+#!/bin/bash
+# 8 GPUs of one box: the bench as the driver launches it
+cd "$GRAFT_REPO_ROOT" || exit 1
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/r02_bench_v10_8gpu.json 2> gpurun_out/r02_bench_v10_8gpu.err
+tail -3 gpurun_out/r02_bench_v10_8gpu.err
+python -c "
+import json
+for l in open('gpurun_out/r02_bench_v10_8gpu.json'):
+    if l.startswith('{'):
+        d=json.loads(l); print(round(d['value']), round(d['ms_per_step'],2), d['n_gpus'], 'e2e', round(d['e2e']['value']), d['config']['host_wait'], d['config']['batch_config'])
+"
