@@ -39,6 +39,24 @@ check("stft kaldi", np.abs(kst[1] - O.kaldi_stft(wav[1], snip_edges=False)).max(
 kfb = ctx.fbank(wav, params=ctx.fbank_kaldi_params(snip_edges=True))
 check("fbank kaldi", np.abs(kfb[0] - O.kaldi_fbank(wav[0], 80, snip_edges=True))[O.kaldi_fbank(wav[0], 80, snip_edges=True) > -8].max() < 1e-3)
 
+# the tile loop proper: more tiles than resident CTAs, so that the dynamic hand-out (global counter, next-tile
+# coordinates passed through shared memory behind the end-of-tile barrier), the pair-lane exchange and the bulk-copy
+# pipeline run for several rounds per CTA; every build of the kernel (SD_OPT_STFT_VARIANT)
+big = synth.fbank_items(5, 12, 160000)
+want = o.stft(big)
+for variant in (0, 3, 5, 6, 2):
+    ctx.set_option(3, variant)
+    got = ctx.stft(big)
+    check("stft 12 x 160000, variant %d" % variant, np.abs(got - want).max() < 1e-4)
+    got = ctx.stft(big)  # second launch: the counter was reset by the last CTA of the first
+    check("stft again, variant %d" % variant, np.abs(got - want).max() < 1e-4)
+ctx.set_option(3, 0)
+fb = ctx.fbank(big[:6], np.ones(6, np.float32))
+check("fbank 6 x 160000", np.isfinite(fb).all())
+if os.environ.get("SDB_SANITIZE_ONLY") == "frontend":
+    print("ALL OK" if ok else "FAILURES")
+    sys.exit(0 if ok else 1)
+
 # segmentation post-processing
 seg = synth.segmentations(2, 24, 293, 3)
 b = ctx.binarize_swf(seg)
