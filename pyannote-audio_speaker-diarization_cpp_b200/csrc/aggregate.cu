@@ -80,7 +80,65 @@ __global__ void __launch_bounds__(256)
     out[idx] = acc;
 }
 
+// speaker_count in one pass (speakerDiarizer.cpp:1691-1735): trim -> sum over the classes -> aggregate(hamming = false,
+// missing = 0, average) -> np.rint, without the two intermediates.  One thread per output frame walks the covering
+// chunks in increasing order like aggregate_kernel; a chunk's value is sum_k bin[c][j + nl][k] formed k-ascending from
+// 0.0 exactly as the separate trim_sum pass formed it, so every bit of the chain is the unfused one's.
+__global__ void __launch_bounds__(256)
+    speaker_count_kernel(const double* __restrict__ bin, const int* __restrict__ starts, int C, int F, int K, int nl,
+                         int Ft, long NF, double epsilon, int32_t* __restrict__ out) {
+    const long f = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= NF) return;
+    int lo = 0, hi = C;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((long)starts[mid] + Ft > f)
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    double acc = 0.0, cnt = 0.0, msk = 0.0;
+    for (int i = lo; i < C; ++i) {
+        const long s = starts[i];
+        if (s > f) break;
+        const int j = (int)(f - s);
+        const double* p = bin + ((size_t)i * F + (size_t)(j + nl)) * K;
+        double v = 0.0;
+        for (int k = 0; k < K; ++k) v = __dadd_rn(v, p[k]);  // speakerDiarizer.cpp:1701-1714
+        double m = 1.0;
+        if (isnan(v)) {
+            m = 0.0;
+            v = 0.0;
+        }
+        acc = __dadd_rn(acc, __dmul_rn(v, m));
+        cnt = __dadd_rn(cnt, m);
+        if (m > msk) msk = m;
+    }
+    acc = __ddiv_rn(acc, cnt > epsilon ? cnt : epsilon);
+    if (fabs(msk) < DBL_EPSILON) acc = 0.0;
+    out[f] = np_rint_impl(acc);
+}
+
 int upload_small(sd_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+
+// tw: the trimmed chunk window (its frames are the Ft kept frames of every chunk)
+int speaker_count_launch(sd_ctx* ctx, const double* d_bin, int C, int F, int K, int nl, int Ft, const sd_window* tw,
+                         const sd_window* frames, int64_t NF, int32_t* d_out) {
+    std::vector<int> starts((size_t)C);
+    double start = tw->start;
+    for (int i = 0; i < C; ++i) {  // as aggregate_launch: running sum of the chunk step, closest frame
+        starts[i] = (int)closest_frame_host(tw->start, frames->step, frames->duration, start);
+        start += tw->step;
+    }
+    int* d_starts = (int*)ctx->scratch(BUF_AGG_STARTS, sizeof(int) * (size_t)C + 8);
+    if (!d_starts) return SD_ERR_NOMEM;
+    const int rc = upload_small(ctx, d_starts, starts.data(), sizeof(int) * (size_t)C);
+    if (rc) return rc;
+    speaker_count_kernel<<<(unsigned)((NF + 255) / 256), 256, 0, ctx->stream>>>(d_bin, d_starts, C, F, K, nl, Ft, (long)NF,
+                                                                            DBL_EPSILON, d_out);
+    SD_LAUNCH_CHECK(ctx);
+    return SD_OK;
+}
 
 int aggregate_launch(sd_ctx* ctx, const double* d_scores, int C, int F, int K, const sd_window* chunks,
                      const sd_window* frames, int hamming, double missing, int skip_average, double epsilon,

@@ -658,15 +658,10 @@ int sd_speaker_count_dev(sd_ctx* ctx, const double* d_binarized, int C, int F, i
     if (n_out) *n_out = NF;
     if (NF > cap) return ctx->fail(SD_ERR_CAPACITY, "sd_speaker_count: need %lld entries, have %lld", (long long)NF,
                                    (long long)cap);
-    double* d_sum = (double*)ctx->scratch(BUF_CNT_TMP, sizeof(double) * (size_t)C * Ft);
-    double* d_agg = (double*)ctx->scratch(BUF_CNT_OUT, sizeof(double) * (size_t)NF);
-    if (!d_sum || !d_agg) return SD_ERR_NOMEM;
-    int rc = trim_sum_launch(ctx, d_binarized, C, F, K, nl, Ft, d_sum);
-    if (rc) return rc;
-    // aggregate(sum_trimmed, trimmed_frames, pre_frame, hamming=false, missing=0.0, skip_average=false), SD:1719
-    rc = aggregate_launch(ctx, d_sum, C, Ft, 1, &tw, frames, 0, 0.0, 0, DBL_EPSILON, d_agg, NF, nullptr, nullptr);
-    if (rc) return rc;
-    rc = rint_launch(ctx, d_agg, NF, d_out);  // np.rint, SD:1731-1735
+    // one kernel: sum over the classes of the trimmed frames -> aggregate(hamming=false, missing=0.0,
+    // skip_average=false) (SD:1719) -> np.rint (SD:1731-1735); the stage-dump entry points still run the three steps
+    // separately (stages.cu)
+    const int rc = speaker_count_launch(ctx, d_binarized, C, F, K, nl, Ft, &tw, frames, NF, d_out);
     if (rc) return rc;
     fill_post(&tw, frames, count_frames);
     return SD_OK;

@@ -196,6 +196,8 @@ int fbank_launch(sd_ctx* ctx, const float* d_wav, int B, int L, const float* d_l
 int aggregate_launch(sd_ctx* ctx, const double* d_scores, int C, int F, int K, const sd_window* chunks,
                      const sd_window* frames, int hamming, double missing, int skip_average, double epsilon,
                      double* d_out, int64_t NF, double* d_count, double* d_mask);
+int speaker_count_launch(sd_ctx* ctx, const double* d_bin, int C, int F, int K, int nl, int Ft, const sd_window* tw,
+                         const sd_window* frames, int64_t NF, int32_t* d_out);
 int binarize_launch(sd_ctx* ctx, const float* d_scores, int C, int F, int K, double onset, int initial_state,
                     double* d_out);
 int binarize_rows_launch(sd_ctx* ctx, const double* d_scores, int R, int F, double onset, int initial_state,
