@@ -82,6 +82,7 @@ struct sd_ctx {
     float* d_twiddle = nullptr;    // [20][20] float2, tw[r][k1] = exp(-2 pi i r k1 / 400)
     float* d_mel = nullptr;        // mel matrix [201][n_mels]
     int mel_key = 0;
+    int mel_parts = 0;             // d_mel holds the (frame, part) table (mel_table.h) instead of the per-filter one
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
     int* d_status = nullptr;       // device-side status word (zero-magnitude etc.)

@@ -12,6 +12,7 @@
 // 8-byte stores that cover whole 1608-byte output rows.
 #include "common.cuh"
 #include "fft400.cuh"
+#include "mel_table.h"
 
 #include <algorithm>
 #include <cmath>
@@ -345,12 +346,6 @@ __global__ void __launch_bounds__(GROUPS* kRadix) __maxnreg__(stft_max_regs(GROU
 // stores, and the utterance maximum (needed by the top_db clamp) through one atomicMax per warp.
 // Spec: embeddings/threeModel.py:212-221 (spectral_magnitude -> Filterbank(n_mels=80) -> MyNormalization);
 // parity unpinned (speechbrain 0.5.14 is not vendored) -- checked against oracle/sd_oracle.c only.
-struct MelTable {       // device copy lives in ctx->d_mel
-    int lo[128];        // first bin of filter m
-    int cnt[128];       // number of bins with non-zero weight
-    int off[128];       // offset of its weights in w[]
-    float w[1024];      // packed non-zero weights
-};
 
 __device__ __forceinline__ int float_order_key(float v) {  // monotone float -> int map for atomicMax
     const int i = __float_as_int(v);
@@ -367,11 +362,21 @@ __host__ __device__ __forceinline__ float float_from_order_key(int k) {
 #endif
 }
 
-template <int GROUPS, int MINB, bool KALDI, bool HAMMING>
+template <bool PARTS>
+struct MelSmem {
+    typedef MelTable type;
+};
+template <>
+struct MelSmem<true> {
+    typedef MelParts type;
+};
+
+// PARTS: the mel projection by (frame, 20-bin part) threads (mel_table.h) instead of one filter per thread
+template <int GROUPS, int MINB, bool KALDI, bool HAMMING, bool PARTS>
 __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     fbank400_kernel(const float* __restrict__ wav, float* __restrict__ out, int L, int T, int tiles_per_item,
                     long total_tiles, const float* __restrict__ window, const float2* __restrict__ twiddle,
-                    int aligned16, const MelTable* __restrict__ mel, int n_mels, float amin, float log_scale,
+                    int aligned16, const void* __restrict__ mel, int n_mels, float amin, float log_scale,
                     int* __restrict__ item_max, FrameGeom fg, KaldiArgs ka) {
     using Cfg = StftCfg<GROUPS>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -381,7 +386,8 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     float* sig = reinterpret_cast<float*>(wtab + kNfft);
     float* pw = reinterpret_cast<float*>(xbuf);  // power spectra [frame][201], aliases the transpose buffer
     __shared__ __align__(8) uint64_t bar;
-    __shared__ MelTable smel;
+    typedef typename MelSmem<PARTS>::type MelT;
+    __shared__ MelT smel;
     __shared__ float2 dc_part[KALDI ? GROUPS * kRadix : 1];
 
     const int g = threadIdx.x / kRadix;
@@ -390,7 +396,7 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
     sincospif((float)r * (1.0f / 200.0f), &ham_s, &ham_c);
     for (int i = threadIdx.x; i < kNfft; i += Cfg::kThreads) wtab[i] = wtab_make(0.5f * window[i]);
     for (int e = threadIdx.x; e < kTwTableUnits; e += Cfg::kThreads) twT[e] = twiddle[tw_table_source(e)];
-    for (int i = threadIdx.x; i < (int)(sizeof(MelTable) / 4); i += Cfg::kThreads)
+    for (int i = threadIdx.x; i < (int)(sizeof(MelT) / 4); i += Cfg::kThreads)
         reinterpret_cast<int*>(&smel)[i] = reinterpret_cast<const int*>(mel)[i];
     const float2* twp = twT + tw_thread_offset(threadIdx.x);
     if (threadIdx.x == 0) {
@@ -472,6 +478,59 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
         const int t0 = ti * Cfg::kTileFrames;
         float vmax = -INFINITY;
         constexpr int kFramesPerPass = Cfg::kThreads / 80 > 0 ? Cfg::kThreads / 80 : 1;  // frame slots per pass
+        if constexpr (PARTS) {
+            // Thread = (frame f, 20-bin part q): the part's bins are read once (lanes of a half-warp: 16 frames, stride
+            // 201 = 9 mod 32 banks; the other half-warp works 80 bins = 16 banks further on), every table entry is a
+            // broadcast, and the two accumulators are flushed to the filters' columns of mo[f][.] as the filters change
+            // (mel_table.h).  40 multiply-adds per thread whatever the part -- the per-filter form has 8 to 104.
+            static_assert(!PARTS || Cfg::kThreads == 16 * kMelParts, "one thread per (frame, part)");
+            float* mo = pw + Cfg::kTileFrames * kBins;  // [frame][n_mels + extra columns], odd row stride
+            const int RS = n_mels + kMelExtraCols + 1;
+            {
+                const int f = (int)(threadIdx.x & 15), h = (int)(threadIdx.x >> 4);
+                const int q = (h >> 1) < 4 ? (h >> 1) + 4 * (h & 1) : 8 + (h & 1);
+                const MelEntry* tab = smel.e[q];
+                const float* prow = pw + f * kBins + q * kMelPartBins;
+                float* orow = mo + f * RS;
+                float accE = 0.f, accO = 0.f;
+#pragma unroll
+                for (int i = 0; i < kMelEntries - 1; ++i) {
+                    const int4 en = *reinterpret_cast<const int4*>(tab + i);  // (wE, wO, fE, fO): one 16-byte broadcast
+                    if (en.z >= 0) {
+                        orow[en.z] = accE;
+                        accE = 0.f;
+                    }
+                    if (en.w >= 0) {
+                        orow[en.w] = accO;
+                        accO = 0.f;
+                    }
+                    const float p = prow[i];  // the 21st entry of parts 0..8 has zero weights; the bin exists
+                    accE = fmaf(__int_as_float(en.x), p, accE);
+                    accO = fmaf(__int_as_float(en.y), p, accO);
+                }
+                const int4 en = *reinterpret_cast<const int4*>(tab + kMelEntries - 1);
+                if (en.z >= 0) orow[en.z] = accE;
+                if (en.w >= 0) orow[en.w] = accO;
+            }
+            __syncthreads();  // every partial sum is in mo
+            for (int m0 = 0; m0 < n_mels; m0 += 80) {
+                const int m = m0 + (int)(threadIdx.x % 80), slot = threadIdx.x / 80;
+                if (m < n_mels && slot < kFramesPerPass) {
+                    const int has = smel.has[m], ex = smel.extra[m];
+#pragma unroll
+                    for (int j = 0; j < Cfg::kTileFrames / kFramesPerPass; ++j) {
+                        const int f = slot + j * kFramesPerPass;
+                        float a = has ? mo[f * RS + m] : 0.f;
+                        if (ex >= 0) a += mo[f * RS + n_mels + ex];
+                        if (t0 + f < T) {
+                            const float db = log_scale * __log2f(fmaxf(a, amin));
+                            out[((size_t)b * T + t0 + f) * n_mels + m] = db;
+                            vmax = fmaxf(vmax, db);
+                        }
+                    }
+                }
+            }
+        } else {
         for (int m0 = 0; m0 < n_mels; m0 += 80) {
             int m = m0 + (int)(threadIdx.x % 80), slot = threadIdx.x / 80;
             if (Cfg::kThreads == 160) {
@@ -504,6 +563,7 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
                 }
             }
         }
+        }  // per-filter projection
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
         if ((threadIdx.x & 31) == 0 && vmax > -INFINITY) atomicMax(item_max + b, float_order_key(vmax));
@@ -704,79 +764,6 @@ int stft_launch(sd_ctx* ctx, const float* d_wav, int B, int L, const sd_stft_par
     return SD_OK;
 }
 
-// speechbrain 0.5.14 Filterbank (triangular, fp32 arithmetic like the torch module): mel points
-// linspace(mel(f_min), mel(f_max), n_mels + 2); centre = hz[1..n_mels]; band = hz[m+1] - hz[m] for both slopes.
-static int build_mel_table(const sd_fbank_params* p, MelTable& t) {
-    const int n_bins = kBins, n_mels = p->n_mels, np = n_mels + 2;
-    if (n_mels < 1 || n_mels > 128) return SD_ERR_UNSUPPORTED;
-    std::vector<float> hz(np);
-    const float mlo = (float)(2595.0 * std::log10(1.0 + (double)p->f_min / 700.0));
-    const float mhi = (float)(2595.0 * std::log10(1.0 + (double)p->f_max / 700.0));
-    for (int i = 0; i < np; ++i) {
-        const float mel = mlo + (mhi - mlo) * (float)i / (float)(np - 1);
-        hz[i] = 700.0f * (std::pow(10.0f, mel / 2595.0f) - 1.0f);
-    }
-    int used = 0;
-    for (int m = 0; m < n_mels; ++m) {
-        const float fc = hz[m + 1], band = hz[m + 1] - hz[m];
-        int lo = -1, hi = -1;
-        std::vector<float> wts(n_bins);
-        for (int f = 0; f < n_bins; ++f) {
-            const float freq = (float)(p->sample_rate / 2) * (float)f / (float)(n_bins - 1);
-            const float slope = (freq - fc) / band;
-            const float l = slope + 1.0f, r = -slope + 1.0f;
-            const float v = std::max(0.0f, std::min(l, r));
-            wts[f] = v;
-            if (v > 0.0f) {
-                if (lo < 0) lo = f;
-                hi = f;
-            }
-        }
-        t.lo[m] = lo < 0 ? 0 : lo;
-        t.cnt[m] = lo < 0 ? 0 : hi - lo + 1;
-        t.off[m] = used;
-        if (used + t.cnt[m] > 1024) return SD_ERR_UNSUPPORTED;
-        for (int i = 0; i < t.cnt[m]; ++i) t.w[used + i] = wts[t.lo[m] + i];
-        used += t.cnt[m];
-    }
-    return SD_OK;
-}
-
-// Kaldi mel banks (kaldi::MelBanks, no VTLN; torchaudio.compliance.kaldi.get_mel_banks): n_mels triangles equally
-// spaced on mel = 1127 ln(1 + f/700) between f_min and f_max (0 = Nyquist), evaluated at the centres of the n_fft/2
-// lower FFT bins (the Nyquist bin gets no weight), slopes linear in mel.
-static int build_mel_table_kaldi(const sd_fbank_params* p, MelTable& t) {
-    const int n_mels = p->n_mels, n_fft_bins = kNfft / 2;
-    if (n_mels < 1 || n_mels > 128) return SD_ERR_UNSUPPORTED;
-    auto mel = [](double f) { return 1127.0 * std::log(1.0 + f / 700.0); };
-    const double nyquist = 0.5 * p->sample_rate, bin_width = (double)p->sample_rate / kNfft;
-    const double high = p->f_max <= 0.f ? nyquist + p->f_max : (double)p->f_max;
-    const double mel_lo = mel(p->f_min), mel_hi = mel(high), delta = (mel_hi - mel_lo) / (n_mels + 1);
-    int used = 0;
-    for (int m = 0; m < n_mels; ++m) {
-        const double left = mel_lo + m * delta, center = left + delta, right = center + delta;
-        int lo = -1, hi = -1;
-        std::vector<float> wts(n_fft_bins, 0.f);
-        for (int i = 0; i < n_fft_bins; ++i) {
-            const double mf = mel(bin_width * i);
-            const double up = (mf - left) / (center - left), down = (right - mf) / (right - center);
-            const double v = std::max(0.0, std::min(up, down));
-            wts[i] = (float)v;
-            if (v > 0.0) {
-                if (lo < 0) lo = i;
-                hi = i;
-            }
-        }
-        t.lo[m] = lo < 0 ? 0 : lo;
-        t.cnt[m] = lo < 0 ? 0 : hi - lo + 1;
-        t.off[m] = used;
-        if (used + t.cnt[m] > 1024) return SD_ERR_UNSUPPORTED;
-        for (int i = 0; i < t.cnt[m]; ++i) t.w[used + i] = wts[t.lo[m] + i];
-        used += t.cnt[m];
-    }
-    return SD_OK;
-}
-
 int fbank_launch(sd_ctx* ctx, const float* d_wav, int B, int L, const float* d_lens, const sd_fbank_params* p,
                  float* d_out) {
     const sd_stft_params* sp = &p->stft;
@@ -786,15 +773,30 @@ int fbank_launch(sd_ctx* ctx, const float* d_wav, int B, int L, const float* d_l
         return ctx->fail(SD_ERR_INVALID, "sd_fbank: unknown frame_mode %d", sp->frame_mode);
     int rc = ensure_tables(ctx, sp);
     if (rc) return rc;
-    const int key = p->n_mels * 1000003 + (int)p->f_min * 7919 + (int)p->f_max + p->sample_rate * 31 + p->mel_kind * 104729;
+    // SD_OPT_STFT_VARIANT 8 (tuning): the mel projection by (frame, 20-bin part) threads (mel_table.h).  Conflict-free
+    // (7 M instead of 18 M bank-conflict wavefronts per 600 items) but not faster: its 16-byte table broadcasts cost as
+    // many wavefronts as the conflicts they remove and it needs one more block barrier -- 1.477 ms against 1.319 ms
+    // for the per-filter form, which therefore stays the default.
+    const bool want_parts = ctx->stft_variant == 8;
+    const int key = p->n_mels * 1000003 + (int)p->f_min * 7919 + (int)p->f_max + p->sample_rate * 31 + p->mel_kind * 104729 +
+                    (want_parts ? 15485863 : 0);
     if (!ctx->d_mel || ctx->mel_key != key) {
         MelTable t;
         std::memset(&t, 0, sizeof(t));
         rc = p->mel_kind == 1 ? build_mel_table_kaldi(p, t) : build_mel_table(p, t);
         if (rc) return ctx->fail(rc, "sd_fbank: unsupported mel configuration (n_mels=%d)", p->n_mels);
-        if (!ctx->d_mel) SD_CUDA(ctx, cudaMalloc(&ctx->d_mel, sizeof(MelTable)));
+        static_assert(sizeof(MelParts) <= 2 * sizeof(MelTable), "d_mel holds either table");
+        if (!ctx->d_mel) SD_CUDA(ctx, cudaMalloc(&ctx->d_mel, 2 * sizeof(MelTable)));
         SD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        SD_CUDA(ctx, cudaMemcpy(ctx->d_mel, &t, sizeof(MelTable), cudaMemcpyHostToDevice));
+        // the (frame, part) form of the projection only on request and when the filterbank has the structure it needs
+        // (mel_table.h: true for the 80-filter speechbrain and Kaldi banks), else one filter per thread
+        std::vector<MelParts> mp(1);
+        ctx->mel_parts = want_parts && build_mel_parts(t, p->n_mels, mp[0]) == SD_OK && 16 * (p->n_mels + kMelExtraCols + 1) * sizeof(float) +
+                                 16 * kBins * sizeof(float) <= 8 * kGroupStride * sizeof(float2);
+        if (ctx->mel_parts)
+            SD_CUDA(ctx, cudaMemcpy(ctx->d_mel, &mp[0], sizeof(MelParts), cudaMemcpyHostToDevice));
+        else
+            SD_CUDA(ctx, cudaMemcpy(ctx->d_mel, &t, sizeof(MelTable), cudaMemcpyHostToDevice));
         ctx->mel_key = key;
     }
     FrameGeom fg;
@@ -822,12 +824,19 @@ int fbank_launch(sd_ctx* ctx, const float* d_wav, int B, int L, const float* d_l
         const int aligned = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_wav) & 15) == 0);
         kernel<<<(unsigned)grid, Cfg::kThreads, Cfg::kSmemBytes, ctx->stream>>>(
             d_wav, d_out, L, T, tiles_per_item, total, ctx->d_window, reinterpret_cast<const float2*>(ctx->d_twiddle),
-            aligned, reinterpret_cast<const MelTable*>(ctx->d_mel), p->n_mels, p->amin, log_scale, d_max, fg, ka);
+            aligned, ctx->d_mel, p->n_mels, p->amin, log_scale, d_max, fg, ka);
         return SD_OK;
     };
     // 96 registers (4 CTAs per SM) without spills for the plain front-end; the Kaldi conditioning needs 128 (3 per SM)
-    rc = kaldi ? launch(fbank400_kernel<8, 3, true, false>)
-               : hamming ? launch(fbank400_kernel<8, 4, false, true>) : launch(fbank400_kernel<8, 4, false, false>);
+    const bool parts = ctx->mel_parts != 0;  // decided when the table was uploaded (same key)
+    if (parts)
+        rc = kaldi ? launch(fbank400_kernel<8, 3, true, false, true>)
+                   : hamming ? launch(fbank400_kernel<8, 4, false, true, true>)
+                             : launch(fbank400_kernel<8, 4, false, false, true>);
+    else
+        rc = kaldi ? launch(fbank400_kernel<8, 3, true, false, false>)
+                   : hamming ? launch(fbank400_kernel<8, 4, false, true, false>)
+                             : launch(fbank400_kernel<8, 4, false, false, false>);
     if (rc) return rc;
     SD_LAUNCH_CHECK(ctx);
     const int total_e = T * p->n_mels;

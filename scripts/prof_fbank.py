@@ -13,6 +13,8 @@ items = int(sys.argv[1]) if len(sys.argv) > 1 else 1773
 L = 160000
 T = 1 + L // 160
 ctx = pkg.Context(0)
+if len(sys.argv) > 2:
+    ctx.set_option(3, int(sys.argv[2]))  # SD_OPT_STFT_VARIANT: 8 = mel projection by (frame, part) threads
 rng = np.random.default_rng(0)
 wav = (0.1 * rng.standard_normal((items, L))).astype(np.float32)
 d_in = ctx.to_device(wav)

@@ -77,6 +77,17 @@ def test_stft_phase_emulation_on_cpu(tmp_path):
     assert out.returncode == 0, out.stdout
 
 
+def test_mel_projection_emulation_on_cpu(tmp_path):
+    """Replays the fused fbank kernel's mel projection (csrc/mel_table.h: (frame, 20-bin part) threads, even / odd
+    accumulators, flush columns) on the CPU against the plain per-filter sums, for the speechbrain and Kaldi banks."""
+    exe = str(tmp_path / "emulate_mel")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "emulate_mel.cpp"), "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "speechbrain 80" in out.stdout and "UNEXPECTED" not in out.stdout
+
+
 def test_batch_has_no_cpu_fallback(pkg):
     import torch
     if torch.cuda.is_available():

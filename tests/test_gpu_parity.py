@@ -109,6 +109,28 @@ def test_fbank_fused_vs_oracle(ctx, oracle, synth, B, L):
     assert err.max() < 5e-2
 
 
+def test_fbank_part_projection_agrees(pkg, synth):
+    """SD_OPT_STFT_VARIANT 8: the mel projection by (frame, 20-bin part) threads (csrc/mel_table.h) gives the per-filter
+    projection's result up to the order of the fp32 additions (filters that straddle a part boundary are summed in two
+    pieces), reference and Kaldi filterbanks, ragged last tile included."""
+    wav = synth.fbank_items(77, 9, 16000 + 480)
+    lens = np.linspace(1.0, 0.5, 9).astype(np.float32)
+    a, b = pkg.Context(0), pkg.Context(0)
+    try:
+        b.set_option(3, 8)
+        for params in (None, "kaldi"):
+            pa = a.fbank_kaldi_params(snip_edges=True) if params else a.fbank_params()
+            pb = b.fbank_kaldi_params(snip_edges=True) if params else b.fbank_params()
+            pa.mean_norm = pb.mean_norm = 0
+            x, y = a.fbank(wav, lens, pa), b.fbank(wav, lens, pb)
+            assert x.shape == y.shape and np.isfinite(y).all()
+            loud = x > x.max() - 50.0
+            assert np.abs(x - y)[loud].max() < 1e-4 and np.abs(x - y).max() < 1e-2
+    finally:
+        a.close()
+        b.close()
+
+
 def test_fbank_without_mean_norm_and_clamp_floor(ctx, oracle, synth):
     wav = synth.fbank_items(5, 2, 32000)
     wav[1, 4000:] = 0.0  # long digital silence -> clamped at (max - 80 dB)
