@@ -611,7 +611,7 @@ def run_reference(args, rank, world):
         return
     synth = ge.load_synth()
     geo = geometry()
-    wav_items = synth.fbank_items(102, 4, geo["L"])  # only the sampled items are needed
+    wav_items = synth.fbank_items(102, 32, geo["L"])  # the sampled items: 1 as written, 32 for the FFT-only figure (as in the product arm)
     seg = synth.segmentations(1102, geo["C"], geo["F"], geo["S"])
     emb, _ = synth.embeddings(202, geo["C"], geo["S"], geo["D"], n_speakers=4)
     diar = synth.segmentations(2102, geo["C"], geo["F"], geo["Kd"]).astype(np.float64)

@@ -71,7 +71,7 @@ int sd_timer_elapsed_ms(sd_ctx* ctx, int slot, float* ms); /* synchronises on th
 int64_t sd_launch_count(const sd_ctx* ctx);
 /* Options.  SD_OPT_FORCE_EXACT_LINKAGE: always run the heap-driven linkage kernel (normally it only runs when
  * the heap-free kernel meets a tied minimum); results are identical either way. */
-typedef enum sd_option { SD_OPT_FORCE_EXACT_LINKAGE = 1, SD_OPT_LINKAGE_THREADS = 2 /* 0 auto, 512, 1024 */, SD_OPT_STFT_VARIANT = 3 /* tuning */, SD_OPT_LINKAGE_CLUSTER = 4 /* 1 (default): 8-CTA cluster merge loop, 0: one CTA */, SD_OPT_STFT_WAVES = 6 /* CTAs per resident slot of the STFT grid: 1 = persistent CTAs (default), n > 1 = slots are handed back n times per launch */, SD_OPT_LINKAGE_WIDE = 5 /* whole-GPU merge loop (one CTA per SM, cooperative launch, global-memory mailbox): 0 never (default), 1 from 32768 rows, 2 always */ } sd_option;
+typedef enum sd_option { SD_OPT_FORCE_EXACT_LINKAGE = 1, SD_OPT_LINKAGE_THREADS = 2 /* 0 auto, 512, 1024 */, SD_OPT_STFT_VARIANT = 3 /* tuning: other builds of the front-end kernels, results within the same tolerance -- 0 default (register Hamming window, 4 CTAs/SM), 1 / 2 window table at 3 / 4 CTAs/SM, 3 five CTAs/SM, 5 8-frame tiles, 6 two sample buffers, 8 fbank mel projection by (frame, part) threads */, SD_OPT_LINKAGE_CLUSTER = 4 /* 1 (default): 8-CTA cluster merge loop, 0: one CTA */, SD_OPT_STFT_WAVES = 6 /* CTAs per resident slot of the STFT grid: 1 = persistent CTAs (default), n > 1 = slots are handed back n times per launch */, SD_OPT_LINKAGE_WIDE = 5 /* whole-GPU merge loop (one CTA per SM, cooperative launch, global-memory mailbox): 0 never (default), 1 from 32768 rows, 2 always */ } sd_option;
 int sd_ctx_set_option(sd_ctx* ctx, int option, int value);
 /* Diagnostic counters accumulated by the kernels: [0] stale nearest-neighbour revalidations in linkage,
  * [1] heap updates replayed after Lance-Williams sweeps, [2] problems handed from the heap-free linkage kernel to
