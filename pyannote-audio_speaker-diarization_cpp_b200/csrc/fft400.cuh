@@ -209,13 +209,16 @@ SD_HD void stft_phase1(const float* sig, int fa_off, int fb_off, const float (&w
     }
 }
 
-// Padded staging: extra floats are inserted after every kHop samples of the tile, alternately kPadEven and kPadOdd,
-// so frame pair g starts at g * (2*kHop + kPadEven + kPadOdd) = 340 g = 20 g (mod 32) banks: the lanes of the two or
-// three 20-thread groups that share a warp then cover distinct banks -> conflict-free 4-byte reads (a uniform pad
-// would have to be 10 = 2 (mod 4) floats, which breaks the 16-byte alignment the bulk (TMA) copies need; 8 and 12
-// keep every segment 16-byte aligned).  Tiles start at an even frame, so segment parity == frame parity.
-constexpr int kPadEven = 8;    // after an even hop segment
-constexpr int kPadOdd = 12;    // after an odd hop segment
+// Padded staging: 20 extra floats are inserted after every second hop segment of the tile, so frame pair g starts at
+// g * (2*kHop + 20) = 340 g = 20 g (mod 32) banks: the lanes of the two or three 20-thread groups that share a warp
+// then cover distinct banks -> conflict-free 4-byte reads.  An even segment and the odd one after it stay contiguous
+// (320 floats = 1 280 bytes, 16-byte aligned), so a tile is fetched with one bulk (TMA) copy per segment PAIR: nine
+// copies instead of eighteen -- the copy instruction takes its operands from uniform registers, so the lanes of the
+// issuing warp are served one after the other (ELECT loop in SASS) and every copy costs that warp ~9 instructions
+// which the other warps of the CTA wait for at the end-of-tile barrier.  Tiles start at an even frame, so segment
+// parity == frame parity.
+constexpr int kPadEven = 0;    // after an even hop segment
+constexpr int kPadOdd = 20;    // after an odd hop segment
 constexpr int kPairStride = 2 * kHop + kPadEven + kPadOdd;  // floats between the first frames of consecutive pairs
 // padded position of sample j of the tile
 SD_HD constexpr int sig_pos(int j) {

@@ -222,8 +222,9 @@ __global__ void __launch_bounds__(GROUPS* kRadix) __maxnreg__(stft_max_regs(GROU
         return aligned16 && s0 >= 0 && s0 + Cfg::kSigFloats <= L;
     };
     // Bulk (TMA) copies of a tile: lane 0 of warp 0 announces the bytes on the mbarrier, then lane j issues the copy
-    // of hop segment j -- one warp instruction instead of an 18-iteration loop in thread 0, whose warp every other
-    // warp of the CTA would wait for at the end-of-tile barrier.  Call with all lanes of warp 0.
+    // of segment pair j (nine copies; the hardware takes them one lane at a time, see fft400.cuh) instead of a loop in
+    // thread 0, whose warp every other warp of the CTA would wait for at the end-of-tile barrier.  Call with all
+    // lanes of warp 0.
     auto issue_bulk = [&](int b, int ti, int k) {  // into sample buffer k, completing on bar[k]
         const int lane = (int)threadIdx.x;
         const long s0 = (long)ti * Cfg::kTileFrames * kHop - fg.lead;
@@ -231,14 +232,15 @@ __global__ void __launch_bounds__(GROUPS* kRadix) __maxnreg__(stft_max_regs(GROU
         float* sig = sig0 + k * kSigStride;
         if (lane == 0) mbar_expect_tx(&bar[k], Cfg::kSigFloats * sizeof(float));
         __syncwarp();
-        const int j = lane * kHop;
+        const int j = lane * 2 * kHop;  // a pair of hop segments is contiguous in the staged layout (fft400.cuh)
         if (j < Cfg::kSigFloats) {
-            const int n = (Cfg::kSigFloats - j) < kHop ? (Cfg::kSigFloats - j) : kHop;
+            const int n = (Cfg::kSigFloats - j) < 2 * kHop ? (Cfg::kSigFloats - j) : 2 * kHop;
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // earlier generic reads of sig vs async writes
             bulk_g2s(sig + sig_pos(j), src + j, n * sizeof(float), &bar[k]);
         }
     };
-    static_assert((Cfg::kSigFloats + kHop - 1) / kHop <= 32, "one hop segment per lane of warp 0");
+    static_assert(kPadEven == 0, "an even hop segment and the next one must be contiguous in shared memory");
+    static_assert((Cfg::kSigFloats + 2 * kHop - 1) / (2 * kHop) <= 32, "one segment pair per lane of warp 0");
     // warp 0: work out the next tile (thread 0: counter value fetched one tile ago, 32-bit division, interior test),
     // start its bulk load into buffer k, and ask the counter for the tile after it
     auto plan_and_issue = [&](int k) -> bool {
@@ -418,9 +420,9 @@ __global__ void __launch_bounds__(GROUPS* kRadix, MINB)
         const float* src = wav + (size_t)b * L + s0;
         if (lane == 0) mbar_expect_tx(&bar, Cfg::kSigFloats * sizeof(float));
         __syncwarp();
-        const int j = lane * kHop;
+        const int j = lane * 2 * kHop;  // one copy per pair of hop segments (contiguous in the staged layout)
         if (j < Cfg::kSigFloats) {
-            const int n = (Cfg::kSigFloats - j) < kHop ? (Cfg::kSigFloats - j) : kHop;
+            const int n = (Cfg::kSigFloats - j) < 2 * kHop ? (Cfg::kSigFloats - j) : 2 * kHop;
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
             bulk_g2s(sig + sig_pos(j), src + j, n * sizeof(float), &bar);
         }
