@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -95,3 +96,13 @@ def test_batch_has_no_cpu_fallback(pkg):
     with pytest.raises(pkg.SdError) as e:
         pkg.Batch(0, 2)
     assert e.value.code == pkg.SD_ERR_CUDA
+
+
+def test_batch_timeline_script_reads_a_committed_trace():
+    """scripts/prof_batch_timeline.py on a trace written by SDB_BATCH_TRACE on a B200 (profiles/): the analysis the
+    batch scheduling of DESIGN.md section 5 was derived from must keep running."""
+    trace = os.path.join(ROOT, "profiles", "r02_trace_v7_f24.csv")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "prof_batch_timeline.py"), trace],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "workers 24" in out.stdout and "merge loop" in out.stdout and "STFT completions" in out.stdout
